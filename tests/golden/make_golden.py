@@ -1,0 +1,95 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on the seeded
+scenarios of tests/scenarios.py.  Run in the build container only:
+
+    python tests/golden/make_golden.py            # writes tests/golden/<name>.npz
+
+Driver loop = main.py:88-138: one extra observation(), then T x [step(actions_t); env.update()].
+The wall-collision draws of walls.py:28 are taped (ref_harness.py) so the trajectory is a pure function of
+(initial state, action tape, noise tape).  Everything recorded is reference output; nothing here is computed
+by the oracle or the CUDA path.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import ref_harness  # noqa: E402
+from scenarios import GOLDEN_SCENARIOS, make_scenario  # noqa: E402
+
+PER_STEP_ANT_KEYS = ["x", "y", "theta", "prev_x", "prev_y", "holding", "mandibles", "reward_state", "activation"]
+
+
+def cfg_to_json(cfg):
+    c = dict(cfg)
+    c["mask"] = None if cfg["mask"] is None else np.asarray(cfg["mask"]).astype(int).tolist()
+    return json.dumps(c)
+
+
+def run_reference(cfg, init, tape):
+    ref = ref_harness.load_reference()
+    ref_harness.set_diffuse(ref, cfg["diffuse_factor"], cfg["evap_factor"])
+    env, api, objs = ref_harness.build_env(ref, cfg, init)
+    if not init.get("act_bool", True):
+        objs["ants"].activate_all_pheromones(np.asarray(init["activation"], dtype=float))
+    rec = {}
+    obs0, agent_state0, state0 = api.observation()
+    rec["obs0"] = obs0; rec["agent_state0"] = agent_state0; rec["state0"] = state0
+    rec["reward0"] = np.asarray(api.reward.rewards, dtype=float).copy()
+    T = tape["rot"].shape[0]
+    per = {"obs": [], "agent_state": [], "reward": [], "done": [], "post_step": [], "post_update": [],
+           "phero_sum": [], "food_sum": [], "explored_count": [], "anthill_food": [], "rock_centers": []}
+    for t in range(T):
+        rot = None if tape["rot_none"][t] else tape["rot"][t].astype(np.int64)
+        ph = None if tape["ph_none"][t] else tape["ph"][t].astype(np.int64)
+        obs, agent_state, reward, done = api.step(rot, ph)
+        per["obs"].append(obs); per["agent_state"].append(agent_state)
+        per["reward"].append(np.asarray(reward, dtype=float).copy()); per["done"].append(bool(done))
+        st = ref_harness.export_state(env, api, objs)
+        per["post_step"].append(np.stack([st["x"], st["y"], st["theta"], st["holding"],
+                                          st["mandibles"].astype(float), st["reward_state"].astype(float)]))
+        ref_harness.run_update(ref, env, tape["noise"][t])
+        st = ref_harness.export_state(env, api, objs)
+        per["post_update"].append(np.stack([st["x"], st["y"], st["theta"], st["holding"],
+                                            st["mandibles"].astype(float), st["reward_state"].astype(float)]))
+        per["phero_sum"].append(st["phero"].sum(axis=(1, 2)))
+        per["food_sum"].append(st["food"].sum())
+        per["explored_count"].append(int(st["explored"].sum()))
+        per["anthill_food"].append(float(st["anthill_food"]))
+        per["rock_centers"].append(st["rock_centers"].copy())
+    final = ref_harness.export_state(env, api, objs)
+    for k, v in per.items():
+        rec["t_" + k] = np.array(v)
+    for k, v in final.items():
+        rec["final_" + k] = np.asarray(v)
+    rec["wall_hits"] = np.int64(ref.walls_proxy.hits)
+    ref.walls_proxy.hits = 0
+    return rec
+
+
+def main():
+    only = set(sys.argv[1:])
+    for name, kw in GOLDEN_SCENARIOS:
+        if only and name not in only:
+            continue
+        cfg, init, tape = make_scenario(**kw)
+        rec = run_reference(cfg, init, tape)
+        out = {"cfg_json": np.array(cfg_to_json(cfg)), "scenario_json": np.array(json.dumps(kw))}
+        for k, v in init.items():
+            out["init_" + k] = np.asarray(v)
+        for k, v in tape.items():
+            out["tape_" + k] = np.asarray(v)
+        out.update(rec)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-18s T=%3d hits=%4d anthill_food=%6.1f explored=%6d  %7.1f KB" % (
+            name, tape["rot"].shape[0], int(rec["wall_hits"]), float(rec["final_anthill_food"]),
+            int(rec["final_explored"].sum()), os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()
