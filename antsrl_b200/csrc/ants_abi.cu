@@ -1,0 +1,826 @@
+// ants_abi.cu -- host side of libantsrl_b200.so: the C ABI declared in include/antsrl_b200.h.
+// Owns all device state of one batch of environments, orders the kernel launches of observation / step / update
+// exactly as the reference orders its object updates, and moves state between dense host
+// arrays and the pitched HBM layout.
+#include "../../include/antsrl_b200.h"
+#include "ants_kernels.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+using ants::Params;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(ANTS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+enum Fam { F_MOVE = 0, F_FOOD, F_PERCEIVE, F_COLLIDE, F_ROCKS, F_EVAP, F_DEPOSIT, F_ABSORB, F_MISC, F_COUNT };
+const char *kFamName[F_COUNT] = {"move", "food_commit", "perceive", "collide", "rocks", "evaporate",
+                                 "deposit", "absorb", "misc"};
+
+struct TimedLaunch {
+    cudaEvent_t a, b;
+    int fam;
+};
+
+}  // namespace
+
+struct AntsBatch {
+    AntsConfig cfg;
+    Params p;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    std::vector<void *> allocs;
+    int64_t device_bytes = 0;
+    // generation counters (16 bit on the device)
+    uint32_t obs_gen = 0, occ_gen = 0, owner_phase = 0;
+    int64_t timestep = 1;
+    int rw_alias = 1, act_bool = 1, prev_synced = 1, needs_sweep = 1;
+    AntsStats stats;
+    // profiling
+    int profiling = 0;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double fam_ms[F_COUNT];
+    int64_t fam_launches[F_COUNT];
+    // device staging for the host-buffer entry points
+    int8_t *st_rot = nullptr, *st_ph = nullptr;
+    float *st_obs = nullptr, *st_as = nullptr, *st_state = nullptr;
+    double *st_reward = nullptr, *st_noise = nullptr;
+    uint32_t *h_counts = nullptr;   // pinned: commit_count, absorb_count readback
+    int perceive_smem = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(AntsBatch *b, T **ptr, int64_t count, bool zero = true) {
+    *ptr = nullptr;
+    if (count <= 0) count = 1;
+    size_t bytes = (size_t)count * sizeof(T);
+    void *d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess)
+        return fail(ANTS_E_ALLOC, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    if (zero) {
+        e = cudaMemsetAsync(d, 0, bytes, b->stream);
+        if (e != cudaSuccess) return fail(ANTS_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+    }
+    b->allocs.push_back(d);
+    b->device_bytes += (int64_t)bytes;
+    *ptr = (T *)d;
+    return ANTS_OK;
+}
+
+#define TRY(expr)                   \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != ANTS_OK) return _r; \
+    } while (0)
+
+cudaEvent_t get_event(AntsBatch *b) {
+    if (!b->event_pool.empty()) {
+        cudaEvent_t e = b->event_pool.back();
+        b->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LaunchScope {   // counts the launch and, when profiling, brackets it with events on the handle's stream
+    AntsBatch *b;
+    int fam;
+    cudaEvent_t a = nullptr, e = nullptr;
+    LaunchScope(AntsBatch *b_, int fam_) : b(b_), fam(fam_) {
+        b->stats.kernel_launches++;
+        b->fam_launches[fam]++;
+        if (b->profiling) {
+            a = get_event(b);
+            e = get_event(b);
+            cudaEventRecord(a, b->stream);
+        }
+    }
+    ~LaunchScope() {
+        if (b->profiling) {
+            cudaEventRecord(e, b->stream);
+            b->timed.push_back({a, e, fam});
+        }
+    }
+};
+
+int collect_timings(AntsBatch *b) {
+    if (b->timed.empty()) return ANTS_OK;
+    CK(cudaStreamSynchronize(b->stream));
+    for (auto &t : b->timed) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t.a, t.b);
+        b->fam_ms[t.fam] += ms;
+        b->event_pool.push_back(t.a);
+        b->event_pool.push_back(t.b);
+    }
+    b->timed.clear();
+    return ANTS_OK;
+}
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ANTS_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return ANTS_OK;
+}
+
+uint32_t next_obs_gen(AntsBatch *b) {
+    if (b->obs_gen >= 0xFFFDu) {   // fold live stamps into "explored long ago" before the counter wraps
+        LaunchScope ls(b, F_MISC);
+        ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 1, 0);
+        b->obs_gen = 0;
+    }
+    return ++b->obs_gen;
+}
+uint32_t next_occ_gen(AntsBatch *b) {
+    if (b->occ_gen >= 0xFFFEu) {
+        LaunchScope ls(b, F_MISC);
+        ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 0, 1);
+        b->occ_gen = 0;
+    }
+    return ++b->occ_gen;
+}
+uint32_t next_owner_phase(AntsBatch *b) {
+    if (b->owner_phase >= 0xFFFEu) {
+        cudaMemsetAsync(b->p.owner, 0, (size_t)b->p.E * b->p.plane * sizeof(uint32_t), b->stream);
+        b->owner_phase = 0;
+    }
+    return ++b->owner_phase;
+}
+
+int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward, int is_step) {
+    const Params &p = b->p;
+    uint32_t og = next_obs_gen(b);
+    int blocks = (int)cdiv(p.EN, ants::kPerceiveThreads);
+    {
+        LaunchScope ls(b, F_PERCEIVE);
+        ants::k_perceive<<<blocks, ants::kPerceiveThreads, b->perceive_smem, b->stream>>>(
+            p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias);
+    }
+    b->rw_alias = 0;
+    return check_launch("k_perceive");
+}
+
+int do_observe(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward) {
+    if (!d_obs || !d_as) return fail(ANTS_E_ARG, "ants_observe: obs and agent_state buffers are required");
+    const Params &p = b->p;
+    uint32_t occ = next_occ_gen(b);
+    {
+        LaunchScope ls(b, F_MOVE);
+        ants::k_occ_stamp<<<(int)cdiv(p.EN, 256), 256, 0, b->stream>>>(p, occ);
+    }
+    TRY(check_launch("k_occ_stamp"));
+    TRY(launch_perceive(b, d_obs, d_as, d_state, d_reward, 0));
+    b->stats.observations++;
+    return ANTS_OK;
+}
+
+int do_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs, float *d_as, double *d_reward,
+            int32_t *done) {
+    if (!d_obs || !d_as) return fail(ANTS_E_ARG, "ants_step: obs and agent_state buffers are required");
+    const Params &p = b->p;
+    if (d_ph && p.P != 2)
+        return fail(ANTS_E_ARG, "pheromone actions need exactly two pheromones (ants.py:92-96), have %d", p.P);
+    CK(cudaMemsetAsync(p.commit_count, 0, sizeof(uint32_t), b->stream));
+    uint32_t phase = next_owner_phase(b);
+    uint32_t occ = next_occ_gen(b);
+    int blocks = (int)cdiv(p.EN, 256);
+    {
+        LaunchScope ls(b, F_MOVE);
+        ants::k_step_move<<<blocks, 256, 0, b->stream>>>(p, d_rot, d_ph, phase << 16, occ, b->prev_synced ? 0 : 1,
+                                                         b->act_bool ? 1.0 : 256.0);
+    }
+    TRY(check_launch("k_step_move"));
+    {
+        LaunchScope ls(b, F_FOOD);
+        ants::k_food_commit<<<64, 128, 0, b->stream>>>(p, phase << 16);
+    }
+    TRY(check_launch("k_food_commit"));
+    b->prev_synced = 0;
+    TRY(launch_perceive(b, d_obs, d_as, nullptr, d_reward, 1));
+    if (done) *done = (b->cfg.max_time == b->timestep) ? 1 : 0;   // RL_api.py:200 (Q15)
+    b->stats.steps++;
+    return ANTS_OK;
+}
+
+int do_update(AntsBatch *b, const double *d_noise) {
+    Params &p = b->p;
+    int blocks = (int)cdiv(p.EN, 256);
+    uint32_t step_id = (uint32_t)b->timestep;
+    b->timestep += 1;                                               // environment.py:45
+    uint32_t phase = next_owner_phase(b);
+    // 1. Walls (order -1) on ants; without rocks also the ant part of Ants.update (order 999), which touches
+    //    nothing the objects in between read.
+    {
+        LaunchScope ls(b, F_COLLIDE);
+        ants::k_collide<<<blocks, 256, 0, b->stream>>>(p, d_noise, step_id, phase << 16, p.R > 0 ? 0 : 1);
+    }
+    TRY(check_launch("k_collide"));
+    // 3. CircleObstacles (order 0)
+    if (p.R > 0) {
+        {
+            LaunchScope ls(b, F_ROCKS);
+            ants::k_rocks_pushed<<<p.E, 256, 0, b->stream>>>(p);
+        }
+        TRY(check_launch("k_rocks_pushed"));
+        {
+            LaunchScope ls(b, F_ROCKS);
+            ants::k_rocks_push_ants<<<blocks, 256, 0, b->stream>>>(p, phase << 16);
+        }
+        TRY(check_launch("k_rocks_push_ants"));
+    }
+    // 1b + 4. wall zeroing of the field (walls.py:30) and Pheromone.update (order 0)
+    if (p.P > 0) {
+        if (b->cfg.diffuse_factor != 0.0) {
+            int nbx = (int)cdiv(p.W, ants::kStX), nby = (int)cdiv(p.H, ants::kStY);
+            {
+                LaunchScope ls(b, F_EVAP);
+                ants::k_diffuse_stencil<<<(unsigned)((int64_t)nbx * nby * p.E * p.P), 256, 0, b->stream>>>(p, nbx, nby);
+            }
+            TRY(check_launch("k_diffuse_stencil"));
+            double *t = p.phero; p.phero = p.phero_alt; p.phero_alt = t;
+            b->stats.active_tiles = b->stats.total_tiles;
+        } else if (b->cfg.evap_mode == ANTS_EVAP_ACTIVE_TILES) {
+            CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned long long), b->stream));
+            LaunchScope ls(b, F_EVAP);
+            ants::k_evaporate_tiles<<<148 * 8, 256, 0, b->stream>>>(p);
+        } else {
+            int64_t per_plane = cdiv(p.plane / 2, 256 * 4);
+            int64_t gx = per_plane < 1 ? 1 : per_plane;
+            LaunchScope ls(b, F_EVAP);
+            ants::k_evaporate_dense<<<(unsigned)(gx * p.E * p.P), 256, 0, b->stream>>>(p, (int)gx);
+        }
+        TRY(check_launch("evaporate"));
+        // 6. Ants.update (order 999): deposit
+        {
+            LaunchScope ls(b, F_DEPOSIT);
+            ants::k_deposit_commit<<<blocks, 256, 0, b->stream>>>(p, phase << 16);
+        }
+        TRY(check_launch("k_deposit_commit"));
+    }
+    // 7. Anthill (order 1000)
+    if (b->needs_sweep) {
+        LaunchScope ls(b, F_ABSORB);
+        ants::k_absorb_sweep<<<p.E, 256, 0, b->stream>>>(p);
+        b->needs_sweep = 0;
+        CK(cudaMemsetAsync(p.absorb_count, 0, sizeof(uint32_t), b->stream));
+    } else {
+        LaunchScope ls(b, F_ABSORB);
+        ants::k_absorb_list<<<1, 256, 0, b->stream>>>(p);
+    }
+    TRY(check_launch("absorb"));
+    b->prev_synced = 1;
+    b->stats.updates++;
+    return ANTS_OK;
+}
+
+bool is_device_accessible_host(const void *ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int ensure_staging(AntsBatch *b) {
+    if (b->st_obs) return ANTS_OK;
+    const Params &p = b->p;
+    TRY(dev_alloc(b, &b->st_rot, p.EN, false));
+    TRY(dev_alloc(b, &b->st_ph, p.EN, false));
+    TRY(dev_alloc(b, &b->st_obs, p.EN * p.S2 * p.C, false));
+    TRY(dev_alloc(b, &b->st_as, p.EN * 2, false));
+    TRY(dev_alloc(b, &b->st_state, p.EN * (2 + p.P), false));
+    TRY(dev_alloc(b, &b->st_reward, p.EN, false));
+    TRY(dev_alloc(b, &b->st_noise, p.EN, false));
+    return ANTS_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int ants_abi_version(void) { return ANTS_ABI_VERSION; }
+const char *ants_last_error(void) { return g_err.c_str(); }
+
+int ants_create(const AntsConfig *cfg, AntsBatch **out) {
+    if (!cfg || !out) return fail(ANTS_E_ARG, "ants_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != ANTS_ABI_VERSION)
+        return fail(ANTS_E_ARG, "abi_version %d != %d", cfg->abi_version, ANTS_ABI_VERSION);
+    if (cfg->n_envs < 1 || cfg->n_ants < 1 || cfg->w < 1 || cfg->h < 1)
+        return fail(ANTS_E_ARG, "n_envs, n_ants, w, h must be >= 1");
+    if (cfg->n_ants > ANTS_MAX_ANTS) return fail(ANTS_E_ARG, "n_ants %d > %d", cfg->n_ants, ANTS_MAX_ANTS);
+    if ((int64_t)cfg->n_envs * cfg->n_ants >= (1ll << 31)) return fail(ANTS_E_ARG, "n_envs * n_ants must be < 2^31");
+    if (cfg->n_phero < 0 || cfg->n_phero > ANTS_MAX_PHERO) return fail(ANTS_E_ARG, "n_phero out of range");
+    if (cfg->n_rocks < 0 || cfg->n_rocks > ANTS_MAX_ROCKS) return fail(ANTS_E_ARG, "n_rocks out of range");
+    if (cfg->radius < 0 || cfg->radius > ANTS_MAX_RADIUS) return fail(ANTS_E_ARG, "radius out of range");
+    if (cfg->n_channels < 1 || cfg->n_channels > ANTS_MAX_CHANNELS) return fail(ANTS_E_ARG, "n_channels out of range");
+    if (cfg->reward_kind < 0 || cfg->reward_kind > 2) return fail(ANTS_E_ARG, "reward_kind out of range");
+    for (int c = 0; c < cfg->n_channels; ++c) {
+        int k = cfg->channel_kind[c];
+        if (k < 0 || k > ANTS_CH_ROCKS) return fail(ANTS_E_ARG, "channel %d: unknown kind %d", c, k);
+        if (k == ANTS_CH_PHERO) {
+            if (cfg->channel_arg[c] < 0 || cfg->channel_arg[c] >= cfg->n_phero)
+                return fail(ANTS_E_ARG, "channel %d: pheromone index out of range", c);
+            if (!cfg->has_max_val)
+                return fail(ANTS_E_ARG, "a perceived pheromone needs max_val (RL_api.py:125 divides by it)");
+        }
+        if (k == ANTS_CH_ROCKS && cfg->n_rocks == 0) return fail(ANTS_E_ARG, "rocks channel without rocks");
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(ANTS_E_CUDA, "no CUDA device (%s); libantsrl_b200 has no CPU path",
+                    ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(ANTS_E_ARG, "device %d of %d", cfg->device, ndev);
+    CK(cudaSetDevice(cfg->device));
+
+    AntsBatch *b = new AntsBatch();
+    b->cfg = *cfg;
+    memset(&b->stats, 0, sizeof b->stats);
+    memset(b->fam_ms, 0, sizeof b->fam_ms);
+    memset(b->fam_launches, 0, sizeof b->fam_launches);
+    if (cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete b;
+        return fail(ANTS_E_CUDA, "cudaStreamCreate failed");
+    }
+    b->stream = b->own_stream;
+    Params &p = b->p;
+    memset(&p, 0, sizeof p);
+    p.E = cfg->n_envs; p.N = cfg->n_ants; p.W = cfg->w; p.H = cfg->h; p.P = cfg->n_phero; p.R = cfg->n_rocks;
+    p.Hp = (int)(cdiv(cfg->h, 16) * 16);
+    p.EN = (int64_t)p.E * p.N;
+    p.plane = (int64_t)p.W * p.Hp;
+    p.radius = cfg->radius; p.S = 2 * cfg->radius + 1; p.S2 = p.S * p.S; p.C = cfg->n_channels;
+    p.has_mask = cfg->has_mask;
+    p.rule_n = 0;
+    for (int c = 0; c < p.C; ++c) {
+        p.ch_kind[c] = cfg->channel_kind[c];
+        p.ch_arg[c] = cfg->channel_arg[c];
+        if (cfg->channel_kind[c] == ANTS_CH_FOOD) p.rule_op[p.rule_n++] = 0;
+        if (cfg->channel_kind[c] == ANTS_CH_ANTHILL) p.rule_op[p.rule_n++] = 1;
+    }
+    p.reward_kind = cfg->reward_kind;
+    p.explore_on = (cfg->reward_kind == ANTS_REWARD_EXPLORE) ||
+                   (cfg->reward_kind == ANTS_REWARD_ALL &&
+                    (cfg->reward_factors[0] != 0.0 || cfg->reward_factors[3] != 0.0));
+    p.has_max_val = cfg->has_max_val;
+    p.tiles_x = (int)cdiv(p.W, ants::kTile);
+    p.tiles_y = p.Hp / ants::kTile;
+    p.delta = cfg->delta; p.fwd_delta = cfg->fwd_delta; p.reward_threshold = cfg->reward_threshold;
+    p.max_speed = cfg->max_speed; p.max_rot_speed = cfg->max_rot_speed;
+    p.csr = cfg->carry_speed_reduction; p.bsr = cfg->backward_speed_reduction;
+    p.f_explore = cfg->reward_factors[0]; p.f_food = cfg->reward_factors[1]; p.f_anthill = cfg->reward_factors[2];
+    p.f_explore_hold = cfg->reward_factors[3]; p.f_heading = cfg->reward_factors[4];
+    // pheromone.py:7-9: ring = DF, centre = 1 - 8 DF, all times (1 - EVAP)
+    {
+        volatile double ring = 1.0 * cfg->diffuse_factor;
+        volatile double centre = 1.0 - 8.0 * cfg->diffuse_factor;
+        volatile double keep = 1.0 - cfg->evap_factor;
+        p.filt_ring = ring * keep;
+        p.filt_center = centre * keep;
+    }
+    p.phero_max_val = cfg->phero_max_val; p.max_hold = cfg->max_hold;
+    p.rng_seed = cfg->rng_seed; p.env_id_base = cfg->env_id_base;
+
+    int rc = ANTS_OK;
+    auto A = [&](int r) { if (rc == ANTS_OK) rc = r; };
+    const int64_t EN = p.EN, cells = (int64_t)p.E * p.plane;
+    A(dev_alloc(b, &p.x, EN)); A(dev_alloc(b, &p.y, EN)); A(dev_alloc(b, &p.theta, EN));
+    A(dev_alloc(b, &p.prev_x, EN)); A(dev_alloc(b, &p.prev_y, EN)); A(dev_alloc(b, &p.prev_theta, EN));
+    A(dev_alloc(b, &p.holding, EN)); A(dev_alloc(b, &p.seed, EN));
+    A(dev_alloc(b, &p.act, EN * (p.P > 0 ? p.P : 1)));
+    A(dev_alloc(b, &p.mandibles, EN)); A(dev_alloc(b, &p.reward_state, EN));
+    A(dev_alloc(b, &p.rw_holding_prev, EN)); A(dev_alloc(b, &p.rw_prev_dist, EN)); A(dev_alloc(b, &p.rewards, EN));
+    A(dev_alloc(b, &p.phero, cells * (p.P > 0 ? p.P : 1)));
+    if (cfg->diffuse_factor != 0.0) A(dev_alloc(b, &p.phero_alt, cells * (p.P > 0 ? p.P : 1)));
+    A(dev_alloc(b, &p.food, cells));
+    A(dev_alloc(b, &p.walls, cells));
+    A(dev_alloc(b, &p.meta, cells));
+    A(dev_alloc(b, &p.owner, cells));
+    if (cfg->evap_mode == ANTS_EVAP_ACTIVE_TILES && cfg->diffuse_factor == 0.0)
+        A(dev_alloc(b, &p.tile_active, (int64_t)p.E * (p.P > 0 ? p.P : 1) * p.tiles_x * p.tiles_y));
+    A(dev_alloc(b, &p.hill, (int64_t)p.E * 4));
+    A(dev_alloc(b, &p.hill_food, (int64_t)p.E));
+    A(dev_alloc(b, &p.rock_c, (int64_t)p.E * p.R * 2)); A(dev_alloc(b, &p.rock_rad, (int64_t)p.E * p.R));
+    A(dev_alloc(b, &p.rock_w, (int64_t)p.E * p.R));
+    A(dev_alloc(b, &p.food_delta, EN, false));
+    A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
+    A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
+    A(dev_alloc(b, &p.tile_counter, 1));
+    b->stats.total_tiles = (int64_t)p.E * p.P * p.tiles_x * p.tiles_y;
+    // perception tables, RL_api.py:92-93: coords[i][j] = ((j - r) * DELTA, (i - r) * DELTA)
+    double *d_px = nullptr, *d_py = nullptr;
+    uint8_t *d_mask = nullptr;
+    A(dev_alloc(b, &d_px, p.S2)); A(dev_alloc(b, &d_py, p.S2)); A(dev_alloc(b, &d_mask, p.S2));
+    if (rc != ANTS_OK) { ants_destroy(b); return rc; }
+    {
+        std::vector<double> px(p.S2), py(p.S2);
+        std::vector<uint8_t> mk(p.S2, 1);
+        for (int i = 0; i < p.S; ++i)
+            for (int j = 0; j < p.S; ++j) {
+                volatile double fx = (double)(j - p.radius), fy = (double)(i - p.radius);
+                px[i * p.S + j] = fx * cfg->delta;
+                py[i * p.S + j] = fy * cfg->delta;
+                if (cfg->has_mask) mk[i * p.S + j] = cfg->mask[i * p.S + j] ? 1 : 0;
+            }
+        cudaMemcpy(d_px, px.data(), p.S2 * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_py, py.data(), p.S2 * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_mask, mk.data(), p.S2, cudaMemcpyHostToDevice);
+        p.samp_px = d_px; p.samp_py = d_py; p.mask = d_mask;
+    }
+    b->perceive_smem = (int)(ants::kPerceiveThreads * sizeof(ants::AntPrep) + 2 * p.S2 * sizeof(double) +
+                             (ants::kPerceiveThreads / 32) * p.S2 * p.C * sizeof(float) + p.S2 + 16);
+    if (b->perceive_smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ants::k_perceive, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             b->perceive_smem);
+        if (e != cudaSuccess) {
+            ants_destroy(b);
+            return fail(ANTS_E_CUDA, "perception window needs %d B of shared memory: %s", b->perceive_smem,
+                        cudaGetErrorString(e));
+        }
+    }
+    if (cudaHostAlloc((void **)&b->h_counts, 64, cudaHostAllocDefault) != cudaSuccess) {
+        ants_destroy(b);
+        return fail(ANTS_E_ALLOC, "cudaHostAlloc failed");
+    }
+    cudaError_t se = cudaStreamSynchronize(b->stream);
+    if (se != cudaSuccess) {
+        ants_destroy(b);
+        return fail(ANTS_E_CUDA, "initialisation failed: %s", cudaGetErrorString(se));
+    }
+    b->stats.device_bytes = b->device_bytes;
+    *out = b;
+    return ANTS_OK;
+}
+
+int ants_destroy(AntsBatch *b) {
+    if (!b) return ANTS_OK;
+    cudaSetDevice(b->cfg.device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    for (auto &t : b->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : b->event_pool) cudaEventDestroy(e);
+    for (void *d : b->allocs) cudaFree(d);
+    if (b->h_counts) cudaFreeHost(b->h_counts);
+    if (b->own_stream) cudaStreamDestroy(b->own_stream);
+    delete b;
+    return ANTS_OK;
+}
+
+int ants_set_stream(AntsBatch *b, void *cuda_stream) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaStreamSynchronize(b->stream));
+    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    return ANTS_OK;
+}
+
+int ants_synchronize(AntsBatch *b) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaSetDevice(b->cfg.device));
+    CK(cudaStreamSynchronize(b->stream));
+    return ANTS_OK;
+}
+
+int ants_import_state(AntsBatch *b, const AntsHostState *s) {
+    if (!b || !s) return fail(ANTS_E_ARG, "null argument");
+    CK(cudaSetDevice(b->cfg.device));
+    Params &p = b->p;
+    cudaStream_t st = b->stream;
+    const size_t EN8 = (size_t)p.EN * sizeof(double);
+    auto up = [&](double *dst, const double *src) -> cudaError_t {
+        return src ? cudaMemcpyAsync(dst, src, EN8, cudaMemcpyHostToDevice, st) : cudaSuccess;
+    };
+    CK(up(p.x, s->x)); CK(up(p.y, s->y)); CK(up(p.theta, s->theta));
+    CK(up(p.prev_x, s->prev_x ? s->prev_x : s->x)); CK(up(p.prev_y, s->prev_y ? s->prev_y : s->y));
+    CK(up(p.prev_theta, s->prev_theta ? s->prev_theta : s->theta));
+    CK(up(p.holding, s->holding)); CK(up(p.seed, s->seed));
+    CK(up(p.rw_holding_prev, s->rw_holding_prev)); CK(up(p.rw_prev_dist, s->rw_prev_dist));
+    CK(up(p.rewards, s->rewards));
+    if (s->mandibles) CK(cudaMemcpyAsync(p.mandibles, s->mandibles, p.EN, cudaMemcpyHostToDevice, st));
+    if (s->reward_state) CK(cudaMemcpyAsync(p.reward_state, s->reward_state, p.EN, cudaMemcpyHostToDevice, st));
+    std::vector<double> act_t;
+    if (s->activation && p.P > 0) {
+        act_t.resize((size_t)p.EN * p.P);
+        for (int64_t i = 0; i < p.EN; ++i)
+            for (int k = 0; k < p.P; ++k) act_t[(size_t)k * p.EN + i] = s->activation[i * p.P + k];
+        CK(cudaMemcpyAsync(p.act, act_t.data(), act_t.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    if (s->x && s->prev_x && s->prev_y && s->y)
+        b->prev_synced = (memcmp(s->x, s->prev_x, EN8) == 0 && memcmp(s->y, s->prev_y, EN8) == 0) ? 1 : 0;
+    else if (s->x)
+        b->prev_synced = 1;
+    const size_t rows = (size_t)p.E * p.W;
+    if (s->phero && p.P > 0) {
+        CK(cudaMemsetAsync(p.phero, 0, (size_t)p.E * p.P * p.plane * sizeof(double), st));
+        CK(cudaMemcpy2DAsync(p.phero, (size_t)p.Hp * 8, s->phero, (size_t)p.H * 8, (size_t)p.H * 8, rows * p.P,
+                             cudaMemcpyHostToDevice, st));
+        if (p.tile_active) {
+            ants::k_tiles_from_phero<<<148 * 4, 256, 0, st>>>(p);
+            TRY(check_launch("k_tiles_from_phero"));
+        }
+    }
+    if (s->food) {
+        CK(cudaMemsetAsync(p.food, 0, (size_t)p.E * p.plane * sizeof(double), st));
+        CK(cudaMemcpy2DAsync(p.food, (size_t)p.Hp * 8, s->food, (size_t)p.H * 8, (size_t)p.H * 8, rows,
+                             cudaMemcpyHostToDevice, st));
+        b->needs_sweep = 1;
+    }
+    std::vector<uint8_t> walls01;
+    if (s->walls) {
+        size_t n = rows * p.H;
+        walls01.resize(n);
+        for (size_t j = 0; j < n; ++j) walls01[j] = s->walls[j] ? 1 : 0;      // Walls.__init__: astype(bool)
+        CK(cudaMemsetAsync(p.walls, 0, (size_t)p.E * p.plane, st));
+        CK(cudaMemcpy2DAsync(p.walls, (size_t)p.Hp, walls01.data(), (size_t)p.H, (size_t)p.H, rows,
+                             cudaMemcpyHostToDevice, st));
+    }
+    uint8_t *d_tmp = nullptr;
+    if (s->explored) {
+        size_t n = rows * p.H;
+        CK(cudaMalloc((void **)&d_tmp, n));
+        CK(cudaMemcpyAsync(d_tmp, s->explored, n, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(p.meta, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
+        ants::k_meta_from_explored<<<148 * 4, 256, 0, st>>>(p, d_tmp);
+        TRY(check_launch("k_meta_from_explored"));
+        b->obs_gen = 0; b->occ_gen = 0;
+    }
+    std::vector<int32_t> hill4;
+    if (s->anthill_xyr) {
+        hill4.resize((size_t)p.E * 4);
+        for (int e = 0; e < p.E; ++e) {
+            int32_t r = s->anthill_xyr[3 * e + 2];
+            hill4[4 * e] = s->anthill_xyr[3 * e]; hill4[4 * e + 1] = s->anthill_xyr[3 * e + 1];
+            hill4[4 * e + 2] = r; hill4[4 * e + 3] = r < 0 ? -1 : r * r;
+        }
+        CK(cudaMemcpyAsync(p.hill, hill4.data(), hill4.size() * 4, cudaMemcpyHostToDevice, st));
+        b->needs_sweep = 1;
+    }
+    if (s->anthill_food) CK(cudaMemcpyAsync(p.hill_food, s->anthill_food, (size_t)p.E * 8, cudaMemcpyHostToDevice, st));
+    if (p.R > 0) {
+        if (s->rock_centers) CK(cudaMemcpyAsync(p.rock_c, s->rock_centers, (size_t)p.E * p.R * 16, cudaMemcpyHostToDevice, st));
+        if (s->rock_radii) CK(cudaMemcpyAsync(p.rock_rad, s->rock_radii, (size_t)p.E * p.R * 8, cudaMemcpyHostToDevice, st));
+        if (s->rock_weights) CK(cudaMemcpyAsync(p.rock_w, s->rock_weights, (size_t)p.E * p.R * 8, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(p.absorb_count, 0, sizeof(uint32_t), st));
+    b->owner_phase = 0;
+    b->timestep = s->timestep > 0 ? s->timestep : 1;
+    b->rw_alias = s->rw_alias ? 1 : 0;
+    b->act_bool = s->act_bool ? 1 : 0;
+    CK(cudaStreamSynchronize(st));   // host temporaries above must outlive the copies
+    if (d_tmp) cudaFree(d_tmp);
+    return ANTS_OK;
+}
+
+int ants_export_state(AntsBatch *b, AntsHostState *s) {
+    if (!b || !s) return fail(ANTS_E_ARG, "null argument");
+    CK(cudaSetDevice(b->cfg.device));
+    Params &p = b->p;
+    cudaStream_t st = b->stream;
+    const size_t EN8 = (size_t)p.EN * sizeof(double);
+    auto down = [&](double *dst, const double *src) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, src, EN8, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
+    CK(down(s->x, p.x)); CK(down(s->y, p.y)); CK(down(s->theta, p.theta));
+    CK(down(s->prev_x, p.prev_x)); CK(down(s->prev_y, p.prev_y)); CK(down(s->prev_theta, p.prev_theta));
+    CK(down(s->holding, p.holding)); CK(down(s->seed, p.seed));
+    CK(down(s->rw_holding_prev, p.rw_holding_prev)); CK(down(s->rw_prev_dist, p.rw_prev_dist));
+    CK(down(s->rewards, p.rewards));
+    if (s->mandibles) CK(cudaMemcpyAsync(s->mandibles, p.mandibles, p.EN, cudaMemcpyDeviceToHost, st));
+    if (s->reward_state) CK(cudaMemcpyAsync(s->reward_state, p.reward_state, p.EN, cudaMemcpyDeviceToHost, st));
+    std::vector<double> act_t;
+    if (s->activation && p.P > 0) {
+        act_t.resize((size_t)p.EN * p.P);
+        CK(cudaMemcpyAsync(act_t.data(), p.act, act_t.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    const size_t rows = (size_t)p.E * p.W;
+    if (s->phero && p.P > 0)
+        CK(cudaMemcpy2DAsync(s->phero, (size_t)p.H * 8, p.phero, (size_t)p.Hp * 8, (size_t)p.H * 8, rows * p.P,
+                             cudaMemcpyDeviceToHost, st));
+    if (s->food)
+        CK(cudaMemcpy2DAsync(s->food, (size_t)p.H * 8, p.food, (size_t)p.Hp * 8, (size_t)p.H * 8, rows,
+                             cudaMemcpyDeviceToHost, st));
+    if (s->walls)
+        CK(cudaMemcpy2DAsync(s->walls, (size_t)p.H, p.walls, (size_t)p.Hp, (size_t)p.H, rows, cudaMemcpyDeviceToHost, st));
+    uint8_t *d_tmp = nullptr;
+    if (s->explored) {
+        size_t n = rows * p.H;
+        CK(cudaMalloc((void **)&d_tmp, n));
+        ants::k_explored_from_meta<<<148 * 4, 256, 0, st>>>(p, d_tmp);
+        TRY(check_launch("k_explored_from_meta"));
+        CK(cudaMemcpyAsync(s->explored, d_tmp, n, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<int32_t> hill4;
+    if (s->anthill_xyr) {
+        hill4.resize((size_t)p.E * 4);
+        CK(cudaMemcpyAsync(hill4.data(), p.hill, hill4.size() * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (s->anthill_food) CK(cudaMemcpyAsync(s->anthill_food, p.hill_food, (size_t)p.E * 8, cudaMemcpyDeviceToHost, st));
+    if (p.R > 0) {
+        if (s->rock_centers) CK(cudaMemcpyAsync(s->rock_centers, p.rock_c, (size_t)p.E * p.R * 16, cudaMemcpyDeviceToHost, st));
+        if (s->rock_radii) CK(cudaMemcpyAsync(s->rock_radii, p.rock_rad, (size_t)p.E * p.R * 8, cudaMemcpyDeviceToHost, st));
+        if (s->rock_weights) CK(cudaMemcpyAsync(s->rock_weights, p.rock_w, (size_t)p.E * p.R * 8, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (d_tmp) cudaFree(d_tmp);
+    if (s->activation && p.P > 0)
+        for (int64_t i = 0; i < p.EN; ++i)
+            for (int k = 0; k < p.P; ++k) s->activation[i * p.P + k] = act_t[(size_t)k * p.EN + i];
+    if (s->anthill_xyr)
+        for (int e = 0; e < p.E; ++e) {
+            s->anthill_xyr[3 * e] = hill4[4 * e]; s->anthill_xyr[3 * e + 1] = hill4[4 * e + 1];
+            s->anthill_xyr[3 * e + 2] = hill4[4 * e + 2];
+        }
+    s->timestep = b->timestep;
+    s->rw_alias = b->rw_alias;
+    s->act_bool = b->act_bool;
+    return ANTS_OK;
+}
+
+int ants_activate_all_pheromones(AntsBatch *b, const double *act, int32_t is_bool) {
+    if (!b || !act) return fail(ANTS_E_ARG, "null argument");
+    CK(cudaSetDevice(b->cfg.device));
+    Params &p = b->p;
+    if (p.P == 0) return ANTS_OK;
+    std::vector<double> act_t((size_t)p.EN * p.P);
+    for (int64_t i = 0; i < p.EN; ++i)
+        for (int k = 0; k < p.P; ++k) {
+            double v = act[i * p.P + k];
+            act_t[(size_t)k * p.EN + i] = is_bool ? (v != 0.0 ? 1.0 : 0.0) : v;
+        }
+    CK(cudaMemcpyAsync(p.act, act_t.data(), act_t.size() * sizeof(double), cudaMemcpyHostToDevice, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->act_bool = is_bool ? 1 : 0;
+    return ANTS_OK;
+}
+
+int ants_observe(AntsBatch *b, float *d_obs, float *d_agent_state, float *d_state, double *d_reward) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaSetDevice(b->cfg.device));
+    return do_observe(b, d_obs, d_agent_state, d_state, d_reward);
+}
+
+int ants_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs, float *d_agent_state,
+              double *d_reward, int32_t *done) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaSetDevice(b->cfg.device));
+    return do_step(b, d_rot, d_ph, d_obs, d_agent_state, d_reward, done);
+}
+
+int ants_update(AntsBatch *b, const double *d_noise) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaSetDevice(b->cfg.device));
+    return do_update(b, d_noise);
+}
+
+int ants_rollout(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape, int32_t n_steps, float *d_obs,
+                 float *d_agent_state, double *d_reward) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaSetDevice(b->cfg.device));
+    for (int t = 0; t < n_steps; ++t) {
+        const int8_t *r = d_rot_tape ? d_rot_tape + (int64_t)t * b->p.EN : nullptr;
+        const int8_t *h = d_ph_tape ? d_ph_tape + (int64_t)t * b->p.EN : nullptr;
+        TRY(do_step(b, r, h, d_obs, d_agent_state, d_reward, nullptr));
+        TRY(do_update(b, nullptr));
+    }
+    return ANTS_OK;
+}
+
+void *ants_host_alloc(uint64_t bytes) {
+    void *ptr = nullptr;
+    if (cudaHostAlloc(&ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        fail(ANTS_E_ALLOC, "cudaHostAlloc of %llu bytes failed", (unsigned long long)bytes);
+        cudaGetLastError();
+        return nullptr;
+    }
+    return ptr;
+}
+
+int ants_host_free(void *ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return ANTS_OK;
+}
+
+int ants_observe_host(AntsBatch *b, float *h_obs, float *h_agent_state, float *h_state, double *h_reward) {
+    if (!b || !h_obs || !h_agent_state) return fail(ANTS_E_ARG, "null argument");
+    CK(cudaSetDevice(b->cfg.device));
+    TRY(ensure_staging(b));
+    const Params &p = b->p;
+    TRY(do_observe(b, b->st_obs, b->st_as, h_state ? b->st_state : nullptr, b->st_reward));
+    CK(cudaMemcpyAsync(h_obs, b->st_obs, (size_t)p.EN * p.S2 * p.C * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(h_agent_state, b->st_as, (size_t)p.EN * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (h_state) CK(cudaMemcpyAsync(h_state, b->st_state, (size_t)p.EN * (2 + p.P) * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (h_reward) CK(cudaMemcpyAsync(h_reward, b->st_reward, (size_t)p.EN * 8, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return ANTS_OK;
+}
+
+int ants_step_host(AntsBatch *b, const int8_t *h_rot, const int8_t *h_ph, float *h_obs, float *h_agent_state,
+                   double *h_reward, int32_t *done) {
+    if (!b || !h_obs || !h_agent_state) return fail(ANTS_E_ARG, "null argument");
+    CK(cudaSetDevice(b->cfg.device));
+    TRY(ensure_staging(b));
+    const Params &p = b->p;
+    if (h_rot) CK(cudaMemcpyAsync(b->st_rot, h_rot, (size_t)p.EN, cudaMemcpyHostToDevice, b->stream));
+    if (h_ph) CK(cudaMemcpyAsync(b->st_ph, h_ph, (size_t)p.EN, cudaMemcpyHostToDevice, b->stream));
+    TRY(do_step(b, h_rot ? b->st_rot : nullptr, h_ph ? b->st_ph : nullptr, b->st_obs, b->st_as, b->st_reward, done));
+    CK(cudaMemcpyAsync(h_obs, b->st_obs, (size_t)p.EN * p.S2 * p.C * 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(h_agent_state, b->st_as, (size_t)p.EN * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (h_reward) CK(cudaMemcpyAsync(h_reward, b->st_reward, (size_t)p.EN * 8, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return ANTS_OK;
+}
+
+int ants_update_host(AntsBatch *b, const double *h_noise) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    CK(cudaSetDevice(b->cfg.device));
+    if (h_noise) {
+        TRY(ensure_staging(b));
+        CK(cudaMemcpyAsync(b->st_noise, h_noise, (size_t)b->p.EN * 8, cudaMemcpyHostToDevice, b->stream));
+        TRY(do_update(b, b->st_noise));
+        CK(cudaStreamSynchronize(b->stream));   // the caller may reuse h_noise
+        return ANTS_OK;
+    }
+    return do_update(b, nullptr);
+}
+
+int ants_get_stats(AntsBatch *b, AntsStats *out) {
+    if (!b || !out) return fail(ANTS_E_ARG, "null argument");
+    CK(cudaSetDevice(b->cfg.device));
+    CK(cudaMemcpyAsync(b->h_counts, b->p.commit_count, 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b->h_counts + 1, b->p.absorb_count, 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b->h_counts + 2, b->p.tile_counter, 8, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->stats.food_commits = b->h_counts[0];
+    b->stats.absorb_events = b->h_counts[1];
+    if (b->p.tile_active) {
+        unsigned long long t;
+        memcpy(&t, b->h_counts + 2, 8);
+        b->stats.active_tiles = (int64_t)t;
+    } else {
+        b->stats.active_tiles = b->stats.total_tiles;
+    }
+    b->stats.device_bytes = b->device_bytes;
+    *out = b->stats;
+    return ANTS_OK;
+}
+
+int ants_set_profiling(AntsBatch *b, int32_t on) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    TRY(collect_timings(b));
+    b->profiling = on ? 1 : 0;
+    return ANTS_OK;
+}
+
+int ants_get_kernel_ms(AntsBatch *b, const char *name, double *ms, int64_t *launches) {
+    if (!b || !name) return fail(ANTS_E_ARG, "null argument");
+    TRY(collect_timings(b));
+    for (int f = 0; f < F_COUNT; ++f)
+        if (strcmp(name, kFamName[f]) == 0) {
+            if (ms) *ms = b->fam_ms[f];
+            if (launches) *launches = b->fam_launches[f];
+            return ANTS_OK;
+        }
+    return fail(ANTS_E_ARG, "unknown kernel family '%s'", name);
+}
+
+int ants_reset_kernel_ms(AntsBatch *b) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    TRY(collect_timings(b));
+    memset(b->fam_ms, 0, sizeof b->fam_ms);
+    memset(b->fam_launches, 0, sizeof b->fam_launches);
+    return ANTS_OK;
+}
+
+}  // extern "C"

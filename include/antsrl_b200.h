@@ -1,0 +1,170 @@
+/*
+ * antsrl_b200.h -- C ABI of libantsrl_b200.so: the AntsRL environment step loop as sm_100a CUDA kernels over a
+ * batch of E independent environments held in structure-of-arrays layout in HBM.
+ *
+ * The reference (SelennLamson/AntsRL) has no FFI; its boundary for this path is the Python object surface
+ *   RLApi.observation()            environment/RL_api.py:96-165
+ *   RLApi.step(rotation, phero)    environment/RL_api.py:168-204
+ *   Environment.update()           environment/environment.py:42-47  (dispatching Walls/CircleObstacles/
+ *                                  Pheromone/Ants/Anthill.update: walls.py:22-30, circle_obstacles.py:32-58,
+ *                                  pheromone.py:43-45, ants.py:123-130, anthill.py:41-46)
+ *   Ants.activate_all_pheromones() environment/ants.py:86-87
+ *   reward.observation()/step()    environment/rewards/reward_custom.py:17-22,37-40,79-106; reward.py:29-38
+ * Each entry point below names the reference method it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.  All functions return 0 on success and a negative ANTS_E_* code on
+ * failure; ants_last_error() returns the message of the last failure on the calling thread.  A handle is bound
+ * to one CUDA device and one stream and is not thread-safe.  There is no CPU fallback: without a CUDA device
+ * ants_create fails with ANTS_E_CUDA.
+ *
+ * Index conventions: ants arrays are [E][N]; planes are [E][W][H] with the reference's [x][y] order (y
+ * contiguous); pheromone planes [E][P][W][H]; activation [E][N][P]; rocks [E][R](x,y).  Host arrays are
+ * dense (no pitch); the library pads rows in HBM internally.
+ */
+#ifndef ANTSRL_B200_H
+#define ANTSRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANTS_ABI_VERSION 1
+#define ANTS_MAX_PHERO 4
+#define ANTS_MAX_CHANNELS 16
+#define ANTS_MAX_RADIUS 7            /* perception window (2r+1)^2 <= 225 samples */
+#define ANTS_MAX_SAMPLES 225
+#define ANTS_MAX_ROCKS 64
+#define ANTS_MAX_ANTS 65535          /* ant index is packed in 16 bits of the ownership stamp */
+
+enum { ANTS_OK = 0, ANTS_E_ARG = -1, ANTS_E_CUDA = -2, ANTS_E_STATE = -3, ANTS_E_ALLOC = -4 };
+
+/* perceived_objects entries, RL_api.py:123-142 */
+enum { ANTS_CH_ANTS = 0, ANTS_CH_PHERO = 1, ANTS_CH_ANTHILL = 2, ANTS_CH_WALLS = 3, ANTS_CH_FOOD = 4,
+       ANTS_CH_ROCKS = 5 };
+/* reward_custom.py: All_Rewards (:43), ExplorationReward (:8), Food_Reward (:28) */
+enum { ANTS_REWARD_ALL = 0, ANTS_REWARD_EXPLORE = 1, ANTS_REWARD_FOOD = 2 };
+/* pheromone field maintenance: dense pass over every cell, or only over tiles that hold pheromone */
+enum { ANTS_EVAP_DENSE = 0, ANTS_EVAP_ACTIVE_TILES = 1 };
+
+typedef struct AntsConfig {
+    int32_t abi_version;             /* must be ANTS_ABI_VERSION */
+    int32_t device;                  /* CUDA device ordinal */
+    int32_t n_envs, n_ants, w, h;    /* E, N, W, H */
+    int32_t n_phero, n_rocks;        /* P <= ANTS_MAX_PHERO, R <= ANTS_MAX_ROCKS */
+    int32_t max_time;                /* Environment.max_time, environment.py:26 */
+    /* perception, RLApi.setup_perception RL_api.py:80-93 */
+    int32_t radius;
+    int32_t has_mask;
+    uint8_t mask[ANTS_MAX_SAMPLES];  /* row-major (2r+1)x(2r+1), 1 = visible */
+    int32_t n_channels;
+    int32_t channel_kind[ANTS_MAX_CHANNELS];
+    int32_t channel_arg[ANTS_MAX_CHANNELS];   /* pheromone index for ANTS_CH_PHERO */
+    double delta;                    /* DELTA = 1.1, RL_api.py:15 */
+    double fwd_delta;                /* perception_fwd_delta */
+    /* RLApi.__init__, RL_api.py:23 */
+    double reward_threshold, max_speed, max_rot_speed, carry_speed_reduction, backward_speed_reduction;
+    /* reward, reward_custom.py:44-50 */
+    int32_t reward_kind;
+    double reward_factors[5];        /* fct_explore, fct_food, fct_anthill, fct_explore_holding, fct_headinganthill */
+    /* pheromone.py:5-10, environment_generator.py:93,97 */
+    double diffuse_factor, evap_factor;
+    int32_t has_max_val;
+    double phero_max_val;
+    double max_hold;
+    /* collision noise when no tape is passed to ants_update: Philox4x32-10 keyed by
+     * (rng_seed, env_id_base + e, timestep, ant) -- results do not depend on how envs are sharded */
+    uint64_t rng_seed;
+    int64_t env_id_base;
+    int32_t evap_mode;               /* ANTS_EVAP_* */
+    int32_t reserved[7];
+} AntsConfig;
+
+/* Host-side SoA view of the whole batch for import/export.  NULL members are skipped. */
+typedef struct AntsHostState {
+    double *x, *y, *theta;                    /* Ants.ants, ants.py:27          [E][N] */
+    double *prev_x, *prev_y, *prev_theta;     /* Ants.prev_ants, ants.py:30     [E][N] */
+    double *holding, *seed;                   /* ants.py:37,41                  [E][N] */
+    double *activation;                       /* Ants.phero_activation          [E][N][P] */
+    uint8_t *mandibles, *reward_state;        /* ants.py:36,38                  [E][N] */
+    double *rw_holding_prev, *rw_prev_dist, *rewards;   /* reward_custom.py:52-60   [E][N] */
+    uint8_t *explored;                        /* explored_map, reward_custom.py:68   [E][W][H] */
+    uint8_t *walls;                           /* Walls.map, walls.py:16         [E][W][H] */
+    double *phero;                            /* Pheromone.phero, pheromone.py:28    [E][P][W][H] */
+    double *food;                             /* Food.qte, food.py:15           [E][W][H] */
+    int32_t *anthill_xyr;                     /* Anthill.x,y,radius anthill.py:22-24 [E][3] */
+    double *anthill_food;                     /* Anthill.food, anthill.py:27    [E] */
+    double *rock_centers, *rock_radii, *rock_weights;   /* circle_obstacles.py:22-24 [E][R][2],[E][R],[E][R] */
+    int64_t timestep;                         /* Environment.timestep, environment.py:27 (all envs in lockstep) */
+    int32_t rw_alias;                         /* reward still aliases Ants.holding, reward_custom.py:66-67 */
+    int32_t act_bool;                         /* phero_activation still has bool dtype, ants.py:83 */
+} AntsHostState;
+
+typedef struct AntsStats {
+    int64_t steps, updates, observations;
+    int64_t kernel_launches;                  /* kernels launched by this handle so far */
+    int64_t active_tiles;                     /* pheromone tiles processed by the last update (tile mode) */
+    int64_t total_tiles;
+    int64_t food_commits, absorb_events;      /* of the last step / update */
+    int64_t device_bytes;                     /* HBM held by the handle */
+} AntsStats;
+
+typedef struct AntsBatch AntsBatch;
+
+int ants_abi_version(void);
+const char *ants_last_error(void);
+
+/* Environment.__init__ + EnvironmentGenerator.generate's object construction, for E envs at once. */
+int ants_create(const AntsConfig *cfg, AntsBatch **out);
+int ants_destroy(AntsBatch *b);
+/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream */
+int ants_set_stream(AntsBatch *b, void *cuda_stream);
+int ants_synchronize(AntsBatch *b);
+
+/* state in / out (host pointers, dense layout).  Also how reference-generated maps reach the GPU. */
+int ants_import_state(AntsBatch *b, const AntsHostState *s);
+int ants_export_state(AntsBatch *b, AntsHostState *s);
+
+/* Ants.activate_all_pheromones, ants.py:86-87.  act: host [E][N][P] */
+int ants_activate_all_pheromones(AntsBatch *b, const double *act, int32_t is_bool);
+
+/* RLApi.observation(), RL_api.py:96-165 (side effect on reward state, as the reference).
+ * DEVICE pointers: obs f32 [E][N][S][S][C]; agent_state f32 [E][N][2]; state f32 [E][N][2+P] (may be NULL);
+ * reward f64 [E][N] (may be NULL). */
+int ants_observe(AntsBatch *b, float *d_obs, float *d_agent_state, float *d_state, double *d_reward);
+
+/* RLApi.step(rotation, on_off_pheromones), RL_api.py:168-204.  DEVICE pointers; d_rot / d_ph int8 [E][N] or
+ * NULL (= the reference's None: leave heading / activation unchanged).  *done (host) = max_time == timestep. */
+int ants_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs, float *d_agent_state,
+              double *d_reward, int32_t *done);
+
+/* Environment.update(), environment.py:42-47.  d_noise: DEVICE f64 [E][N] uniforms in [0,1) replacing the
+ * np.random.random draw of walls.py:28 (ant a consumes d_noise[e][a] iff it collides), or NULL for Philox. */
+int ants_update(AntsBatch *b, const double *d_noise);
+
+/* T x [step(actions_t); update()] with device-resident action tapes [T][E][N] and Philox noise; the outputs
+ * of the last step stay in the buffers.  Used by the throughput benchmark (no host round trip per step). */
+int ants_rollout(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape, int32_t n_steps,
+                 float *d_obs, float *d_agent_state, double *d_reward);
+
+/* Host-buffer variants (the reference-facing path: numpy in, numpy out).  Buffers obtained from
+ * ants_host_alloc are pinned and are copied to/from directly; other host memory is staged. */
+void *ants_host_alloc(uint64_t bytes);
+int ants_host_free(void *p);
+int ants_observe_host(AntsBatch *b, float *h_obs, float *h_agent_state, float *h_state, double *h_reward);
+int ants_step_host(AntsBatch *b, const int8_t *h_rot, const int8_t *h_ph, float *h_obs, float *h_agent_state,
+                   double *h_reward, int32_t *done);
+int ants_update_host(AntsBatch *b, const double *h_noise);
+
+int ants_get_stats(AntsBatch *b, AntsStats *out);
+/* time (ms) spent by the named kernel family since the last reset, measured with CUDA events on the handle's
+ * stream when profiling is enabled with ants_set_profiling(b, 1): "move", "food_commit", "perceive",
+ * "collide", "rocks", "evaporate", "deposit", "absorb" */
+int ants_set_profiling(AntsBatch *b, int32_t on);
+int ants_get_kernel_ms(AntsBatch *b, const char *name, double *ms, int64_t *launches);
+int ants_reset_kernel_ms(AntsBatch *b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANTSRL_B200_H */
