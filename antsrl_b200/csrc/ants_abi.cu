@@ -501,7 +501,7 @@ int ants_destroy(AntsBatch *b) {
 int ants_set_stream(AntsBatch *b, void *cuda_stream) {
     if (!b) return fail(ANTS_E_ARG, "null handle");
     CK(cudaStreamSynchronize(b->stream));
-    b->stream = cuda_stream ? (cudaStream_t)cuda_stream : b->own_stream;
+    b->stream = (cudaStream_t)cuda_stream;   // 0 = the legacy default stream (what torch uses by default)
     return ANTS_OK;
 }
 

@@ -117,7 +117,8 @@ const char *ants_last_error(void);
 /* Environment.__init__ + EnvironmentGenerator.generate's object construction, for E envs at once. */
 int ants_create(const AntsConfig *cfg, AntsBatch **out);
 int ants_destroy(AntsBatch *b);
-/* use an existing cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream */
+/* run on an existing cudaStream_t (e.g. torch's current stream; NULL = the legacy default stream).  A new
+ * handle runs on its own non-blocking stream until this is called. */
 int ants_set_stream(AntsBatch *b, void *cuda_stream);
 int ants_synchronize(AntsBatch *b);
 
