@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- ant-steps/s of the AntsRL environment step loop on B200 (contract in the task brief).
+
+One "step" = one pass of the hot path over the whole batch: RLApi.step(actions_t) followed by Environment.update()
+(obs, agent_state and reward materialised in HBM every step), on synthetic maps from the drop-in generator
+(env e <- seed 1000 + e, actions i.i.d. uniform rot in {-1,0,1}, ph in {0,1,2} from RandomState(12345), in-kernel
+Philox collision noise).  value = envs x ants x steps / time, whole job over all ranks (weak scaling: the per-GPU
+shard is fixed; N = 8 of the default workload is BASELINE.json configs[3]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg2] [--envs E] [--evap tiles|dense]
+    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+
+Extra JSON keys: roofline (dominant kernel vs measured HBM peak), cpu_baseline (oracle on host cores, bounded
+sample), e2e (host buffers through the C ABI, copies inside the timed region), kernels (per-family ms), clocks.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[3] sharded over 8 GPUs: 512 envs per GPU (cfg 4)
+    "cfg4": dict(w=1024, h=1024, n_ants=1024, n_phero=2, n_rocks=64, walls=(400, 5, 15), food=(320, 5, 10),
+                 envs_per_gpu=512, desc="1024x1024 map, 1024 ants/env, 64 rocks, 512 envs per GPU (4096 on 8)"),
+    # configs[2]
+    "cfg3": dict(w=256, h=256, n_ants=256, n_phero=2, n_rocks=0, walls=(16, 5, 15), food=(26, 5, 10),
+                 envs_per_gpu=4096, desc="256x256 map, 256 ants/env, 4096 envs per GPU"),
+    # configs[1]
+    "cfg2": dict(w=200, h=200, n_ants=50, n_phero=2, n_rocks=0, walls=(10, 5, 15), food=(20, 5, 10),
+                 envs_per_gpu=1024, desc="reference default 200x200 map, 50 ants/env, 1024 envs per GPU"),
+}
+
+
+def make_generator(wl, steps):
+    from antsrl_b200.generator import BatchedEnvironmentGenerator, CirclesGenerator
+    return BatchedEnvironmentGenerator(wl["w"], wl["h"], wl["n_ants"], wl["n_phero"], wl["n_rocks"],
+                                       CirclesGenerator(*wl["food"]), CirclesGenerator(*wl["walls"]),
+                                       max_steps=steps, seed_base=1000)
+
+
+def _gen_chunk(args):
+    wl, steps, first, n = args
+    g = make_generator(wl, steps)
+    return g.generate_states(n, first)
+
+
+def generate_states_parallel(wl, steps, first_env, n_envs):
+    nproc = max(1, min(os.cpu_count() or 1, 32, n_envs))
+    if nproc == 1 or n_envs < 8:
+        return _gen_chunk((wl, steps, first_env, n_envs))
+    per = (n_envs + nproc - 1) // nproc
+    jobs = [(wl, steps, first_env + s, min(per, n_envs - s)) for s in range(0, n_envs, per)]
+    with mp.get_context("fork").Pool(len(jobs)) as pool:
+        parts = pool.map(_gen_chunk, jobs)
+    return [s for p in parts for s in p]
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(r[col].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU baseline
+def _cpu_worker(args):
+    """One independent env per process: the oracle (numpy port of the reference loop, scipy convolve2d included)."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    wl, env_id, warm, steps = args
+    from oracle.antsrl_oracle import OracleEnv, philox_uniform
+    g = make_generator(wl, warm + steps + 1)
+    st = g.generate_states(1, env_id)[0]
+    env = OracleEnv(g.cfg, st)
+    env.activate_all_pheromones(np.ones((wl["n_ants"], wl["n_phero"])) * 10.0)
+    rs = np.random.RandomState(12345 + env_id)
+    env.observation()
+    t0 = None
+    for t in range(warm + steps):
+        if t == warm:
+            t0 = time.perf_counter()
+        rot = rs.randint(0, 3, wl["n_ants"]) - 1
+        ph = rs.randint(0, 3, wl["n_ants"])
+        env.step(rot, ph)
+        env.update(philox_uniform(0, env_id, t + 1, wl["n_ants"]))
+    return time.perf_counter() - t0
+
+
+def run_cpu_baseline(wl, warm, steps, procs=None):
+    procs = procs or (os.cpu_count() or 1)
+    t_wall = time.perf_counter()
+    with mp.get_context("fork").Pool(procs) as pool:
+        times = pool.map(_cpu_worker, [(wl, e, warm, steps) for e in range(procs)])
+    t_wall = time.perf_counter() - t_wall
+    worst = max(times)
+    value = procs * wl["n_ants"] * steps / worst
+    return {"value": value, "unit": "ant-steps/s", "cores": procs, "kind": "port",
+            "sample": "%d independent envs (one per process, %d processes) x %d timed steps of step()+update() after "
+                      "%d warm-up, %dx%d map, %d ants/env, oracle = numpy port of the reference loop incl. scipy "
+                      "convolve2d" % (procs, procs, steps, warm, wl["w"], wl["h"], wl["n_ants"]),
+            "ms_per_env_step": 1000.0 * float(np.mean(times)) / steps, "wall_s": t_wall}
+
+
+# ----------------------------------------------------------------------------------------------- roofline
+def algorithmic_bytes(fam, wl, E, C, stats):
+    """Algorithmic bytes per launch of one kernel family (stated in DESIGN.md)."""
+    N, P, W, H = wl["n_ants"], wl["n_phero"], wl["w"], wl["h"]
+    EN = E * N
+    if fam == "perceive":       # obs f32 + agent_state + reward out, 49-sample gathers, per-ant state
+        per_ant = 49 * C * 4 + 8 + 8 + 49 * (8 * P + 8 + 1 + 1 + 1) + 82
+        return EN * per_ant
+    if fam == "evaporate":
+        if stats.get("evap_mode") == "tiles":
+            return stats["active_tiles"] * 256 * (16 + 1)
+        return E * W * H * (16 * P + 1)
+    if fam == "move":
+        return EN * (48 + 1 + 8 + 2 + 32 + 1 + 8 * P + 2)
+    if fam == "collide":
+        return EN * (24 + 16 + 1 + 48 + 4 + 2)
+    if fam == "deposit":
+        return EN * (16 + 4 + 8 * P + 16)
+    if fam == "rocks":
+        return EN * (16 + 16 + 24) + E * wl["n_rocks"] * 48
+    return 0
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- main arms
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = WORKLOADS[args.workload]
+    E = args.envs or wl["envs_per_gpu"]
+    N = wl["n_ants"]
+    K, W_ = args.steps, args.warmup
+    total_steps = W_ + K + args.e2e_steps + K + 4
+
+    t_setup = time.perf_counter()
+    gen = make_generator(wl, total_steps + 10)
+    states = generate_states_parallel(wl, total_steps + 10, rank * E, E)
+    from antsrl_b200 import BatchedAnts
+    from antsrl_b200.generator import stack_states
+    batch = BatchedAnts(gen.cfg, E, device=local_rank, evap_mode=args.evap, rng_seed=20261018, env_id_base=rank * E)
+    batch.import_state(stack_states(states, gen.cfg["reward_kind"]))
+    del states
+    batch.activate_all_pheromones(np.ones((E, N, wl["n_phero"])) * 10.0)      # agent.initialize, collect_agent.py:100
+    C = len(gen.cfg["channels"])
+    rs = np.random.RandomState(12345 + rank)
+    n_tape = min(64, total_steps)
+    rot_tape = torch.from_numpy((rs.randint(0, 3, size=(n_tape, E, N)) - 1).astype(np.int8)).cuda()
+    ph_tape = torch.from_numpy(rs.randint(0, 3, size=(n_tape, E, N)).astype(np.int8)).cuda()
+    batch.observe()                                                           # main.py:88
+    t_setup = time.perf_counter() - t_setup
+
+    step_no = [0]
+
+    def one_step():
+        t = step_no[0] % n_tape
+        batch.step(rot_tape[t], ph_tape[t])
+        batch.update(None)
+        step_no[0] += 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W_):
+        one_step()
+    barrier()
+    launches0 = batch.stats()["kernel_launches"]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            one_step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = batch.stats()["kernel_launches"] - launches0
+    if world > 1:
+        tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    value = world * E * N * K / (ms / 1000.0)
+
+    # ---- per-kernel timing (same K steps, CUDA events around every launch on the launching stream)
+    batch.set_profiling(True)
+    batch.reset_kernel_ms()
+    barrier()
+    for _ in range(K):
+        one_step()
+    barrier()
+    kms = batch.kernel_ms()
+    st = batch.stats()
+    batch.set_profiling(False)
+    st["evap_mode"] = args.evap if gen.cfg["diffuse_factor"] == 0 else "dense"
+    total_k = sum(v[0] for v in kms.values()) or 1.0
+    kernels = {f: {"ms_per_step": v[0] / K, "launches_per_step": v[1] / K, "share": v[0] / total_k}
+               for f, v in kms.items() if v[1]}
+    dom = max(kernels, key=lambda f: kernels[f]["ms_per_step"])
+    peak, peak_src = load_peaks()
+    lps = max(kernels[dom]["launches_per_step"], 1e-9)
+    dom_ms_per_launch = kernels[dom]["ms_per_step"] / lps
+    abytes = algorithmic_bytes(dom, wl, E, C, st) / (lps if dom != "rocks" else 1.0)
+    if dom == "rocks":
+        dom_ms_per_launch = kernels[dom]["ms_per_step"]
+    achieved = abytes / (dom_ms_per_launch / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": abytes, "ms_per_launch": dom_ms_per_launch}
+    # whole-step view: algorithmic bytes of every family per step / step time
+    step_bytes = sum(algorithmic_bytes(f, wl, E, C, st) for f in kernels)
+    roofline["step_achieved"] = step_bytes / (ms / K / 1000.0) / 1e9
+    roofline["step_frac"] = roofline["step_achieved"] / peak
+    roofline["bytes_per_ant_step"] = step_bytes / (E * N)
+
+    # ---- end to end through the host-buffer C ABI (numpy in, numpy out; copies inside the timed region)
+    e2e = None
+    if args.e2e_steps > 0:
+        h_rot = batch.pinned("rot", (E, N), np.int8)
+        h_ph = batch.pinned("ph", (E, N), np.int8)
+        h_rot[:] = rot_tape[0].cpu().numpy()
+        h_ph[:] = ph_tape[0].cpu().numpy()
+        batch.step_host(h_rot, h_ph)
+        batch.update_host(None)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.e2e_steps):
+            batch.step_host(h_rot, h_ph)
+            batch.update_host(None)
+        ev1.record()
+        barrier()
+        e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1000.0)
+        if world > 1:
+            tmax = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            e_ms = float(tmax.item())
+        e2e = {"value": world * E * N * args.e2e_steps / (e_ms / 1000.0), "unit": "ant-steps/s",
+               "h2d_bytes_per_step": 2 * E * N, "d2h_bytes_per_step": E * N * (49 * C * 4 + 8 + 8),
+               "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
+               "api": "ants_step_host + ants_update_host (pinned numpy buffers)"}
+
+    # ---- optional end-of-rollout statistics reduction (the only collective of the design)
+    rollout_stats = None
+    fin = batch.export_state(keys=("anthill_food", "holding"))
+    local = torch.tensor([float(fin["anthill_food"].sum()), float(fin["holding"].sum())], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    rollout_stats = {"anthill_food_total": float(local[0].item()), "carried_food_total": float(local[1].item())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu_baseline(wl, 2, args.cpu_steps)
+
+    if rank == 0:
+        line = {
+            "metric": "ant-steps/sec (envs x ants x steps)", "value": value, "unit": "ant-steps/s",
+            "n_gpus": world, "steps": K, "warmup": W_, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "envs_per_gpu": E, "envs_total": E * world,
+                       "ants_per_env": N, "map": [wl["w"], wl["h"]], "pheromones": wl["n_phero"], "rocks": wl["n_rocks"],
+                       "obs": "7x7x%d f32" % C, "evaporation": st["evap_mode"],
+                       "precision": "f64 positions/fields, f32 obs", "l2": "state per GPU (%.1f GB) >> 126 MB L2"
+                       % (st["device_bytes"] / 1e9), "parallelism": "env-sharded x%d, no per-step collective" % world,
+                       "noise": "in-kernel Philox", "actions": "uniform random, pre-recorded tape on device"},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "kernels": kernels,
+            "e2e": e2e, "cpu_baseline": cpu, "rollout_stats": rollout_stats,
+            "active_tile_fraction": (st["active_tiles"] / st["total_tiles"]) if st["total_tiles"] else None,
+            "setup_s": t_setup,
+        }
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's own CPU algorithm for the path (oracle port; the Python reference cannot travel to the GPU
+    box), all host cores, one env per process; each bench step = one step()+update() of every env."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    procs = os.cpu_count() or 1
+    r = run_cpu_baseline(wl, args.warmup, args.steps, procs)
+    line = {"impl": "reference", "metric": "ant-steps/sec (envs x ants x steps)", "value": r["value"],
+            "unit": "ant-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_env_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "envs_total": procs,
+                       "ants_per_env": wl["n_ants"], "map": [wl["w"], wl["h"]]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "ant-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
+    ap.add_argument("--evap", default="tiles", choices=["tiles", "dense"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

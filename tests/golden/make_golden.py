@@ -93,3 +93,51 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Generator fixtures: the reference's EnvironmentGenerator.generate (environment_generator.py:52-106) with its
+# own CirclesGenerator (map_generators.py:28-46) for walls and food, for a few seeds / sizes.
+GEN_CASES = [
+    ("gen_200_s1000", dict(w=200, h=200, n_ants=50, n_rocks=0, walls=(10, 5, 15), food=(20, 5, 10), seed=1000)),
+    ("gen_200_s1001", dict(w=200, h=200, n_ants=50, n_rocks=0, walls=(10, 5, 15), food=(20, 5, 10), seed=1001)),
+    ("gen_96x64_s7", dict(w=96, h=64, n_ants=33, n_rocks=0, walls=(6, 3, 9), food=(8, 3, 6), seed=7)),
+    ("gen_rocks_s5", dict(w=128, h=128, n_ants=40, n_rocks=5, walls=(8, 5, 12), food=(10, 4, 8), seed=5)),
+]
+
+
+def make_generator_fixtures():
+    ref = ref_harness.load_reference()
+    for name, c in GEN_CASES:
+        ref.gen.n_rocks = c["n_rocks"]     # works around the bare name at environment_generator.py:83-84 (Q17)
+        reward = ref.rewards.All_Rewards(1, 2, 10, 1, 3)
+        api = ref.api.RLApi(reward, 1, 1, 40 / 180 * np.pi, 0.05, 0.5)
+        g = ref.gen.EnvironmentGenerator(c["w"], c["h"], c["n_ants"], 2, c["n_rocks"],
+                                         ref.maps.CirclesGenerator(*c["food"]), ref.maps.CirclesGenerator(*c["walls"]),
+                                         100, seed=c["seed"])
+        env = g.generate(api)
+        objs = {"pheros": []}
+        for o in env.objects:
+            n = type(o).__name__
+            if n == "Anthill": objs["anthill"] = o
+            elif n == "Walls": objs["walls"] = o
+            elif n == "Food": objs["food"] = o
+            elif n == "CircleObstacles": objs["rocks"] = o
+            elif n == "Ants": objs["ants"] = o
+            elif n == "Pheromone": objs["pheros"].append(o)
+        st = ref_harness.export_state(env, api, objs)
+        out = {"case_json": np.array(json.dumps(c)),
+               "channels": np.array([type(o).__name__ for o in api.perceived_objects])}
+        for k, v in st.items():
+            out["state_" + k] = np.asarray(v)
+        out["mask"] = api.perception_mask.astype(np.uint8)
+        out["fwd_delta"] = np.float64(api.perception_fwd_delta)
+        out["radius"] = np.int64(api.perception_radius)
+        path = os.path.join(HERE, name + ".npz")
+        np.savez_compressed(path, **out)
+        print("%-18s walls=%5d food=%5d  %6.1f KB" % (name, int(st["walls"].sum()), int(st["food"].sum()),
+                                                      os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "gen" in sys.argv[1:]):
+    make_generator_fixtures()
