@@ -69,7 +69,7 @@ struct AntsBatch {
     float *st_obs = nullptr, *st_as = nullptr, *st_state = nullptr;
     double *st_reward = nullptr, *st_noise = nullptr;
     uint32_t *h_counts = nullptr;   // pinned: commit_count, absorb_count readback
-    int perceive_smem = 0;
+    int perceive_smem = 0, perceive_layout = 0;
 };
 
 namespace {
@@ -183,8 +183,18 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
     int blocks = (int)cdiv(p.EN, ants::kPerceiveThreads);
     {
         LaunchScope ls(b, F_PERCEIVE);
-        ants::k_perceive<<<blocks, ants::kPerceiveThreads, b->perceive_smem, b->stream>>>(
-            p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias);
+        const int rounds = (p.S2 + 31) / 32;
+        const int layout = b->perceive_layout;
+#define ANTS_PERCEIVE(R, L)                                                                                \
+    ants::k_perceive<R, L><<<blocks, ants::kPerceiveThreads, b->perceive_smem, b->stream>>>(               \
+        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias)
+        if (rounds == 2 && layout == 1) ANTS_PERCEIVE(2, 1);
+        else if (rounds == 2 && layout == 2) ANTS_PERCEIVE(2, 2);
+        else if (rounds <= 1) ANTS_PERCEIVE(1, 0);
+        else if (rounds == 2) ANTS_PERCEIVE(2, 0);
+        else if (rounds <= 4) ANTS_PERCEIVE(4, 0);
+        else ANTS_PERCEIVE(8, 0);
+#undef ANTS_PERCEIVE
     }
     b->rw_alias = 0;
     return check_launch("k_perceive");
@@ -461,10 +471,22 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         p.samp_px = d_px; p.samp_py = d_py; p.mask = d_mask;
     }
     b->perceive_smem = (int)(ants::kPerceiveThreads * sizeof(ants::AntPrep) + 2 * p.S2 * sizeof(double) +
-                             (ants::kPerceiveThreads / 32) * p.S2 * p.C * sizeof(float) + p.S2 + 16);
+                             (ants::kPerceiveThreads / 32) * ants::kGroup * p.S2 * p.C * sizeof(float) + p.S2 + 16);
+    {   // straight-line perception code for the generator's default channel list (with / without rocks)
+        const int std6[6] = {ANTS_CH_ANTS, ANTS_CH_PHERO, ANTS_CH_PHERO, ANTS_CH_ANTHILL, ANTS_CH_WALLS, ANTS_CH_FOOD};
+        bool ok = p.P == 2 && (p.C == 6 || p.C == 7) && cfg->has_max_val;
+        for (int c = 0; ok && c < 6; ++c) ok = p.ch_kind[c] == std6[c];
+        ok = ok && p.ch_arg[1] == 0 && p.ch_arg[2] == 1;
+        if (ok && p.C == 7) ok = p.ch_kind[6] == ANTS_CH_ROCKS;
+        b->perceive_layout = ok ? (p.C == 7 ? 2 : 1) : 0;
+    }
     if (b->perceive_smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ants::k_perceive, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             b->perceive_smem);
+        cudaError_t e = cudaFuncSetAttribute(ants::k_perceive<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
         if (e != cudaSuccess) {
             ants_destroy(b);
             return fail(ANTS_E_CUDA, "perception window needs %d B of shared memory: %s", b->perceive_smem,

@@ -198,23 +198,50 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
 //            gathers from the meta / pheromone / food / wall planes, analytic anthill disc, exact rock test on
 //            the culled set, exploration count by ballot, mask, then the (S2 x C) f32 tile is staged in shared
 //            memory and written with coalesced stores.
-constexpr int kPerceiveThreads = 256;
+constexpr int kPerceiveThreads = 128;      // 4 warps = 128 consecutive ants per block
+constexpr int kGroup = 4;                   // ants staged per TMA bulk store: 4 * S2 * C * 4 B is a multiple of 16
 
 struct AntPrep {
     double xf, yf, ct, st;       // shifted position, cos/sin(theta + pi/2)
     double r_other, mult;        // reward terms without the exploration count; exploration multiplier
     unsigned long long rocks;    // candidate rocks
+    int e, pad;                  // environment of the ant
 };
 
+// wrap an integer sample coordinate onto the torus (np.mod on ints); the fast path covers |offset| < n
+__device__ __forceinline__ int wrap_coord(int v, int n) {
+    if (v < 0) v += n; else if (v >= n) v -= n;
+    return ((unsigned)v < (unsigned)n) ? v : imod(v, n);
+}
+
+// shared -> global bulk copy through the async proxy (TMA 1-D bulk store, SASS UBLKCP)
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+// LAYOUT 0: any perceived_objects list (switch per channel)
+// LAYOUT 1: the generator's default list [ants, phero0, phero1, anthill, walls, food] (environment_generator.py:64-99)
+// LAYOUT 2: the same plus rocks as 7th channel
+template <int ROUNDS, int LAYOUT>
 __global__ void __launch_bounds__(kPerceiveThreads)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    AntPrep *prep = reinterpret_cast<AntPrep *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int SC = p.S2 * p.C;
+    float *s_obs = reinterpret_cast<float *>(smem_raw);                        // [4 warps][kGroup][S2*C], 16 B aligned
+    AntPrep *prep = reinterpret_cast<AntPrep *>(s_obs + (kPerceiveThreads / 32) * kGroup * SC);
     double *s_px = reinterpret_cast<double *>(prep + kPerceiveThreads);
     double *s_py = s_px + p.S2;
-    float *s_obs = reinterpret_cast<float *>(s_py + p.S2);                     // [8 warps][S2*C]
-    uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_obs + (kPerceiveThreads / 32) * p.S2 * p.C);
+    uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_py + p.S2);
 
     const int tid = threadIdx.x;
     for (int k = tid; k < p.S2; k += kPerceiveThreads) {
@@ -234,6 +261,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             sincos(th, &s0, &c0);
             sincos(th + 3.141592653589793 * 0.5, &s1, &c1);                    // RL_api.py:101,107-108
             AntPrep q;
+            q.e = e; q.pad = 0;
             q.xf = x; q.yf = y;
             if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // :103-104
             q.ct = c1; q.st = s1;
@@ -282,51 +310,96 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             }
         }
     }
+    // which planes the configured channels read (block-uniform)
+    bool need_food = LAYOUT != 0, need_walls = LAYOUT != 0, need_meta = LAYOUT != 0 || p.explore_on != 0;
+    unsigned ph_need = LAYOUT != 0 ? 3u : 0u;
+    if (LAYOUT == 0) {
+        for (int c = 0; c < p.C; ++c) {
+            int kd = p.ch_kind[c];
+            need_food |= kd == 4; need_walls |= kd == 3; need_meta |= kd == 0;
+            if (kd == 1) ph_need |= 1u << p.ch_arg[c];
+        }
+    }
+    constexpr int NPH = LAYOUT != 0 ? 2 : 4;
+    const double inv_max = 1.0 / p.phero_max_val;   // obs is f32: x * (1/max) == x / max to well below 1e-5
+    const bool has_mask = p.has_mask != 0;
+    const bool explore_on = p.explore_on != 0;
     __syncthreads();
 
     // ---- phase B
     const int warp = tid >> 5, lane = tid & 31;
-    const int SC = p.S2 * p.C;
-    float *wobs = s_obs + warp * SC;
-    const int rounds = (p.S2 + 31) >> 5;
-    for (int k = 0; k < 32; ++k) {
-        int64_t i = base + warp * 32 + k;
-        if (i >= p.EN) break;
-        int e = (int)(i / p.N);
-        const AntPrep q = prep[warp * 32 + k];
-        const int64_t eoff = (int64_t)e * p.plane;
-        const int32_t *hl = p.hill + 4 * e;
-        int count = 0;
-        for (int rd = 0; rd < rounds; ++rd) {
-            int s = rd * 32 + lane;
-            bool valid = s < p.S2;
-            bool unexplored = false;
-            if (valid) {
+    float *wobs = s_obs + warp * kGroup * SC;
+    for (int g = 0; g < 32; g += kGroup) {
+        const int64_t i0 = base + warp * 32 + g;
+        if (i0 >= p.EN) break;
+        int n_in_group = (int)((p.EN - i0) < kGroup ? (p.EN - i0) : kGroup);
+        // the previous group's bulk store must have finished reading the staging tile
+        if (lane == 0) bulk_store_wait_read();
+        __syncwarp();
+        for (int j = 0; j < n_in_group; ++j) {
+            const int64_t i = i0 + j;
+            const AntPrep q = prep[warp * 32 + g + j];
+            const int e = q.e;
+            const int64_t eoff = (int64_t)e * p.plane;
+            const int32_t *hl = p.hill + 4 * e;
+            const double *foodp = p.food + eoff;
+            const uint8_t *wallp = p.walls + eoff;
+            uint32_t *metap = p.meta + eoff;
+            const double *php = p.phero + (int64_t)e * p.P * p.plane;
+            int ixs[ROUNDS], iys[ROUNDS], cell[ROUNDS];
+            uint32_t mt[ROUNDS];
+            double fd[ROUNDS], ph[ROUNDS][NPH];
+            uint8_t wl[ROUNDS];
+            // sample cells: round(rot(theta + pi/2) * offset + xy_f) mod (W, H), RL_api.py:110-119
+#pragma unroll
+            for (int rd = 0; rd < ROUNDS; ++rd) {
+                int s = rd * 32 + lane;
+                s = s < p.S2 ? s : 0;                                          // idle lanes shadow sample 0
                 double px = s_px[s], py = s_py[s];
-                double rx = q.ct * px - q.st * py;                             // RL_api.py:110-111
+                double rx = q.ct * px - q.st * py;
                 double ry = q.st * px + q.ct * py;
-                int ix = imod((int)rint(rx + q.xf), p.W);                      // :114-119 (half-to-even, Q11)
-                int iy = imod((int)rint(ry + q.yf), p.H);
-                int64_t cell = eoff + (int64_t)ix * p.Hp + iy;
-                uint32_t mt = p.meta[cell];
-                if (p.explore_on) {
-                    uint32_t eg = mt & 0xFFFFu;
+                ixs[rd] = wrap_coord(__double2int_rn(rx + q.xf), p.W);        // half-to-even, Q11
+                iys[rd] = wrap_coord(__double2int_rn(ry + q.yf), p.H);
+                cell[rd] = ixs[rd] * p.Hp + iys[rd];
+            }
+            // all gathers of this ant in flight together
+#pragma unroll
+            for (int rd = 0; rd < ROUNDS; ++rd) {
+                mt[rd] = need_meta ? metap[cell[rd]] : 0u;
+                fd[rd] = need_food ? foodp[cell[rd]] : 0.0;
+                wl[rd] = need_walls ? wallp[cell[rd]] : (uint8_t)0;
+#pragma unroll
+                for (int kp = 0; kp < NPH; ++kp)
+                    ph[rd][kp] = ((ph_need >> kp) & 1u) ? php[(int64_t)kp * p.plane + cell[rd]] : 0.0;
+            }
+            int count = 0;
+#pragma unroll
+            for (int rd = 0; rd < ROUNDS; ++rd) {
+                int s = rd * 32 + lane;
+                bool valid = s < p.S2;
+                bool unexplored = false;
+                if (explore_on) {
+                    uint32_t eg = mt[rd] & 0xFFFFu;
                     unexplored = (eg == 0u) || (eg == obs_gen);                // gather-before-scatter, Q7
-                    if (eg == 0u) reinterpret_cast<uint16_t *>(p.meta + cell)[0] = (uint16_t)obs_gen;
+                    if (valid && eg == 0u) reinterpret_cast<uint16_t *>(metap + cell[rd])[0] = (uint16_t)obs_gen;
                 }
-                bool vis = s_mask[s] != 0;
-                float *o = wobs + s * p.C;
-                for (int c = 0; c < p.C; ++c) {
-                    double v;
-                    switch (p.ch_kind[c]) {
-                        case 0: v = ((mt >> 16) == occ_gen) ? 1.0 : 0.0; break;                       // :136-142
-                        case 1: v = p.phero[((int64_t)e * p.P + p.ch_arg[c]) * p.plane + (cell - eoff)]
-                                    / p.phero_max_val; break;                                         // :124-125
-                        case 2: v = in_hill(hl, ix, iy) ? 1.0 : 0.0; break;                           // :130-131
-                        case 3: v = p.walls[cell] ? 1.0 : 0.0; break;                                 // :128-129
-                        case 4: v = p.food[cell]; break;                                              // :126-127
-                        default: {                                                                    // :132-135
-                            v = 0.0;
+                count += __popc(__ballot_sync(0xffffffffu, valid && unexplored));
+                if (!valid) continue;
+                const bool vis = s_mask[s] != 0;
+                float *o = wobs + (j * p.S2 + s) * p.C;
+                const int ix = ixs[rd], iy = iys[rd];
+                if (LAYOUT != 0) {
+                    if (vis) {
+                        double p0 = ph[rd][0] * inv_max, p1 = ph[rd][1] * inv_max, f = fd[rd];
+                        if (has_mask) { p0 = (p0 + 1.0) - 1.0; p1 = (p1 + 1.0) - 1.0; f = (f + 1.0) - 1.0; }   // :147-148
+                        o[0] = ((mt[rd] >> 16) == occ_gen) ? 1.f : 0.f;                               // :136-142
+                        o[1] = (float)p0;                                                             // :124-125
+                        o[2] = (float)p1;
+                        o[3] = in_hill(hl, ix, iy) ? 1.f : 0.f;                                       // :130-131
+                        o[4] = wl[rd] ? 1.f : 0.f;                                                    // :128-129
+                        o[5] = (float)f;                                                              // :126-127
+                        if (LAYOUT == 2) {                                                            // :132-135
+                            float rv = 0.f;
                             unsigned long long rm = q.rocks;
                             const double *rc = p.rock_c + (int64_t)e * p.R * 2;
                             const double *rr = p.rock_rad + (int64_t)e * p.R;
@@ -334,41 +407,81 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                                 int r = __ffsll((long long)rm) - 1;
                                 rm &= rm - 1;
                                 double ddx = (double)ix - rc[2 * r], ddy = (double)iy - rc[2 * r + 1];
-                                if (sqrt(ddx * ddx + ddy * ddy) < rr[r]) { v = 1.0; break; }
+                                if (sqrt(ddx * ddx + ddy * ddy) < rr[r]) { rv = 1.f; break; }
+                            }
+                            o[6] = rv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < (LAYOUT == 2 ? 7 : 6); ++c) o[c] = -1.f;
+                    }
+                } else {
+                    for (int c = 0; c < p.C; ++c) {
+                        double v;
+                        switch (p.ch_kind[c]) {
+                            case 0: v = ((mt[rd] >> 16) == occ_gen) ? 1.0 : 0.0; break;
+                            case 1: {
+                                int a = p.ch_arg[c];
+                                double pv = a == 0 ? ph[rd][0] : a == 1 ? ph[rd][1] : a == 2 ? ph[rd][NPH > 2 ? 2 : 0]
+                                                                                          : ph[rd][NPH > 3 ? 3 : 0];
+                                v = pv * inv_max;
+                                break;
+                            }
+                            case 2: v = in_hill(hl, ix, iy) ? 1.0 : 0.0; break;
+                            case 3: v = wl[rd] ? 1.0 : 0.0; break;
+                            case 4: v = fd[rd]; break;
+                            default: {
+                                v = 0.0;
+                                unsigned long long rm = q.rocks;
+                                const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+                                const double *rr = p.rock_rad + (int64_t)e * p.R;
+                                while (rm) {
+                                    int r = __ffsll((long long)rm) - 1;
+                                    rm &= rm - 1;
+                                    double ddx = (double)ix - rc[2 * r], ddy = (double)iy - rc[2 * r + 1];
+                                    if (sqrt(ddx * ddx + ddy * ddy) < rr[r]) { v = 1.0; break; }
+                                }
                             }
                         }
+                        if (has_mask) v = vis ? (v + 1.0) - 1.0 : -1.0;        // :147-148 mask*(p+1)-1
+                        o[c] = (float)v;
                     }
-                    if (p.has_mask) v = vis ? (v + 1.0) - 1.0 : -1.0;          // :147-148 mask*(p+1)-1
-                    o[c] = (float)v;
                 }
             }
-            count += __popc(__ballot_sync(0xffffffffu, valid && unexplored));
-        }
-        __syncwarp();
-        // coalesced copy of the (S2 x C) tile
-        float *dst = obs + i * SC;
-        for (int t = lane; t < SC; t += 32) dst[t] = wobs[t];
-        if (lane == 0) {
-            double reward;
-            if (p.reward_kind == 1) {
-                reward = (double)count / 10.0;                                 // reward_custom.py:19
-            } else if (p.reward_kind == 0) {
-                reward = 0.0;
-                if (p.explore_on) reward += ((double)count / 10.0) * q.mult;   // :89-94
-                reward += q.r_other;                                           // :106
-            } else {
-                reward = q.r_other;
-            }
-            p.rewards[i] = reward;
-            if (reward_out != nullptr) reward_out[i] = reward;
-            if (is_step) {                                                     // ants.py:119-121 (Q16)
-                int rs = p.reward_state[i];
-                rs += ((reward - p.reward_threshold) > 0.0) ? 255 : 0;
-                p.reward_state[i] = (uint8_t)(rs > 255 ? 255 : rs);
+            if (lane == 0) {
+                double reward;
+                if (p.reward_kind == 1) {
+                    reward = (double)count / 10.0;                             // reward_custom.py:19
+                } else if (p.reward_kind == 0) {
+                    reward = 0.0;
+                    if (explore_on) reward += ((double)count / 10.0) * q.mult; // :89-94
+                    reward += q.r_other;                                       // :106
+                } else {
+                    reward = q.r_other;
+                }
+                p.rewards[i] = reward;
+                if (reward_out != nullptr) reward_out[i] = reward;
+                if (is_step) {                                                 // ants.py:119-121 (Q16)
+                    int rs = p.reward_state[i];
+                    rs += ((reward - p.reward_threshold) > 0.0) ? 255 : 0;
+                    p.reward_state[i] = (uint8_t)(rs > 255 ? 255 : rs);
+                }
             }
         }
-        __syncwarp();
+        // flush the staged (n_in_group x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
+        float *dst = obs + i0 * SC;
+        const uint32_t bytes = (uint32_t)(n_in_group * SC * 4);
+        if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) bulk_store_s2g(dst, wobs, bytes);
+        } else {
+            __syncwarp();
+            for (int t = lane; t < n_in_group * SC; t += 32) dst[t] = wobs[t];
+            __syncwarp();
+        }
     }
+    if (lane == 0) bulk_store_wait_read();   // smem must stay valid until the last bulk store has read it
 }
 
 // ------------------------------------------------------------------------------------------------ update, ants side
