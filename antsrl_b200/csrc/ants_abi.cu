@@ -9,6 +9,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -69,7 +70,7 @@ struct AntsBatch {
     float *st_obs = nullptr, *st_as = nullptr, *st_state = nullptr;
     double *st_reward = nullptr, *st_noise = nullptr;
     uint32_t *h_counts = nullptr;   // pinned: commit_count, absorb_count readback
-    int perceive_smem = 0, perceive_layout = 0;
+    int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128;
 };
 
 namespace {
@@ -180,20 +181,26 @@ uint32_t next_owner_phase(AntsBatch *b) {
 int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward, int is_step) {
     const Params &p = b->p;
     uint32_t og = next_obs_gen(b);
-    int blocks = (int)cdiv(p.EN, ants::kPerceiveThreads);
+    int blocks = 0;
     {
         LaunchScope ls(b, F_PERCEIVE);
-        const int rounds = (p.S2 + 31) / 32;
         const int layout = b->perceive_layout;
-#define ANTS_PERCEIVE(R, L)                                                                                \
-    ants::k_perceive<R, L><<<blocks, ants::kPerceiveThreads, b->perceive_smem, b->stream>>>(               \
-        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias)
-        if (rounds == 2 && layout == 1) ANTS_PERCEIVE(2, 1);
-        else if (rounds == 2 && layout == 2) ANTS_PERCEIVE(2, 2);
-        else if (rounds <= 1) ANTS_PERCEIVE(1, 0);
-        else if (rounds == 2) ANTS_PERCEIVE(2, 0);
-        else if (rounds <= 4) ANTS_PERCEIVE(4, 0);
-        else ANTS_PERCEIVE(8, 0);
+        const uint32_t magic = (1u << 20) / (uint32_t)p.S2 + 1u;   // f / S2 == (f * magic) >> 20 for f < 2048
+        const int threads = b->perceive_threads;
+        static const int dbg = getenv("ANTS_DBG") ? atoi(getenv("ANTS_DBG")) : 0;
+        blocks = (int)cdiv(p.EN, threads);
+#define ANTS_PERCEIVE(L, SF)                                                                               \
+    ants::k_perceive<L, SF><<<blocks, threads, b->perceive_smem, b->stream>>>(                             \
+        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, dbg)
+        if (p.S == 7) {
+            if (layout == 1) ANTS_PERCEIVE(1, 7);
+            else if (layout == 2) ANTS_PERCEIVE(2, 7);
+            else ANTS_PERCEIVE(0, 7);
+        } else {
+            if (layout == 1) ANTS_PERCEIVE(1, 0);
+            else if (layout == 2) ANTS_PERCEIVE(2, 0);
+            else ANTS_PERCEIVE(0, 0);
+        }
 #undef ANTS_PERCEIVE
     }
     b->rw_alias = 0;
@@ -445,6 +452,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.hill_food, (int64_t)p.E));
     A(dev_alloc(b, &p.rock_c, (int64_t)p.E * p.R * 2)); A(dev_alloc(b, &p.rock_rad, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.rock_w, (int64_t)p.E * p.R));
+    A(dev_alloc(b, &p.rock_grid, (int64_t)p.E * cdiv(p.W, 32) * cdiv(p.H, 32)));
     A(dev_alloc(b, &p.food_delta, EN, false));
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
     A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
@@ -470,8 +478,22 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         cudaMemcpy(d_mask, mk.data(), p.S2, cudaMemcpyHostToDevice);
         p.samp_px = d_px; p.samp_py = d_py; p.mask = d_mask;
     }
-    b->perceive_smem = (int)(ants::kPerceiveThreads * sizeof(ants::AntPrep) + 2 * p.S2 * sizeof(double) +
-                             (ants::kPerceiveThreads / 32) * ants::kGroup * p.S2 * p.C * sizeof(float) + p.S2 + 16);
+    {   // ants per staged chunk: as many as fit ~12 KB per warp, keeping the chunk a multiple of 16 B and the
+        // flat sample index below 2048 (magic division); threads per block: as many warps as fit ~100 KB
+        int sc_bytes = p.S2 * p.C * 4;
+        int g = ants::kMaxGroup;
+        while (g > 1 && (g * sc_bytes > 6 * 1024 || g * p.S2 >= 2048)) g >>= 1;
+        b->perceive_group = g;
+        int threads = ants::kPerceiveThreads;
+        auto smem_for = [&](int t) {
+            return (int)((t / 32) * g * sc_bytes + (t * p.S2 + 1) * 4 + t * sizeof(ants::AntPrep) + p.S * 8 + t * 4 +
+                         p.S2 + 64);
+        };
+        while (threads > 32 && smem_for(threads) > 100 * 1024) threads >>= 1;
+        b->perceive_threads = threads;
+        b->perceive_smem = smem_for(threads);
+        if (const char *x = getenv("ANTS_PERCEIVE_EXTRA_SMEM")) b->perceive_smem += atoi(x);   // occupancy experiments
+    }
     {   // straight-line perception code for the generator's default channel list (with / without rocks)
         const int std6[6] = {ANTS_CH_ANTS, ANTS_CH_PHERO, ANTS_CH_PHERO, ANTS_CH_ANTHILL, ANTS_CH_WALLS, ANTS_CH_FOOD};
         bool ok = p.P == 2 && (p.C == 6 || p.C == 7) && cfg->has_max_val;
@@ -481,12 +503,12 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         b->perceive_layout = ok ? (p.C == 7 ? 2 : 1) : 0;
     }
     if (b->perceive_smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ants::k_perceive<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(ants::k_perceive<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
+        cudaError_t e = cudaSuccess;
+        const void *fns[6] = {(const void *)ants::k_perceive<0, 0>, (const void *)ants::k_perceive<1, 0>,
+                              (const void *)ants::k_perceive<2, 0>, (const void *)ants::k_perceive<0, 7>,
+                              (const void *)ants::k_perceive<1, 7>, (const void *)ants::k_perceive<2, 7>};
+        for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+            e = cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
         if (e != cudaSuccess) {
             ants_destroy(b);
             return fail(ANTS_E_CUDA, "perception window needs %d B of shared memory: %s", b->perceive_smem,
@@ -613,6 +635,8 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         if (s->rock_centers) CK(cudaMemcpyAsync(p.rock_c, s->rock_centers, (size_t)p.E * p.R * 16, cudaMemcpyHostToDevice, st));
         if (s->rock_radii) CK(cudaMemcpyAsync(p.rock_rad, s->rock_radii, (size_t)p.E * p.R * 8, cudaMemcpyHostToDevice, st));
         if (s->rock_weights) CK(cudaMemcpyAsync(p.rock_w, s->rock_weights, (size_t)p.E * p.R * 8, cudaMemcpyHostToDevice, st));
+        ants::k_rock_grid_build<<<p.E, 128, 0, st>>>(p);
+        TRY(check_launch("k_rock_grid_build"));
     }
     CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(p.absorb_count, 0, sizeof(uint32_t), st));

@@ -51,6 +51,7 @@ struct Params {
     int32_t *hill;                         // [E][4] = x, y, r, r*r
     double *hill_food;                     // [E]
     double *rock_c, *rock_rad, *rock_w;    // [E][R][2], [E][R], [E][R]
+    unsigned long long *rock_grid;         // [E][ceil(W/32)][ceil(H/32)] bitmask of rocks near each 32x32 block
     const double *samp_px, *samp_py;       // [S2] perception_coords * DELTA (RL_api.py:92-93)
     const uint8_t *mask;                   // [S2]
     // scratch
@@ -199,12 +200,12 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
 //            the culled set, exploration count by ballot, mask, then the (S2 x C) f32 tile is staged in shared
 //            memory and written with coalesced stores.
 constexpr int kPerceiveThreads = 128;      // 4 warps = 128 consecutive ants per block
-constexpr int kGroup = 4;                   // ants staged per TMA bulk store: 4 * S2 * C * 4 B is a multiple of 16
+constexpr int kMaxGroup = 8;                // ants staged per TMA bulk store (4 or 8 ants: bytes are a multiple of 16)
+constexpr int kGridShift = 5;               // rock grid cell = 32 x 32 map cells
 
 struct AntPrep {
-    double xf, yf, ct, st;       // shifted position, cos/sin(theta + pi/2)
     double r_other, mult;        // reward terms without the exploration count; exploration multiplier
-    unsigned long long rocks;    // candidate rocks
+    unsigned long long rocks;    // candidate rocks (from the rock grid)
     int e, pad;                  // environment of the ant
 };
 
@@ -228,54 +229,129 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 }
 
+// Candidate rocks of a point: every rock whose (radius + reach) box overlaps the point's 32x32 grid cell was
+// OR-ed into that cell by rock_grid_mark, so one 8-byte load replaces a loop over all rocks.
+__device__ __forceinline__ unsigned long long rock_candidates(const Params &p, int e, double x, double y) {
+    const int gw = (p.W + 31) >> kGridShift, gh = (p.H + 31) >> kGridShift;
+    int gx = cell_of(pymod(x, (double)p.W), p.W) >> kGridShift;
+    int gy = cell_of(pymod(y, (double)p.H), p.H) >> kGridShift;
+    return p.rock_grid[((int64_t)e * gw + gx) * gh + gy];
+}
+__device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad) {
+    const int gw = (p.W + 31) >> kGridShift, gh = (p.H + 31) >> kGridShift;
+    const double L = rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
+    unsigned long long *g = p.rock_grid + (int64_t)e * gw * gh;
+    const unsigned long long bit = 1ull << r;
+    // sample the box [c - L, c + L] every <= 32 cells (and at its far edge): hits every grid cell it overlaps
+    for (double ox = -L;; ox += 32.0) {
+        if (ox > L) ox = L;
+        int gx = cell_of(pymod(cx + ox, (double)p.W), p.W) >> kGridShift;
+        for (double oy = -L;; oy += 32.0) {
+            if (oy > L) oy = L;
+            int gy = cell_of(pymod(cy + oy, (double)p.H), p.H) >> kGridShift;
+            atomicOr(g + gx * gh + gy, bit);
+            if (oy >= L) break;
+        }
+        if (ox >= L) break;
+    }
+}
+
 // LAYOUT 0: any perceived_objects list (switch per channel)
 // LAYOUT 1: the generator's default list [ants, phero0, phero1, anthill, walls, food] (environment_generator.py:64-99)
 // LAYOUT 2: the same plus rocks as 7th channel
-template <int ROUNDS, int LAYOUT>
+// SFIX: perception window side known at compile time (7 = the default 7x7 window), 0 = run-time side.
+//
+// Block = blockDim.x threads = as many consecutive ants; warp w owns ants [32w, 32w+32) from start to end (no
+// block barrier after the table load).
+//   phase A (thread per ant): f64 trigonometry of the rotated sampling frame; ALL sample cells of the ant,
+//            round(rot(theta + pi/2) * offset + xy_f) mod (W,H), with the products cos*offset / sin*offset
+//            computed once per row / column, packed (x << 16 | y) into shared memory; reward terms that do not
+//            need the exploration count; agent_state / state outputs; candidate rocks from the rock grid.
+//   phase B (warp, flat sample index): the warp walks its ants in chunks of `group` ants; the chunk's
+//            group*S2 samples are spread over the 32 lanes and processed in batches of U lane-slots whose
+//            gathers (meta / pheromone / food / walls planes) are all issued before any is consumed; analytic
+//            anthill disc, exact rock test on the candidates; exploration counts per ant with match_any + shared
+//            atomics; the chunk's (group x S2 x C) f32 tile is staged in shared memory and leaves with ONE TMA
+//            bulk store.
+//   phase C (thread per ant): reward epilogue and Ants.give_reward.
+template <int LAYOUT, int SFIX>
 __global__ void __launch_bounds__(kPerceiveThreads)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
-           double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias) {
+           double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
+           int group, uint32_t s2_magic, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int SC = p.S2 * p.C;
-    float *s_obs = reinterpret_cast<float *>(smem_raw);                        // [4 warps][kGroup][S2*C], 16 B aligned
-    AntPrep *prep = reinterpret_cast<AntPrep *>(s_obs + (kPerceiveThreads / 32) * kGroup * SC);
-    double *s_px = reinterpret_cast<double *>(prep + kPerceiveThreads);
-    double *s_py = s_px + p.S2;
-    uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_py + p.S2);
+    const int S = SFIX ? SFIX : p.S;
+    const int S2 = S * S, C = p.C;
+    const int SC = S2 * C;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+    float *s_obs = reinterpret_cast<float *>(smem_raw);                        // [warps][group][S2*C], 16 B aligned
+    uint32_t *s_cell = reinterpret_cast<uint32_t *>(s_obs + nwarps * group * SC);   // [threads][S2]
+    AntPrep *prep = reinterpret_cast<AntPrep *>(s_cell + nthreads * S2 + ((nthreads * S2) & 1));
+    double *s_off = reinterpret_cast<double *>(prep + nthreads);               // [S] = (k - r) * DELTA
+    int *s_cnt = reinterpret_cast<int *>(s_off + S);
+    uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cnt + nthreads);
 
     const int tid = threadIdx.x;
-    for (int k = tid; k < p.S2; k += kPerceiveThreads) {
-        s_px[k] = p.samp_px[k];
-        s_py[k] = p.samp_py[k];
-        s_mask[k] = p.has_mask ? p.mask[k] : 1;
-    }
-    const int64_t base = (int64_t)blockIdx.x * kPerceiveThreads;
+    for (int k = tid; k < S2; k += nthreads) s_mask[k] = p.has_mask ? p.mask[k] : 1;
+    for (int k = tid; k < S; k += nthreads) s_off[k] = p.samp_px[k];          // row 0 of perception_coords[..., 0]
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * nthreads;
 
     // ---- phase A
     {
-        int64_t i = base + tid;
+        const int64_t i = base + tid;
+        s_cnt[tid] = 0;
         if (i < p.EN) {
-            int e = (int)(i / p.N);
-            double x = p.x[i], y = p.y[i], th = p.theta[i], hold = p.holding[i];
-            double s0, c0, s1, c1;
+            const int e = (int)(i / p.N);
+            const double x = p.x[i], y = p.y[i], th = p.theta[i], hold = p.holding[i];
+            double s0, c0, st, ct;
             sincos(th, &s0, &c0);
-            sincos(th + 3.141592653589793 * 0.5, &s1, &c1);                    // RL_api.py:101,107-108
+            sincos(th + 3.141592653589793 * 0.5, &st, &ct);                    // RL_api.py:101,107-108
+            double xf = x, yf = y;
+            if (p.fwd_delta != 0.0) { xf = x + c0 * p.fwd_delta; yf = y + s0 * p.fwd_delta; }   // :103-104
+            // sample cells, RL_api.py:110-119: rel_x = cos*X - sin*Y, rel_y = sin*X + cos*Y with X = off[j],
+            // Y = off[i]; abs = round_half_even(rel + xy_f) mod (W, H)
+            uint32_t *mycell = s_cell + tid * S2;
+            if (SFIX) {
+                double cX[SFIX ? SFIX : 1], sX[SFIX ? SFIX : 1];
+#pragma unroll
+                for (int j = 0; j < SFIX; ++j) { const double o = s_off[j]; cX[j] = ct * o; sX[j] = st * o; }
+#pragma unroll
+                for (int ii = 0; ii < SFIX; ++ii) {
+                    const double o = s_off[ii];
+                    const double sY = st * o, cY = ct * o;
+#pragma unroll
+                    for (int j = 0; j < SFIX; ++j) {
+                        const int ix = wrap_coord(__double2int_rn((cX[j] - sY) + xf), p.W);
+                        const int iy = wrap_coord(__double2int_rn((sX[j] + cY) + yf), p.H);
+                        mycell[ii * SFIX + j] = ((uint32_t)ix << 16) | (uint32_t)iy;
+                    }
+                }
+            } else {
+                for (int ii = 0; ii < S; ++ii) {
+                    const double oy = s_off[ii];
+                    const double sY = st * oy, cY = ct * oy;
+                    for (int j = 0; j < S; ++j) {
+                        const double ox = s_off[j];
+                        const int ix = wrap_coord(__double2int_rn((ct * ox - sY) + xf), p.W);
+                        const int iy = wrap_coord(__double2int_rn((st * ox + cY) + yf), p.H);
+                        mycell[ii * S + j] = ((uint32_t)ix << 16) | (uint32_t)iy;
+                    }
+                }
+            }
             AntPrep q;
             q.e = e; q.pad = 0;
-            q.xf = x; q.yf = y;
-            if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // :103-104
-            q.ct = c1; q.st = s1;
             // reward.observation, reward_custom.py
-            double hprev = rw_alias ? hold : p.rw_holding_prev[i];             // Q18
-            double d = hold - hprev;
+            const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
+            const double d = hold - hprev;
             q.r_other = 0.0; q.mult = 1.0;
             if (p.reward_kind == 0) {                                          // All_Rewards, :79-106
-                double r_food = d < 0.0 ? 0.0 : d;
-                double r_hill = d < 0.0 ? 1.0 : 0.0;
+                const double r_food = d < 0.0 ? 0.0 : d;
+                const double r_hill = d < 0.0 ? 1.0 : 0.0;
                 const int32_t *hl = p.hill + 4 * e;
-                double ddx = x - (double)hl[0], ddy = y - (double)hl[1];
-                double nd = sqrt(ddx * ddx + ddy * ddy);
-                double heading = (p.rw_prev_dist[i] > nd && hold > 0.0) ? 0.1 : 0.0;
+                const double ddx = x - (double)hl[0], ddy = y - (double)hl[1];
+                const double nd = sqrt(ddx * ddx + ddy * ddy);
+                const double heading = (p.rw_prev_dist[i] > nd && hold > 0.0) ? 0.1 : 0.0;
                 p.rw_prev_dist[i] = nd;
                 q.r_other = r_food * p.f_food + r_hill * p.f_anthill + heading * p.f_heading;
                 q.mult = (hold == 0.0) ? p.f_explore : p.f_explore_hold;
@@ -284,21 +360,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 q.r_other = d < 0.0 ? 10.0 : d;
                 p.rw_holding_prev[i] = hold;
             }
-            // rocks that can touch this ant's sampling window (wrapped distance: samples wrap, rocks do not)
-            q.rocks = 0ull;
-            if (p.R > 0) {
-                double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.5;
-                const double *rc = p.rock_c + (int64_t)e * p.R * 2;
-                const double *rr = p.rock_rad + (int64_t)e * p.R;
-                double cx = pymod(q.xf, (double)p.W), cy = pymod(q.yf, (double)p.H);
-                for (int r = 0; r < p.R; ++r) {
-                    double ddx = fabs(rc[2 * r] - cx), ddy = fabs(rc[2 * r + 1] - cy);
-                    ddx = fmin(ddx, fabs((double)p.W - ddx));
-                    ddy = fmin(ddy, fabs((double)p.H - ddy));
-                    double lim = rr[r] + reach;
-                    if (ddx * ddx + ddy * ddy <= lim * lim) q.rocks |= 1ull << r;
-                }
-            }
+            q.rocks = (p.R > 0 && (LAYOUT == 2 || LAYOUT == 0)) ? rock_candidates(p, e, xf, yf) : 0ull;
             prep[tid] = q;
             agent_state[2 * i] = (float)hold;                                  // RL_api.py:160-162
             agent_state[2 * i + 1] = (float)p.seed[i];
@@ -313,8 +375,10 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
     // which planes the configured channels read (block-uniform)
     bool need_food = LAYOUT != 0, need_walls = LAYOUT != 0, need_meta = LAYOUT != 0 || p.explore_on != 0;
     unsigned ph_need = LAYOUT != 0 ? 3u : 0u;
+    if (dbg & 1) { need_food = need_walls = need_meta = false; ph_need = 0; }
+    if (dbg & 16) { need_food = need_walls = false; ph_need = 0; }
     if (LAYOUT == 0) {
-        for (int c = 0; c < p.C; ++c) {
+        for (int c = 0; c < C; ++c) {
             int kd = p.ch_kind[c];
             need_food |= kd == 4; need_walls |= kd == 3; need_meta |= kd == 0;
             if (kd == 1) ph_need |= 1u << p.ch_arg[c];
@@ -324,83 +388,83 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
     const double inv_max = 1.0 / p.phero_max_val;   // obs is f32: x * (1/max) == x / max to well below 1e-5
     const bool has_mask = p.has_mask != 0;
     const bool explore_on = p.explore_on != 0;
-    __syncthreads();
+    __syncwarp();
 
     // ---- phase B
     const int warp = tid >> 5, lane = tid & 31;
-    float *wobs = s_obs + warp * kGroup * SC;
-    for (int g = 0; g < 32; g += kGroup) {
+    float *wobs = s_obs + warp * group * SC;
+    const uint32_t *wcell = s_cell + warp * 32 * S2;
+    const AntPrep *wprep = prep + warp * 32;
+    for (int g = 0; g < 32; g += group) {
+        if (dbg & 8) break;
         const int64_t i0 = base + warp * 32 + g;
         if (i0 >= p.EN) break;
-        int n_in_group = (int)((p.EN - i0) < kGroup ? (p.EN - i0) : kGroup);
-        // the previous group's bulk store must have finished reading the staging tile
+        int n_in = 32 - g < group ? 32 - g : group;
+        if (p.EN - i0 < n_in) n_in = (int)(p.EN - i0);
+        const int nsamp = n_in * S2;
+        // the previous chunk's bulk store must have finished reading the staging tile
         if (lane == 0) bulk_store_wait_read();
         __syncwarp();
-        for (int j = 0; j < n_in_group; ++j) {
-            const int64_t i = i0 + j;
-            const AntPrep q = prep[warp * 32 + g + j];
-            const int e = q.e;
-            const int64_t eoff = (int64_t)e * p.plane;
-            const int32_t *hl = p.hill + 4 * e;
-            const double *foodp = p.food + eoff;
-            const uint8_t *wallp = p.walls + eoff;
-            uint32_t *metap = p.meta + eoff;
-            const double *php = p.phero + (int64_t)e * p.P * p.plane;
-            int ixs[ROUNDS], iys[ROUNDS], cell[ROUNDS];
-            uint32_t mt[ROUNDS];
-            double fd[ROUNDS], ph[ROUNDS][NPH];
-            uint8_t wl[ROUNDS];
-            // sample cells: round(rot(theta + pi/2) * offset + xy_f) mod (W, H), RL_api.py:110-119
+        const int iters = (nsamp + 31) >> 5;
+        constexpr int U = 4;                       // lane-slots per batch: all gathers of a batch are in flight together
+        for (int it0 = 0; it0 < iters; it0 += U) {
+            int fs[U], es[U];
+            uint32_t cw[U], mt[U];
+            double fd[U], ph[U][NPH];
+            uint8_t wl[U];
 #pragma unroll
-            for (int rd = 0; rd < ROUNDS; ++rd) {
-                int s = rd * 32 + lane;
-                s = s < p.S2 ? s : 0;                                          // idle lanes shadow sample 0
-                double px = s_px[s], py = s_py[s];
-                double rx = q.ct * px - q.st * py;
-                double ry = q.st * px + q.ct * py;
-                ixs[rd] = wrap_coord(__double2int_rn(rx + q.xf), p.W);        // half-to-even, Q11
-                iys[rd] = wrap_coord(__double2int_rn(ry + q.yf), p.H);
-                cell[rd] = ixs[rd] * p.Hp + iys[rd];
+            for (int u = 0; u < U; ++u) {
+                if (it0 + u >= iters) break;                                   // warp-uniform
+                const int f_raw = (it0 + u) * 32 + lane;
+                const int f = f_raw < nsamp ? f_raw : 0;                       // idle tail lanes shadow sample 0
+                const int aj = (int)(((uint32_t)f * s2_magic) >> 20);         // f / S2
+                const uint32_t c2 = wcell[g * S2 + f];
+                const int e = wprep[g + aj].e;
+                const int cell = (int)(c2 >> 16) * p.Hp + (int)(c2 & 0xFFFFu);
+                const int64_t eoff = (int64_t)e * p.plane + cell;
+                fs[u] = f_raw; es[u] = e; cw[u] = c2;
+                mt[u] = need_meta ? p.meta[eoff] : 0u;
+                fd[u] = need_food ? p.food[eoff] : 0.0;
+                wl[u] = need_walls ? p.walls[eoff] : (uint8_t)0;
+                const double *php = p.phero + (int64_t)e * p.P * p.plane + cell;
+#pragma unroll
+                for (int kp = 0; kp < NPH; ++kp) ph[u][kp] = ((ph_need >> kp) & 1u) ? php[(int64_t)kp * p.plane] : 0.0;
             }
-            // all gathers of this ant in flight together
 #pragma unroll
-            for (int rd = 0; rd < ROUNDS; ++rd) {
-                mt[rd] = need_meta ? metap[cell[rd]] : 0u;
-                fd[rd] = need_food ? foodp[cell[rd]] : 0.0;
-                wl[rd] = need_walls ? wallp[cell[rd]] : (uint8_t)0;
-#pragma unroll
-                for (int kp = 0; kp < NPH; ++kp)
-                    ph[rd][kp] = ((ph_need >> kp) & 1u) ? php[(int64_t)kp * p.plane + cell[rd]] : 0.0;
-            }
-            int count = 0;
-#pragma unroll
-            for (int rd = 0; rd < ROUNDS; ++rd) {
-                int s = rd * 32 + lane;
-                bool valid = s < p.S2;
-                bool unexplored = false;
+            for (int u = 0; u < U; ++u) {
+                if (it0 + u >= iters) break;                                   // warp-uniform
+                const bool valid = fs[u] < nsamp;
+                const int f = valid ? fs[u] : 0;
+                const int aj = (int)(((uint32_t)f * s2_magic) >> 20);
+                const int e = es[u];
+                const int ix = (int)(cw[u] >> 16), iy = (int)(cw[u] & 0xFFFFu);
                 if (explore_on) {
-                    uint32_t eg = mt[rd] & 0xFFFFu;
-                    unexplored = (eg == 0u) || (eg == obs_gen);                // gather-before-scatter, Q7
-                    if (valid && eg == 0u) reinterpret_cast<uint16_t *>(metap + cell[rd])[0] = (uint16_t)obs_gen;
+                    const uint32_t eg = mt[u] & 0xFFFFu;
+                    const bool unexplored = valid && ((eg == 0u) || (eg == obs_gen));     // gather-before-scatter, Q7
+                    if (valid && eg == 0u && !(dbg & 4))
+                        reinterpret_cast<uint16_t *>(p.meta + (int64_t)e * p.plane + ix * p.Hp + iy)[0] = (uint16_t)obs_gen;
+                    const unsigned peers = __match_any_sync(0xffffffffu, aj);
+                    const unsigned votes = __ballot_sync(0xffffffffu, unexplored) & peers;
+                    if (votes && lane == __ffs(peers) - 1) atomicAdd(s_cnt + warp * 32 + g + aj, __popc(votes));
                 }
-                count += __popc(__ballot_sync(0xffffffffu, valid && unexplored));
                 if (!valid) continue;
+                const int s = f - aj * S2;
                 const bool vis = s_mask[s] != 0;
-                float *o = wobs + (j * p.S2 + s) * p.C;
-                const int ix = ixs[rd], iy = iys[rd];
+                float *o = wobs + f * C;
+                const int32_t *hl = p.hill + 4 * e;
+                // mask * (perception + 1) - 1 (RL_api.py:147-148): the +1-1 round trip changes a value by at most
+                // 2^-53 absolute, far below the resolution of the f32 observation, so visible samples pass through.
                 if (LAYOUT != 0) {
                     if (vis) {
-                        double p0 = ph[rd][0] * inv_max, p1 = ph[rd][1] * inv_max, f = fd[rd];
-                        if (has_mask) { p0 = (p0 + 1.0) - 1.0; p1 = (p1 + 1.0) - 1.0; f = (f + 1.0) - 1.0; }   // :147-148
-                        o[0] = ((mt[rd] >> 16) == occ_gen) ? 1.f : 0.f;                               // :136-142
-                        o[1] = (float)p0;                                                             // :124-125
-                        o[2] = (float)p1;
+                        o[0] = ((mt[u] >> 16) == occ_gen) ? 1.f : 0.f;                                // :136-142
+                        o[1] = (float)(ph[u][0] * inv_max);                                           // :124-125
+                        o[2] = (float)(ph[u][1] * inv_max);
                         o[3] = in_hill(hl, ix, iy) ? 1.f : 0.f;                                       // :130-131
-                        o[4] = wl[rd] ? 1.f : 0.f;                                                    // :128-129
-                        o[5] = (float)f;                                                              // :126-127
+                        o[4] = wl[u] ? 1.f : 0.f;                                                     // :128-129
+                        o[5] = (float)fd[u];                                                          // :126-127
                         if (LAYOUT == 2) {                                                            // :132-135
                             float rv = 0.f;
-                            unsigned long long rm = q.rocks;
+                            unsigned long long rm = wprep[g + aj].rocks;
                             const double *rc = p.rock_c + (int64_t)e * p.R * 2;
                             const double *rr = p.rock_rad + (int64_t)e * p.R;
                             while (rm) {
@@ -416,23 +480,23 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                         for (int c = 0; c < (LAYOUT == 2 ? 7 : 6); ++c) o[c] = -1.f;
                     }
                 } else {
-                    for (int c = 0; c < p.C; ++c) {
+                    for (int c = 0; c < C; ++c) {
                         double v;
                         switch (p.ch_kind[c]) {
-                            case 0: v = ((mt[rd] >> 16) == occ_gen) ? 1.0 : 0.0; break;
+                            case 0: v = ((mt[u] >> 16) == occ_gen) ? 1.0 : 0.0; break;
                             case 1: {
                                 int a = p.ch_arg[c];
-                                double pv = a == 0 ? ph[rd][0] : a == 1 ? ph[rd][1] : a == 2 ? ph[rd][NPH > 2 ? 2 : 0]
-                                                                                          : ph[rd][NPH > 3 ? 3 : 0];
+                                double pv = a == 0 ? ph[u][0] : a == 1 ? ph[u][1] : a == 2 ? ph[u][NPH > 2 ? 2 : 0]
+                                                                                        : ph[u][NPH > 3 ? 3 : 0];
                                 v = pv * inv_max;
                                 break;
                             }
                             case 2: v = in_hill(hl, ix, iy) ? 1.0 : 0.0; break;
-                            case 3: v = wl[rd] ? 1.0 : 0.0; break;
-                            case 4: v = fd[rd]; break;
+                            case 3: v = wl[u] ? 1.0 : 0.0; break;
+                            case 4: v = fd[u]; break;
                             default: {
                                 v = 0.0;
-                                unsigned long long rm = q.rocks;
+                                unsigned long long rm = wprep[g + aj].rocks;
                                 const double *rc = p.rock_c + (int64_t)e * p.R * 2;
                                 const double *rr = p.rock_rad + (int64_t)e * p.R;
                                 while (rm) {
@@ -443,42 +507,49 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                                 }
                             }
                         }
-                        if (has_mask) v = vis ? (v + 1.0) - 1.0 : -1.0;        // :147-148 mask*(p+1)-1
-                        o[c] = (float)v;
+                        o[c] = (has_mask && !vis) ? -1.f : (float)v;
                     }
                 }
             }
-            if (lane == 0) {
-                double reward;
-                if (p.reward_kind == 1) {
-                    reward = (double)count / 10.0;                             // reward_custom.py:19
-                } else if (p.reward_kind == 0) {
-                    reward = 0.0;
-                    if (explore_on) reward += ((double)count / 10.0) * q.mult; // :89-94
-                    reward += q.r_other;                                       // :106
-                } else {
-                    reward = q.r_other;
-                }
-                p.rewards[i] = reward;
-                if (reward_out != nullptr) reward_out[i] = reward;
-                if (is_step) {                                                 // ants.py:119-121 (Q16)
-                    int rs = p.reward_state[i];
-                    rs += ((reward - p.reward_threshold) > 0.0) ? 255 : 0;
-                    p.reward_state[i] = (uint8_t)(rs > 255 ? 255 : rs);
-                }
-            }
         }
-        // flush the staged (n_in_group x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
+        // flush the staged (n_in x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
         float *dst = obs + i0 * SC;
-        const uint32_t bytes = (uint32_t)(n_in_group * SC * 4);
+        const uint32_t bytes = (uint32_t)(n_in * SC * 4);
         if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) bulk_store_s2g(dst, wobs, bytes);
+            if (lane == 0 && !(dbg & 2)) bulk_store_s2g(dst, wobs, bytes);
         } else {
             __syncwarp();
-            for (int t = lane; t < n_in_group * SC; t += 32) dst[t] = wobs[t];
+            for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
             __syncwarp();
+        }
+    }
+    __syncwarp();
+
+    // ---- phase C: reward epilogue, thread per ant (this warp's own ants)
+    {
+        const int64_t i = base + tid;
+        if (i < p.EN) {
+            const AntPrep &q = prep[tid];
+            const int count = s_cnt[tid];
+            double reward;
+            if (p.reward_kind == 1) {
+                reward = (double)count / 10.0;                                 // reward_custom.py:19
+            } else if (p.reward_kind == 0) {
+                reward = 0.0;
+                if (explore_on) reward += ((double)count / 10.0) * q.mult;     // :89-94
+                reward += q.r_other;                                           // :106
+            } else {
+                reward = q.r_other;
+            }
+            p.rewards[i] = reward;
+            if (reward_out != nullptr) reward_out[i] = reward;
+            if (is_step) {                                                     // ants.py:119-121 (Q16)
+                int rs = p.reward_state[i];
+                rs += ((reward - p.reward_threshold) > 0.0) ? 255 : 0;
+                p.reward_state[i] = (uint8_t)(rs > 255 ? 255 : rs);
+            }
         }
     }
     if (lane == 0) bulk_store_wait_read();   // smem must stay valid until the last bulk store has read it
@@ -513,6 +584,12 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
 __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
     int e = blockIdx.x;
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    {   // the rock grid is rebuilt from the new centres
+        const int gcells = ((p.W + 31) >> kGridShift) * ((p.H + 31) >> kGridShift);
+        unsigned long long *g = p.rock_grid + (int64_t)e * gcells;
+        for (int k = threadIdx.x; k < gcells; k += blockDim.x) g[k] = 0ull;
+        __syncthreads();
+    }
     const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
     for (int r = warp; r < p.R; r += nwarp) {
         double *c = p.rock_c + ((int64_t)e * p.R + r) * 2;
@@ -541,8 +618,10 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
         __syncwarp();
         if (lane == 0) {
             double wt = p.rock_w[(int64_t)e * p.R + r];
-            c[0] = cx - sx / wt;
-            c[1] = cy - sy / wt;
+            double nx = cx - sx / wt, ny = cy - sy / wt;
+            c[0] = nx;
+            c[1] = ny;
+            rock_grid_mark(p, e, r, nx, ny, rad);
         }
     }
 }
@@ -787,6 +866,16 @@ __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
         if (clear_occ) hi = 0;
         p.meta[j] = (hi << 16) | lo;
     }
+}
+__global__ void k_rock_grid_build(Params p) {          // one block per env (after import)
+    const int e = blockIdx.x;
+    const int gcells = ((p.W + 31) >> kGridShift) * ((p.H + 31) >> kGridShift);
+    unsigned long long *g = p.rock_grid + (int64_t)e * gcells;
+    for (int k = threadIdx.x; k < gcells; k += blockDim.x) g[k] = 0ull;
+    __syncthreads();
+    for (int r = threadIdx.x; r < p.R; r += blockDim.x)
+        rock_grid_mark(p, e, r, p.rock_c[((int64_t)e * p.R + r) * 2], p.rock_c[((int64_t)e * p.R + r) * 2 + 1],
+                       p.rock_rad[(int64_t)e * p.R + r]);
 }
 __global__ void k_tiles_from_phero(Params p) {
     // mark every tile that holds a non-zero pheromone cell (after import)
