@@ -70,6 +70,7 @@ struct AntsBatch {
     float *st_obs = nullptr, *st_as = nullptr, *st_state = nullptr;
     double *st_reward = nullptr, *st_noise = nullptr;
     uint32_t *h_counts = nullptr;   // pinned: commit_count, absorb_count readback
+    uint32_t *tile_list = nullptr;
     int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128;
 };
 
@@ -187,11 +188,10 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
         const int layout = b->perceive_layout;
         const uint32_t magic = (1u << 20) / (uint32_t)p.S2 + 1u;   // f / S2 == (f * magic) >> 20 for f < 2048
         const int threads = b->perceive_threads;
-        static const int dbg = getenv("ANTS_DBG") ? atoi(getenv("ANTS_DBG")) : 0;
         blocks = (int)cdiv(p.EN, threads);
 #define ANTS_PERCEIVE(L, SF)                                                                               \
     ants::k_perceive<L, SF><<<blocks, threads, b->perceive_smem, b->stream>>>(                             \
-        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, dbg)
+        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic)
         if (p.S == 7) {
             if (layout == 1) ANTS_PERCEIVE(1, 7);
             else if (layout == 2) ANTS_PERCEIVE(2, 7);
@@ -284,17 +284,23 @@ int do_update(AntsBatch *b, const double *d_noise) {
                 ants::k_diffuse_stencil<<<(unsigned)((int64_t)nbx * nby * p.E * p.P), 256, 0, b->stream>>>(p, nbx, nby);
             }
             TRY(check_launch("k_diffuse_stencil"));
-            double *t = p.phero; p.phero = p.phero_alt; p.phero_alt = t;
+            {
+                LaunchScope ls(b, F_EVAP);
+                ants::k_diffuse_commit<<<148 * 8, 256, 0, b->stream>>>(p);
+            }
             b->stats.active_tiles = b->stats.total_tiles;
         } else if (b->cfg.evap_mode == ANTS_EVAP_ACTIVE_TILES) {
             CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned long long), b->stream));
+            {
+                LaunchScope ls(b, F_EVAP);
+                ants::k_tiles_compact<<<148 * 4, 256, 0, b->stream>>>(p, b->tile_list);
+            }
+            TRY(check_launch("k_tiles_compact"));
             LaunchScope ls(b, F_EVAP);
-            ants::k_evaporate_tiles<<<148 * 8, 256, 0, b->stream>>>(p);
+            ants::k_evaporate_tiles<<<148 * 16, 256, 0, b->stream>>>(p, b->tile_list);
         } else {
-            int64_t per_plane = cdiv(p.plane / 2, 256 * 4);
-            int64_t gx = per_plane < 1 ? 1 : per_plane;
             LaunchScope ls(b, F_EVAP);
-            ants::k_evaporate_dense<<<(unsigned)(gx * p.E * p.P), 256, 0, b->stream>>>(p, (int)gx);
+            ants::k_evaporate_dense<<<148 * 16, 256, 0, b->stream>>>(p);
         }
         TRY(check_launch("evaporate"));
         // 6. Ants.update (order 999): deposit
@@ -415,6 +421,11 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     p.has_max_val = cfg->has_max_val;
     p.tiles_x = (int)cdiv(p.W, ants::kTile);
     p.tiles_y = p.Hp / ants::kTile;
+    // cell record: { f64 phero[P]; f64 food; u32 meta; u8 wall; pad } in 32 B (P <= 2) or 64 B
+    p.food_off = 8 * p.P; p.meta_off = 8 * p.P + 8; p.wall_off = 8 * p.P + 12;
+    p.rec_shift = (8 * p.P + 16 <= 32) ? 5 : 6;
+    p.grid_w = (int)cdiv(p.W, 1 << ants::kGridShift);
+    p.grid_h = (int)cdiv(p.H, 1 << ants::kGridShift);
     p.delta = cfg->delta; p.fwd_delta = cfg->fwd_delta; p.reward_threshold = cfg->reward_threshold;
     p.max_speed = cfg->max_speed; p.max_rot_speed = cfg->max_rot_speed;
     p.csr = cfg->carry_speed_reduction; p.bsr = cfg->backward_speed_reduction;
@@ -440,49 +451,47 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.act, EN * (p.P > 0 ? p.P : 1)));
     A(dev_alloc(b, &p.mandibles, EN)); A(dev_alloc(b, &p.reward_state, EN));
     A(dev_alloc(b, &p.rw_holding_prev, EN)); A(dev_alloc(b, &p.rw_prev_dist, EN)); A(dev_alloc(b, &p.rewards, EN));
-    A(dev_alloc(b, &p.phero, cells * (p.P > 0 ? p.P : 1)));
+    A(dev_alloc(b, &p.cells, cells << p.rec_shift));
     if (cfg->diffuse_factor != 0.0) A(dev_alloc(b, &p.phero_alt, cells * (p.P > 0 ? p.P : 1)));
-    A(dev_alloc(b, &p.food, cells));
-    A(dev_alloc(b, &p.walls, cells));
-    A(dev_alloc(b, &p.meta, cells));
     A(dev_alloc(b, &p.owner, cells));
     if (cfg->evap_mode == ANTS_EVAP_ACTIVE_TILES && cfg->diffuse_factor == 0.0)
-        A(dev_alloc(b, &p.tile_active, (int64_t)p.E * (p.P > 0 ? p.P : 1) * p.tiles_x * p.tiles_y));
+    {
+        A(dev_alloc(b, &p.tile_active, (int64_t)p.E * p.tiles_x * p.tiles_y));
+        A(dev_alloc(b, &b->tile_list, (int64_t)p.E * p.tiles_x * p.tiles_y, false));
+    }
     A(dev_alloc(b, &p.hill, (int64_t)p.E * 4));
     A(dev_alloc(b, &p.hill_food, (int64_t)p.E));
     A(dev_alloc(b, &p.rock_c, (int64_t)p.E * p.R * 2)); A(dev_alloc(b, &p.rock_rad, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.rock_w, (int64_t)p.E * p.R));
-    A(dev_alloc(b, &p.rock_grid, (int64_t)p.E * cdiv(p.W, 32) * cdiv(p.H, 32)));
+    A(dev_alloc(b, &p.rock_grid, (int64_t)p.E * p.grid_w * p.grid_h));
     A(dev_alloc(b, &p.food_delta, EN, false));
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
     A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
     A(dev_alloc(b, &p.tile_counter, 1));
-    b->stats.total_tiles = (int64_t)p.E * p.P * p.tiles_x * p.tiles_y;
+    b->stats.total_tiles = (int64_t)p.E * p.tiles_x * p.tiles_y;
     // perception tables, RL_api.py:92-93: coords[i][j] = ((j - r) * DELTA, (i - r) * DELTA)
-    double *d_px = nullptr, *d_py = nullptr;
+    double *d_off = nullptr;
     uint8_t *d_mask = nullptr;
-    A(dev_alloc(b, &d_px, p.S2)); A(dev_alloc(b, &d_py, p.S2)); A(dev_alloc(b, &d_mask, p.S2));
+    A(dev_alloc(b, &d_off, p.S)); A(dev_alloc(b, &d_mask, p.S2));
     if (rc != ANTS_OK) { ants_destroy(b); return rc; }
     {
-        std::vector<double> px(p.S2), py(p.S2);
+        std::vector<double> off(p.S);
         std::vector<uint8_t> mk(p.S2, 1);
-        for (int i = 0; i < p.S; ++i)
-            for (int j = 0; j < p.S; ++j) {
-                volatile double fx = (double)(j - p.radius), fy = (double)(i - p.radius);
-                px[i * p.S + j] = fx * cfg->delta;
-                py[i * p.S + j] = fy * cfg->delta;
-                if (cfg->has_mask) mk[i * p.S + j] = cfg->mask[i * p.S + j] ? 1 : 0;
-            }
-        cudaMemcpy(d_px, px.data(), p.S2 * sizeof(double), cudaMemcpyHostToDevice);
-        cudaMemcpy(d_py, py.data(), p.S2 * sizeof(double), cudaMemcpyHostToDevice);
+        for (int k = 0; k < p.S; ++k) {
+            volatile double fk = (double)(k - p.radius);
+            off[k] = fk * cfg->delta;
+        }
+        if (cfg->has_mask)
+            for (int k = 0; k < p.S2; ++k) mk[k] = cfg->mask[k] ? 1 : 0;
+        cudaMemcpy(d_off, off.data(), p.S * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(d_mask, mk.data(), p.S2, cudaMemcpyHostToDevice);
-        p.samp_px = d_px; p.samp_py = d_py; p.mask = d_mask;
+        p.samp_off = d_off; p.mask = d_mask;
     }
     {   // ants per staged chunk: as many as fit ~12 KB per warp, keeping the chunk a multiple of 16 B and the
         // flat sample index below 2048 (magic division); threads per block: as many warps as fit ~100 KB
         int sc_bytes = p.S2 * p.C * 4;
         int g = ants::kMaxGroup;
-        while (g > 1 && (g * sc_bytes > 6 * 1024 || g * p.S2 >= 2048)) g >>= 1;
+        while (g > 1 && (g * sc_bytes > 8 * 1024 || g * p.S2 >= 2048)) g >>= 1;
         b->perceive_group = g;
         int threads = ants::kPerceiveThreads;
         auto smem_for = [&](int t) {
@@ -492,7 +501,6 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         while (threads > 32 && smem_for(threads) > 100 * 1024) threads >>= 1;
         b->perceive_threads = threads;
         b->perceive_smem = smem_for(threads);
-        if (const char *x = getenv("ANTS_PERCEIVE_EXTRA_SMEM")) b->perceive_smem += atoi(x);   // occupancy experiments
     }
     {   // straight-line perception code for the generator's default channel list (with / without rocks)
         const int std6[6] = {ANTS_CH_ANTS, ANTS_CH_PHERO, ANTS_CH_PHERO, ANTS_CH_ANTHILL, ANTS_CH_WALLS, ANTS_CH_FOOD};
@@ -584,39 +592,38 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         b->prev_synced = (memcmp(s->x, s->prev_x, EN8) == 0 && memcmp(s->y, s->prev_y, EN8) == 0) ? 1 : 0;
     else if (s->x)
         b->prev_synced = 1;
-    const size_t rows = (size_t)p.E * p.W;
+    // map fields: dense host array -> device scratch -> pack kernel into the cell records
+    const size_t ncell = (size_t)p.E * p.W * p.H;
+    void *d_tmp = nullptr;
+    if (s->phero || s->food || s->walls || s->explored) {
+        size_t need = ncell * 8 * ((s->phero && p.P > 1) ? p.P : 1);
+        cudaError_t me = cudaMalloc(&d_tmp, need);
+        if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "import scratch of %zu bytes: %s", need, cudaGetErrorString(me));
+    }
     if (s->phero && p.P > 0) {
-        CK(cudaMemsetAsync(p.phero, 0, (size_t)p.E * p.P * p.plane * sizeof(double), st));
-        CK(cudaMemcpy2DAsync(p.phero, (size_t)p.Hp * 8, s->phero, (size_t)p.H * 8, (size_t)p.H * 8, rows * p.P,
-                             cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tmp, s->phero, ncell * 8 * p.P, cudaMemcpyHostToDevice, st));
+        for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k);
+        TRY(check_launch("k_pack_f64"));
         if (p.tile_active) {
             ants::k_tiles_from_phero<<<148 * 4, 256, 0, st>>>(p);
             TRY(check_launch("k_tiles_from_phero"));
         }
     }
     if (s->food) {
-        CK(cudaMemsetAsync(p.food, 0, (size_t)p.E * p.plane * sizeof(double), st));
-        CK(cudaMemcpy2DAsync(p.food, (size_t)p.Hp * 8, s->food, (size_t)p.H * 8, (size_t)p.H * 8, rows,
-                             cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tmp, s->food, ncell * 8, cudaMemcpyHostToDevice, st));
+        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off);
+        TRY(check_launch("k_pack_f64"));
         b->needs_sweep = 1;
     }
-    std::vector<uint8_t> walls01;
     if (s->walls) {
-        size_t n = rows * p.H;
-        walls01.resize(n);
-        for (size_t j = 0; j < n; ++j) walls01[j] = s->walls[j] ? 1 : 0;      // Walls.__init__: astype(bool)
-        CK(cudaMemsetAsync(p.walls, 0, (size_t)p.E * p.plane, st));
-        CK(cudaMemcpy2DAsync(p.walls, (size_t)p.Hp, walls01.data(), (size_t)p.H, (size_t)p.H, rows,
-                             cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tmp, s->walls, ncell, cudaMemcpyHostToDevice, st));
+        ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 0);      // Walls.__init__: astype(bool)
+        TRY(check_launch("k_pack_u8"));
     }
-    uint8_t *d_tmp = nullptr;
     if (s->explored) {
-        size_t n = rows * p.H;
-        CK(cudaMalloc((void **)&d_tmp, n));
-        CK(cudaMemcpyAsync(d_tmp, s->explored, n, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(p.meta, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
-        ants::k_meta_from_explored<<<148 * 4, 256, 0, st>>>(p, d_tmp);
-        TRY(check_launch("k_meta_from_explored"));
+        CK(cudaMemcpyAsync(d_tmp, s->explored, ncell, cudaMemcpyHostToDevice, st));
+        ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 1);
+        TRY(check_launch("k_pack_u8"));
         b->obs_gen = 0; b->occ_gen = 0;
     }
     std::vector<int32_t> hill4;
@@ -670,22 +677,33 @@ int ants_export_state(AntsBatch *b, AntsHostState *s) {
         act_t.resize((size_t)p.EN * p.P);
         CK(cudaMemcpyAsync(act_t.data(), p.act, act_t.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
-    const size_t rows = (size_t)p.E * p.W;
-    if (s->phero && p.P > 0)
-        CK(cudaMemcpy2DAsync(s->phero, (size_t)p.H * 8, p.phero, (size_t)p.Hp * 8, (size_t)p.H * 8, rows * p.P,
-                             cudaMemcpyDeviceToHost, st));
-    if (s->food)
-        CK(cudaMemcpy2DAsync(s->food, (size_t)p.H * 8, p.food, (size_t)p.Hp * 8, (size_t)p.H * 8, rows,
-                             cudaMemcpyDeviceToHost, st));
-    if (s->walls)
-        CK(cudaMemcpy2DAsync(s->walls, (size_t)p.H, p.walls, (size_t)p.Hp, (size_t)p.H, rows, cudaMemcpyDeviceToHost, st));
-    uint8_t *d_tmp = nullptr;
+    // map fields: unpack kernel from the cell records -> device scratch -> dense host array
+    const size_t ncell = (size_t)p.E * p.W * p.H;
+    void *d_tmp = nullptr;
+    if ((s->phero && p.P > 0) || s->food || s->walls || s->explored) {
+        size_t need = ncell * 8 * ((s->phero && p.P > 1) ? p.P : 1);
+        cudaError_t me = cudaMalloc(&d_tmp, need);
+        if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "export scratch of %zu bytes: %s", need, cudaGetErrorString(me));
+    }
+    if (s->phero && p.P > 0) {
+        for (int k = 0; k < p.P; ++k) ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k);
+        TRY(check_launch("k_unpack_f64"));
+        CK(cudaMemcpyAsync(s->phero, d_tmp, ncell * 8 * p.P, cudaMemcpyDeviceToHost, st));
+    }
+    if (s->food) {
+        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off);
+        TRY(check_launch("k_unpack_f64"));
+        CK(cudaMemcpyAsync(s->food, d_tmp, ncell * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (s->walls) {
+        ants::k_unpack_u8<<<148 * 8, 256, 0, st>>>(p, (uint8_t *)d_tmp, 0);
+        TRY(check_launch("k_unpack_u8"));
+        CK(cudaMemcpyAsync(s->walls, d_tmp, ncell, cudaMemcpyDeviceToHost, st));
+    }
     if (s->explored) {
-        size_t n = rows * p.H;
-        CK(cudaMalloc((void **)&d_tmp, n));
-        ants::k_explored_from_meta<<<148 * 4, 256, 0, st>>>(p, d_tmp);
-        TRY(check_launch("k_explored_from_meta"));
-        CK(cudaMemcpyAsync(s->explored, d_tmp, n, cudaMemcpyDeviceToHost, st));
+        ants::k_unpack_u8<<<148 * 8, 256, 0, st>>>(p, (uint8_t *)d_tmp, 1);
+        TRY(check_launch("k_unpack_u8"));
+        CK(cudaMemcpyAsync(s->explored, d_tmp, ncell, cudaMemcpyDeviceToHost, st));
     }
     std::vector<int32_t> hill4;
     if (s->anthill_xyr) {

@@ -1,13 +1,18 @@
 // ants_kernels.cuh -- sm_100a device code of the AntsRL step loop (one batch of E independent environments).
 //
-// Design: ant-centric flat kernels over all E*N ants.  The reference's "last writer wins"
-// fancy-index scatters (quirk Q1: ants.py:116, pheromone.py:39, RL_api.py:141) and its gather-before-scatter
-// exploration reward (Q7: reward_custom.py:89-93) are resolved without per-environment barriers through
-// generation-stamped planes:
-//   owner[e][x][y] : u32 = (phase << 16) | ant   written with atomicMax -> highest ant index of the current
+// Design.  Ant-centric flat kernels over all E*N ants; the map of every environment is ONE array
+// of cell records (array of structures), sized so that a cell is exactly one 32-byte DRAM sector for the
+// reference's two pheromones:
+//     record (P <= 2: 32 B, P <= 4: 64 B) = { f64 phero[P]; f64 food; u32 meta; u8 wall; pad }
+//     meta = (occ_gen << 16) | explored_gen
+// A perception sample therefore costs one sector and two 128-bit loads instead of five scattered plane reads.
+// The reference's "last writer wins" fancy-index scatters (quirk Q1: ants.py:116, pheromone.py:39,
+// RL_api.py:141) and its gather-before-scatter exploration reward (Q7: reward_custom.py:89-93) are resolved
+// without per-environment barriers through generation stamps:
+//   owner[e][x][y] : u32 = (phase << 16) | ant   written with atomicMax -> the highest ant index of the current
 //                    scatter phase owns the cell (food pickup/drop, pheromone deposit)
-//   meta[e][x][y]  : u32 = (occ_gen << 16) | explored_gen; occ_gen == current step  => an ant stands here;
-//                    explored_gen == 0 or == current observation => the cell was unexplored before this observation
+//   meta.occ_gen == current step                  => an ant stands on the cell ("ants" perception channel)
+//   meta.explored_gen == 0 or == this observation => the cell was unexplored before this observation
 // All position / angle / sample-coordinate arithmetic is f64 in the reference's operation order (compiled with
 // -fmad=false) so that truncated / rounded cell indices agree with numpy.
 #pragma once
@@ -18,11 +23,12 @@ namespace ants {
 
 constexpr int kMaxCh = 16;
 constexpr int kTile = 16;                 // pheromone activity tile: 16 x 16 cells
+constexpr int kGridShift = 4;             // rock grid cell = 16 x 16 map cells
 
 struct Params {
     int32_t E, N, W, H, Hp, P, R;
     int64_t EN;                            // E * N
-    int64_t plane;                         // W * Hp cells per env plane
+    int64_t plane;                         // W * Hp cells per env
     int32_t radius, S, S2, C;
     int32_t has_mask;
     int32_t ch_kind[kMaxCh];
@@ -30,7 +36,10 @@ struct Params {
     int32_t rule_n;
     int32_t rule_op[kMaxCh];               // mandible rule in perceived_objects order: 0 = food OR, 1 = anthill AND
     int32_t reward_kind, explore_on, has_max_val;
-    int32_t tiles_x, tiles_y;              // activity tiles per plane
+    int32_t tiles_x, tiles_y;              // activity tiles per env
+    int32_t rec_shift;                     // log2(record bytes): 5 or 6
+    int32_t food_off, meta_off, wall_off;  // byte offsets inside a record (phero k at 8k)
+    int32_t grid_w, grid_h;                // rock grid dims
     double delta, fwd_delta, reward_threshold, max_speed, max_rot_speed, csr, bsr;
     double f_explore, f_food, f_anthill, f_explore_hold, f_heading;
     double filt_center, filt_ring, phero_max_val, max_hold;
@@ -41,22 +50,20 @@ struct Params {
     double *act;                           // [P][E*N]
     uint8_t *mandibles, *reward_state;
     double *rw_holding_prev, *rw_prev_dist, *rewards;
-    // planes, row pitch Hp
-    double *phero;                         // [E][P][W][Hp]
-    double *phero_alt;                     // ping-pong target of the diffusion stencil (DIFFUSE_FACTOR != 0)
-    double *food;                          // [E][W][Hp]
-    uint8_t *walls;                        // [E][W][Hp]
-    uint32_t *meta, *owner;                // [E][W][Hp]
-    uint8_t *tile_active;                  // [E][P][tiles_x][tiles_y]
+    // map
+    uint8_t *cells;                        // [E][W][Hp] records
+    uint32_t *owner;                       // [E][W][Hp]
+    double *phero_alt;                     // [E][P][W][Hp] scratch of the diffusion stencil (DIFFUSE_FACTOR != 0)
+    uint8_t *tile_active;                  // [E][tiles_x][tiles_y]
     int32_t *hill;                         // [E][4] = x, y, r, r*r
     double *hill_food;                     // [E]
     double *rock_c, *rock_rad, *rock_w;    // [E][R][2], [E][R], [E][R]
-    unsigned long long *rock_grid;         // [E][ceil(W/32)][ceil(H/32)] bitmask of rocks near each 32x32 block
-    const double *samp_px, *samp_py;       // [S2] perception_coords * DELTA (RL_api.py:92-93)
+    unsigned long long *rock_grid;         // [E][grid_w][grid_h] bitmask of rocks near each 16x16 block
+    const double *samp_off;                // [S] = (k - r) * DELTA  (RL_api.py:92-93)
     const uint8_t *mask;                   // [S2]
     // scratch
     double *food_delta;                    // [E*N]
-    uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food plane this step
+    uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food of a cell this step
     uint32_t *absorb_list, *absorb_count;  // (env, cell) pairs of food lying inside the anthill disc
     unsigned long long *tile_counter;      // tiles processed by the evaporation kernel
 };
@@ -85,6 +92,19 @@ __device__ __forceinline__ bool in_hill(const int32_t *hl, int cx, int cy) {   /
     int dx = hl[0] - cx, dy = hl[1] - cy;
     return dx * dx + dy * dy <= hl[3];
 }
+// wrap an integer sample coordinate onto the torus (np.mod on ints); the fast path covers |offset| < n
+__device__ __forceinline__ int wrap_coord(int v, int n) {
+    if (v < 0) v += n; else if (v >= n) v -= n;
+    return ((unsigned)v < (unsigned)n) ? v : imod(v, n);
+}
+// cell record accessors
+__device__ __forceinline__ uint8_t *rec_at(const Params &p, int e, int cell) {
+    return p.cells + (((int64_t)e * p.plane + cell) << p.rec_shift);
+}
+__device__ __forceinline__ double *rec_phero(uint8_t *r, int k) { return reinterpret_cast<double *>(r) + k; }
+__device__ __forceinline__ double *rec_food(const Params &p, uint8_t *r) { return reinterpret_cast<double *>(r + p.food_off); }
+__device__ __forceinline__ uint32_t *rec_meta(const Params &p, uint8_t *r) { return reinterpret_cast<uint32_t *>(r + p.meta_off); }
+__device__ __forceinline__ uint8_t *rec_wall(const Params &p, uint8_t *r) { return r + p.wall_off; }
 
 // Philox4x32-10, counter (ant, step, env, 0), key (seed_lo, seed_hi) -> one double in [0,1) built like
 // numpy's random_sample: ((a >> 5) * 2^26 + (b >> 6)) / 2^53.  Mirrored by oracle.philox_uniform.
@@ -103,6 +123,46 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t env, ui
     return (a * 67108864.0 + b) / 9007199254740992.0;
 }
 
+// shared -> global bulk copy through the async proxy (TMA 1-D bulk store, SASS UBLKCP)
+__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+// Candidate rocks of a point: every rock whose (radius + reach) box overlaps the point's grid cell was OR-ed
+// into that cell by rock_grid_mark, so one 8-byte load replaces a loop over all rocks.
+__device__ __forceinline__ unsigned long long rock_candidates(const Params &p, int e, double x, double y) {
+    int gx = cell_of(pymod(x, (double)p.W), p.W) >> kGridShift;
+    int gy = cell_of(pymod(y, (double)p.H), p.H) >> kGridShift;
+    return p.rock_grid[((int64_t)e * p.grid_w + gx) * p.grid_h + gy];
+}
+__device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad) {
+    const double L = rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
+    const double step = (double)(1 << kGridShift);
+    unsigned long long *g = p.rock_grid + (int64_t)e * p.grid_w * p.grid_h;
+    const unsigned long long bit = 1ull << r;
+    // sample the box [c - L, c + L] every grid step (and at its far edge): hits every grid cell it overlaps
+    for (double ox = -L;; ox += step) {
+        if (ox > L) ox = L;
+        int gx = cell_of(pymod(cx + ox, (double)p.W), p.W) >> kGridShift;
+        for (double oy = -L;; oy += step) {
+            if (oy > L) oy = L;
+            int gy = cell_of(pymod(cy + oy, (double)p.H), p.H) >> kGridShift;
+            atomicOr(g + gx * p.grid_h + gy, bit);
+            if (oy >= L) break;
+        }
+        if (ox >= L) break;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ step, part 1
 // RLApi.step lines 178-196 for every ant: mandible rule, pickup / drop bookkeeping (ants.py:102-117),
 // pheromone activation (ants.py:89-96), rotation (ants.py:62-67), forward move on the torus (ants.py:69-80),
@@ -118,8 +178,8 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     double hold = p.holding[i];
     int m_old = p.mandibles[i] != 0;
     int pcx = cell_of(p.prev_x[i], p.W), pcy = cell_of(p.prev_y[i], p.H);      // RL_api.py:178
-    int64_t pcell = (int64_t)e * p.plane + (int64_t)pcx * p.Hp + pcy;
-    double f = p.food[pcell];
+    int pcell = pcx * p.Hp + pcy;
+    double f = *rec_food(p, rec_at(p, e, pcell));
     const int32_t *hl = p.hill + 4 * e;
     bool hill = in_hill(hl, cell_of(x, p.W), cell_of(y, p.H));                  // RL_api.py:184
     int m = m_old;
@@ -134,7 +194,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     hold = hold + (taken - dropped);                                            // ants.py:117
     // ants.py:116 `qte[xy] += dropped - taken`: the highest ant index standing in the cell wins (Q1).  Ants in
     // a cell that holds no food and is outside the hill cannot change it and need not compete.
-    if (all_stamp || f > 0.0 || hill) atomicMax(p.owner + pcell, owner_stamp | (uint32_t)a);
+    if (all_stamp || f > 0.0 || hill) atomicMax(p.owner + (int64_t)e * p.plane + pcell, owner_stamp | (uint32_t)a);
     if (delta != 0.0) {
         uint32_t slot = atomicAdd(p.commit_count, 1u);
         p.commit_list[slot] = (uint32_t)i;
@@ -155,8 +215,8 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     x = pymod(x + c * fwd, (double)p.W);                                        // ants.py:69-80
     y = pymod(y + s * fwd, (double)p.H);
     p.x[i] = x; p.y[i] = y; p.theta[i] = th;
-    int64_t ocell = (int64_t)e * p.plane + (int64_t)cell_of(x, p.W) * p.Hp + cell_of(y, p.H);
-    reinterpret_cast<uint16_t *>(p.meta + ocell)[1] = (uint16_t)occ_gen;
+    uint8_t *orec = rec_at(p, e, cell_of(x, p.W) * p.Hp + cell_of(y, p.H));
+    reinterpret_cast<uint16_t *>(rec_meta(p, orec))[1] = (uint16_t)occ_gen;
 }
 
 // Occupancy stamp alone, for a stand-alone observation() (main.py:88).
@@ -164,8 +224,8 @@ __global__ void __launch_bounds__(256) k_occ_stamp(Params p, uint32_t occ_gen) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
-    int64_t ocell = (int64_t)e * p.plane + (int64_t)cell_of(p.x[i], p.W) * p.Hp + cell_of(p.y[i], p.H);
-    reinterpret_cast<uint16_t *>(p.meta + ocell)[1] = (uint16_t)occ_gen;
+    uint8_t *orec = rec_at(p, e, cell_of(p.x[i], p.W) * p.Hp + cell_of(p.y[i], p.H));
+    reinterpret_cast<uint16_t *>(rec_meta(p, orec))[1] = (uint16_t)occ_gen;
 }
 
 // ------------------------------------------------------------------------------------------------ step, part 2
@@ -178,84 +238,23 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
         int e = (int)(i / p.N);
         int a = (int)(i - (int64_t)e * p.N);
         int pcx = cell_of(p.prev_x[i], p.W), pcy = cell_of(p.prev_y[i], p.H);
-        int64_t pcell = (int64_t)e * p.plane + (int64_t)pcx * p.Hp + pcy;
-        if (p.owner[pcell] != (owner_stamp | (uint32_t)a)) continue;
-        double nv = p.food[pcell] + p.food_delta[i];
-        p.food[pcell] = nv;
+        int pcell = pcx * p.Hp + pcy;
+        if (p.owner[(int64_t)e * p.plane + pcell] != (owner_stamp | (uint32_t)a)) continue;
+        double *fp = rec_food(p, rec_at(p, e, pcell));
+        double nv = *fp + p.food_delta[i];
+        *fp = nv;
         if (nv != 0.0 && in_hill(p.hill + 4 * e, pcx, pcy)) {
             uint32_t s = atomicAdd(p.absorb_count, 1u);
             p.absorb_list[2 * s] = (uint32_t)e;
-            p.absorb_list[2 * s + 1] = (uint32_t)(pcx * p.Hp + pcy);
+            p.absorb_list[2 * s + 1] = (uint32_t)pcell;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ perception + reward
 // RLApi.observation (RL_api.py:96-165) fused with reward.observation (reward_custom.py) and, when called from
-// step, Ants.give_reward (ants.py:119-121).  Block = 256 threads = 256 consecutive ants.
-//   phase A (thread per ant): f64 trigonometry of the rotated sampling frame, reward terms that do not need
-//            the exploration count, agent_state / state outputs, rock culling.
-//   phase B (warp per ant, lanes = samples): sample cell = round(rot(theta + pi/2) * offset + xy_f) mod (W,H),
-//            gathers from the meta / pheromone / food / wall planes, analytic anthill disc, exact rock test on
-//            the culled set, exploration count by ballot, mask, then the (S2 x C) f32 tile is staged in shared
-//            memory and written with coalesced stores.
-constexpr int kPerceiveThreads = 128;      // 4 warps = 128 consecutive ants per block
-constexpr int kMaxGroup = 8;                // ants staged per TMA bulk store (4 or 8 ants: bytes are a multiple of 16)
-constexpr int kGridShift = 5;               // rock grid cell = 32 x 32 map cells
-
-struct AntPrep {
-    double r_other, mult;        // reward terms without the exploration count; exploration multiplier
-    unsigned long long rocks;    // candidate rocks (from the rock grid)
-    int e, pad;                  // environment of the ant
-};
-
-// wrap an integer sample coordinate onto the torus (np.mod on ints); the fast path covers |offset| < n
-__device__ __forceinline__ int wrap_coord(int v, int n) {
-    if (v < 0) v += n; else if (v >= n) v -= n;
-    return ((unsigned)v < (unsigned)n) ? v : imod(v, n);
-}
-
-// shared -> global bulk copy through the async proxy (TMA 1-D bulk store, SASS UBLKCP)
-__device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
-                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-__device__ __forceinline__ void bulk_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-}
-
-// Candidate rocks of a point: every rock whose (radius + reach) box overlaps the point's 32x32 grid cell was
-// OR-ed into that cell by rock_grid_mark, so one 8-byte load replaces a loop over all rocks.
-__device__ __forceinline__ unsigned long long rock_candidates(const Params &p, int e, double x, double y) {
-    const int gw = (p.W + 31) >> kGridShift, gh = (p.H + 31) >> kGridShift;
-    int gx = cell_of(pymod(x, (double)p.W), p.W) >> kGridShift;
-    int gy = cell_of(pymod(y, (double)p.H), p.H) >> kGridShift;
-    return p.rock_grid[((int64_t)e * gw + gx) * gh + gy];
-}
-__device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad) {
-    const int gw = (p.W + 31) >> kGridShift, gh = (p.H + 31) >> kGridShift;
-    const double L = rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
-    unsigned long long *g = p.rock_grid + (int64_t)e * gw * gh;
-    const unsigned long long bit = 1ull << r;
-    // sample the box [c - L, c + L] every <= 32 cells (and at its far edge): hits every grid cell it overlaps
-    for (double ox = -L;; ox += 32.0) {
-        if (ox > L) ox = L;
-        int gx = cell_of(pymod(cx + ox, (double)p.W), p.W) >> kGridShift;
-        for (double oy = -L;; oy += 32.0) {
-            if (oy > L) oy = L;
-            int gy = cell_of(pymod(cy + oy, (double)p.H), p.H) >> kGridShift;
-            atomicOr(g + gx * gh + gy, bit);
-            if (oy >= L) break;
-        }
-        if (ox >= L) break;
-    }
-}
-
+// step, Ants.give_reward (ants.py:119-121).
+//
 // LAYOUT 0: any perceived_objects list (switch per channel)
 // LAYOUT 1: the generator's default list [ants, phero0, phero1, anthill, walls, food] (environment_generator.py:64-99)
 // LAYOUT 2: the same plus rocks as 7th channel
@@ -268,17 +267,26 @@ __device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, do
 //            computed once per row / column, packed (x << 16 | y) into shared memory; reward terms that do not
 //            need the exploration count; agent_state / state outputs; candidate rocks from the rock grid.
 //   phase B (warp, flat sample index): the warp walks its ants in chunks of `group` ants; the chunk's
-//            group*S2 samples are spread over the 32 lanes and processed in batches of U lane-slots whose
-//            gathers (meta / pheromone / food / walls planes) are all issued before any is consumed; analytic
-//            anthill disc, exact rock test on the candidates; exploration counts per ant with match_any + shared
-//            atomics; the chunk's (group x S2 x C) f32 tile is staged in shared memory and leaves with ONE TMA
-//            bulk store.
+//            group*S2 samples are spread over the 32 lanes and processed in batches of U lane-slots whose record
+//            loads (one 32-byte sector per sample) are all issued before any is consumed; analytic anthill disc,
+//            exact rock test on the candidates; per-lane packed exploration counters; the chunk's
+//            (group x S2 x C) f32 tile is staged in shared memory and leaves with ONE TMA bulk store.
 //   phase C (thread per ant): reward epilogue and Ants.give_reward.
+constexpr int kPerceiveThreads = 128;
+constexpr int kMaxGroup = 4;                // ants per staged chunk (4 ants: bytes are always a multiple of 16)
+
+struct AntPrep {
+    double r_other, mult;        // reward terms without the exploration count; exploration multiplier
+    unsigned long long rocks;    // candidate rocks (from the rock grid)
+    const uint8_t *cells;        // records of the ant's environment
+    int e, pad;
+};
+
 template <int LAYOUT, int SFIX>
 __global__ void __launch_bounds__(kPerceiveThreads)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
-           int group, uint32_t s2_magic, int dbg) {
+           int group, uint32_t s2_magic) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = SFIX ? SFIX : p.S;
     const int S2 = S * S, C = p.C;
@@ -293,7 +301,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
 
     const int tid = threadIdx.x;
     for (int k = tid; k < S2; k += nthreads) s_mask[k] = p.has_mask ? p.mask[k] : 1;
-    for (int k = tid; k < S; k += nthreads) s_off[k] = p.samp_px[k];          // row 0 of perception_coords[..., 0]
+    for (int k = tid; k < S; k += nthreads) s_off[k] = p.samp_off[k];
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * nthreads;
 
@@ -316,7 +324,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 double cX[SFIX ? SFIX : 1], sX[SFIX ? SFIX : 1];
 #pragma unroll
                 for (int j = 0; j < SFIX; ++j) { const double o = s_off[j]; cX[j] = ct * o; sX[j] = st * o; }
-#pragma unroll
+#pragma unroll 1
                 for (int ii = 0; ii < SFIX; ++ii) {
                     const double o = s_off[ii];
                     const double sY = st * o, cY = ct * o;
@@ -341,6 +349,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             }
             AntPrep q;
             q.e = e; q.pad = 0;
+            q.cells = p.cells + (((int64_t)e * p.plane) << p.rec_shift);
             // reward.observation, reward_custom.py
             const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
             const double d = hold - hprev;
@@ -372,22 +381,10 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             }
         }
     }
-    // which planes the configured channels read (block-uniform)
-    bool need_food = LAYOUT != 0, need_walls = LAYOUT != 0, need_meta = LAYOUT != 0 || p.explore_on != 0;
-    unsigned ph_need = LAYOUT != 0 ? 3u : 0u;
-    if (dbg & 1) { need_food = need_walls = need_meta = false; ph_need = 0; }
-    if (dbg & 16) { need_food = need_walls = false; ph_need = 0; }
-    if (LAYOUT == 0) {
-        for (int c = 0; c < C; ++c) {
-            int kd = p.ch_kind[c];
-            need_food |= kd == 4; need_walls |= kd == 3; need_meta |= kd == 0;
-            if (kd == 1) ph_need |= 1u << p.ch_arg[c];
-        }
-    }
-    constexpr int NPH = LAYOUT != 0 ? 2 : 4;
     const double inv_max = 1.0 / p.phero_max_val;   // obs is f32: x * (1/max) == x / max to well below 1e-5
     const bool has_mask = p.has_mask != 0;
     const bool explore_on = p.explore_on != 0;
+    const int food_off = p.food_off, meta_off = p.meta_off, wall_off = p.wall_off, rec_shift = p.rec_shift;
     __syncwarp();
 
     // ---- phase B
@@ -395,8 +392,8 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
     float *wobs = s_obs + warp * group * SC;
     const uint32_t *wcell = s_cell + warp * 32 * S2;
     const AntPrep *wprep = prep + warp * 32;
+    constexpr int U = 4;                       // lane-slots per batch: all record loads of a batch are in flight together
     for (int g = 0; g < 32; g += group) {
-        if (dbg & 8) break;
         const int64_t i0 = base + warp * 32 + g;
         if (i0 >= p.EN) break;
         int n_in = 32 - g < group ? 32 - g : group;
@@ -406,99 +403,97 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
         if (lane == 0) bulk_store_wait_read();
         __syncwarp();
         const int iters = (nsamp + 31) >> 5;
-        constexpr int U = 4;                       // lane-slots per batch: all gathers of a batch are in flight together
+        uint32_t cnt_packed = 0;               // per-lane exploration counts, one byte per ant of the chunk
         for (int it0 = 0; it0 < iters; it0 += U) {
-            int fs[U], es[U];
-            uint32_t cw[U], mt[U];
-            double fd[U], ph[U][NPH];
-            uint8_t wl[U];
+            uint32_t cw[U];
+            const uint8_t *rp[U];
+            uint4 lo[U], hi[U];                // record halves (P == 2 fast path) or generic fields packed likewise
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (it0 + u >= iters) break;                                   // warp-uniform
                 const int f_raw = (it0 + u) * 32 + lane;
-                const int f = f_raw < nsamp ? f_raw : 0;                       // idle tail lanes shadow sample 0
+                const int f = f_raw < nsamp ? f_raw : 0;                       // idle lanes / slots shadow sample 0
                 const int aj = (int)(((uint32_t)f * s2_magic) >> 20);         // f / S2
-                const uint32_t c2 = wcell[g * S2 + f];
-                const int e = wprep[g + aj].e;
-                const int cell = (int)(c2 >> 16) * p.Hp + (int)(c2 & 0xFFFFu);
-                const int64_t eoff = (int64_t)e * p.plane + cell;
-                fs[u] = f_raw; es[u] = e; cw[u] = c2;
-                mt[u] = need_meta ? p.meta[eoff] : 0u;
-                fd[u] = need_food ? p.food[eoff] : 0.0;
-                wl[u] = need_walls ? p.walls[eoff] : (uint8_t)0;
-                const double *php = p.phero + (int64_t)e * p.P * p.plane + cell;
-#pragma unroll
-                for (int kp = 0; kp < NPH; ++kp) ph[u][kp] = ((ph_need >> kp) & 1u) ? php[(int64_t)kp * p.plane] : 0.0;
+                cw[u] = wcell[g * S2 + f];
+                const int cell = (int)(cw[u] >> 16) * p.Hp + (int)(cw[u] & 0xFFFFu);
+                rp[u] = wprep[g + aj].cells + ((int64_t)cell << rec_shift);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (it0 + u >= iters) break;                                   // warp-uniform
-                const bool valid = fs[u] < nsamp;
-                const int f = valid ? fs[u] : 0;
-                const int aj = (int)(((uint32_t)f * s2_magic) >> 20);
-                const int e = es[u];
-                const int ix = (int)(cw[u] >> 16), iy = (int)(cw[u] & 0xFFFFu);
-                if (explore_on) {
-                    const uint32_t eg = mt[u] & 0xFFFFu;
-                    const bool unexplored = valid && ((eg == 0u) || (eg == obs_gen));     // gather-before-scatter, Q7
-                    if (valid && eg == 0u && !(dbg & 4))
-                        reinterpret_cast<uint16_t *>(p.meta + (int64_t)e * p.plane + ix * p.Hp + iy)[0] = (uint16_t)obs_gen;
-                    const unsigned peers = __match_any_sync(0xffffffffu, aj);
-                    const unsigned votes = __ballot_sync(0xffffffffu, unexplored) & peers;
-                    if (votes && lane == __ffs(peers) - 1) atomicAdd(s_cnt + warp * 32 + g + aj, __popc(votes));
+                if (LAYOUT != 0) {             // P == 2: {ph0, ph1} | {food, meta, wall}
+                    lo[u] = *reinterpret_cast<const uint4 *>(rp[u]);
+                    hi[u] = *reinterpret_cast<const uint4 *>(rp[u] + 16);
+                } else {                       // generic record: gather the fields into the same register shape
+                    const double fdv = *reinterpret_cast<const double *>(rp[u] + food_off);
+                    const uint32_t mtv = *reinterpret_cast<const uint32_t *>(rp[u] + meta_off);
+                    const uint32_t wlv = *(rp[u] + wall_off);
+                    hi[u] = make_uint4((uint32_t)__double2loint(fdv), (uint32_t)__double2hiint(fdv), mtv, wlv);
+                    lo[u] = make_uint4(0u, 0u, 0u, 0u);
                 }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int f_raw = (it0 + u) * 32 + lane;
+                const bool valid = f_raw < nsamp;
                 if (!valid) continue;
+                const int f = f_raw;
+                const int aj = (int)(((uint32_t)f * s2_magic) >> 20);
                 const int s = f - aj * S2;
+                const int ix = (int)(cw[u] >> 16), iy = (int)(cw[u] & 0xFFFFu);
+                const uint32_t mt = hi[u].z;
+                const double fd = __hiloint2double((int)hi[u].y, (int)hi[u].x);
+                const bool wl = (hi[u].w & 0xFFu) != 0;
+                if (explore_on) {
+                    const uint32_t eg = mt & 0xFFFFu;
+                    if ((eg == 0u) || (eg == obs_gen)) cnt_packed += 1u << (8 * aj);       // gather-before-scatter, Q7
+                    if (eg == 0u)
+                        *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(rp[u]) + meta_off) = (uint16_t)obs_gen;
+                }
                 const bool vis = s_mask[s] != 0;
                 float *o = wobs + f * C;
-                const int32_t *hl = p.hill + 4 * e;
+                const AntPrep &q = wprep[g + aj];
+                const int32_t *hl = p.hill + 4 * q.e;
                 // mask * (perception + 1) - 1 (RL_api.py:147-148): the +1-1 round trip changes a value by at most
                 // 2^-53 absolute, far below the resolution of the f32 observation, so visible samples pass through.
                 if (LAYOUT != 0) {
-                    if (vis) {
-                        o[0] = ((mt[u] >> 16) == occ_gen) ? 1.f : 0.f;                                // :136-142
-                        o[1] = (float)(ph[u][0] * inv_max);                                           // :124-125
-                        o[2] = (float)(ph[u][1] * inv_max);
-                        o[3] = in_hill(hl, ix, iy) ? 1.f : 0.f;                                       // :130-131
-                        o[4] = wl[u] ? 1.f : 0.f;                                                     // :128-129
-                        o[5] = (float)fd[u];                                                          // :126-127
-                        if (LAYOUT == 2) {                                                            // :132-135
-                            float rv = 0.f;
-                            unsigned long long rm = wprep[g + aj].rocks;
-                            const double *rc = p.rock_c + (int64_t)e * p.R * 2;
-                            const double *rr = p.rock_rad + (int64_t)e * p.R;
+                    const double ph0 = __hiloint2double((int)lo[u].y, (int)lo[u].x);
+                    const double ph1 = __hiloint2double((int)lo[u].w, (int)lo[u].z);
+                    float v0 = ((mt >> 16) == occ_gen) ? 1.f : 0.f;                                   // :136-142
+                    float v1 = (float)(ph0 * inv_max);                                                // :124-125
+                    float v2 = (float)(ph1 * inv_max);
+                    float v3 = in_hill(hl, ix, iy) ? 1.f : 0.f;                                       // :130-131
+                    float v4 = wl ? 1.f : 0.f;                                                        // :128-129
+                    float v5 = (float)fd;                                                             // :126-127
+                    float v6 = 0.f;
+                    if (LAYOUT == 2) {                                                                // :132-135
+                        unsigned long long rm = q.rocks;
+                        if (rm) {
+                            const double *rc = p.rock_c + (int64_t)q.e * p.R * 2;
+                            const double *rr = p.rock_rad + (int64_t)q.e * p.R;
                             while (rm) {
                                 int r = __ffsll((long long)rm) - 1;
                                 rm &= rm - 1;
                                 double ddx = (double)ix - rc[2 * r], ddy = (double)iy - rc[2 * r + 1];
-                                if (sqrt(ddx * ddx + ddy * ddy) < rr[r]) { rv = 1.f; break; }
+                                if (sqrt(ddx * ddx + ddy * ddy) < rr[r]) { v6 = 1.f; break; }
                             }
-                            o[6] = rv;
                         }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < (LAYOUT == 2 ? 7 : 6); ++c) o[c] = -1.f;
                     }
+                    if (!vis) { v0 = v1 = v2 = v3 = v4 = v5 = v6 = -1.f; }
+                    o[0] = v0; o[1] = v1; o[2] = v2; o[3] = v3; o[4] = v4; o[5] = v5;
+                    if (LAYOUT == 2) o[6] = v6;
                 } else {
                     for (int c = 0; c < C; ++c) {
                         double v;
                         switch (p.ch_kind[c]) {
-                            case 0: v = ((mt[u] >> 16) == occ_gen) ? 1.0 : 0.0; break;
-                            case 1: {
-                                int a = p.ch_arg[c];
-                                double pv = a == 0 ? ph[u][0] : a == 1 ? ph[u][1] : a == 2 ? ph[u][NPH > 2 ? 2 : 0]
-                                                                                        : ph[u][NPH > 3 ? 3 : 0];
-                                v = pv * inv_max;
-                                break;
-                            }
+                            case 0: v = ((mt >> 16) == occ_gen) ? 1.0 : 0.0; break;
+                            case 1: v = *reinterpret_cast<const double *>(rp[u] + 8 * p.ch_arg[c]) * inv_max; break;
                             case 2: v = in_hill(hl, ix, iy) ? 1.0 : 0.0; break;
-                            case 3: v = wl[u] ? 1.0 : 0.0; break;
-                            case 4: v = fd[u]; break;
+                            case 3: v = wl ? 1.0 : 0.0; break;
+                            case 4: v = fd; break;
                             default: {
                                 v = 0.0;
-                                unsigned long long rm = wprep[g + aj].rocks;
-                                const double *rc = p.rock_c + (int64_t)e * p.R * 2;
-                                const double *rr = p.rock_rad + (int64_t)e * p.R;
+                                unsigned long long rm = q.rocks;
+                                const double *rc = p.rock_c + (int64_t)q.e * p.R * 2;
+                                const double *rr = p.rock_rad + (int64_t)q.e * p.R;
                                 while (rm) {
                                     int r = __ffsll((long long)rm) - 1;
                                     rm &= rm - 1;
@@ -512,13 +507,25 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 }
             }
         }
+        // exploration counts of the chunk: byte-wise warp reduction of the packed per-lane counters
+        if (explore_on) {
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) {
+                // split into even / odd bytes so that sums up to 255 per ant cannot carry into a neighbour
+                uint32_t ev = cnt_packed & 0x00FF00FFu, od = (cnt_packed >> 8) & 0x00FF00FFu;
+                ev += __shfl_xor_sync(0xffffffffu, ev, sh);
+                od += __shfl_xor_sync(0xffffffffu, od, sh);
+                cnt_packed = (ev & 0x00FF00FFu) | ((od & 0x00FF00FFu) << 8);
+            }
+            if (lane < n_in) s_cnt[warp * 32 + g + lane] = (int)((cnt_packed >> (8 * lane)) & 0xFFu);
+        }
         // flush the staged (n_in x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
         float *dst = obs + i0 * SC;
         const uint32_t bytes = (uint32_t)(n_in * SC * 4);
         if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && !(dbg & 2)) bulk_store_s2g(dst, wobs, bytes);
+            if (lane == 0) bulk_store_s2g(dst, wobs, bytes);
         } else {
             __syncwarp();
             for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
@@ -565,8 +572,7 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
     int e = (int)(i / p.N);
     int a = (int)(i - (int64_t)e * p.N);
     double x = p.x[i], y = p.y[i], th = p.theta[i];
-    int64_t eoff = (int64_t)e * p.plane;
-    if (p.walls[eoff + (int64_t)cell_of(x, p.W) * p.Hp + cell_of(y, p.H)]) {
+    if (*rec_wall(p, rec_at(p, e, cell_of(x, p.W) * p.Hp + cell_of(y, p.H)))) {
         x = p.prev_x[i]; y = p.prev_y[i];
         double u = noise ? noise[i] : philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)a);
         th += u - 0.5;                                                         // not re-wrapped (Q3)
@@ -574,55 +580,106 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
     }
     if (finish) {
         p.prev_x[i] = x; p.prev_y[i] = y; p.prev_theta[i] = th;
-        atomicMax(p.owner + eoff + (int64_t)cell_of(x, p.W) * p.Hp + cell_of(y, p.H), owner_stamp | (uint32_t)a);
+        atomicMax(p.owner + (int64_t)e * p.plane + cell_of(x, p.W) * p.Hp + cell_of(y, p.H), owner_stamp | (uint32_t)a);
         p.reward_state[i] = (uint8_t)((double)p.reward_state[i] * 0.9);        // ants.py:130
     }
 }
 
-// CircleObstacles.update, first half (circle_obstacles.py:35-40): ants push rocks.  One block per env, one warp
-// per rock (looping); contributions are summed in ant order like np.sum(axis=0).
+// CircleObstacles.update, first half (circle_obstacles.py:35-40): ants push rocks.  One block per env.
+// Ant-centric: every ant looks up the rocks registered near it in the rock grid (built from the current
+// centres) and appends its pushes to a shared list; one thread per rock then sums its entries in ant order like
+// np.sum(axis=0) and moves the rock.  If the list overflows, the env falls back to the exhaustive warp-per-rock
+// scan.  Finally the grid is rebuilt from the new centres.
+constexpr int kPushCap = 768;
 __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
-    int e = blockIdx.x;
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    {   // the rock grid is rebuilt from the new centres
-        const int gcells = ((p.W + 31) >> kGridShift) * ((p.H + 31) >> kGridShift);
+    __shared__ int s_n;
+    __shared__ int s_rock[kPushCap], s_ant[kPushCap];
+    __shared__ double s_px[kPushCap], s_py[kPushCap];
+    const int e = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
+    double *rc = p.rock_c + (int64_t)e * p.R * 2;
+    const double *rr = p.rock_rad + (int64_t)e * p.R;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int a = threadIdx.x; a < p.N; a += blockDim.x) {
+        const double x = xs[a], y = ys[a];
+        unsigned long long rm = rock_candidates(p, e, x, y);
+        while (rm) {
+            int r = __ffsll((long long)rm) - 1;
+            rm &= rm - 1;
+            double vx = rc[2 * r] - x, vy = rc[2 * r + 1] - y;
+            double d = sqrt(vx * vx + vy * vy);
+            double rad = rr[r];
+            if (!(d > rad)) {
+                double fac = 1.0 - rad / (d + 0.001);
+                int slot = atomicAdd(&s_n, 1);
+                if (slot < kPushCap) { s_rock[slot] = r; s_ant[slot] = a; s_px[slot] = vx * fac; s_py[slot] = vy * fac; }
+            }
+        }
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n <= kPushCap) {
+        for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
+            double sx = 0.0, sy = 0.0;
+            int last = -1;
+            for (;;) {                                   // entries of rock r in increasing ant order
+                int best = -1, besta = 0x7fffffff;
+                for (int k = 0; k < n; ++k)
+                    if (s_rock[k] == r && s_ant[k] > last && s_ant[k] < besta) { besta = s_ant[k]; best = k; }
+                if (best < 0) break;
+                sx += s_px[best]; sy += s_py[best];
+                last = besta;
+            }
+            if (last >= 0) {
+                double wt = p.rock_w[(int64_t)e * p.R + r];
+                rc[2 * r] = rc[2 * r] - sx / wt;
+                rc[2 * r + 1] = rc[2 * r + 1] - sy / wt;
+            } else {                                     // centers -= 0 / weight
+                rc[2 * r] = rc[2 * r] - 0.0;
+                rc[2 * r + 1] = rc[2 * r + 1] - 0.0;
+            }
+        }
+    } else {
+        for (int r = warp; r < p.R; r += nwarp) {
+            double cx = rc[2 * r], cy = rc[2 * r + 1], rad = rr[r];
+            double sx = 0.0, sy = 0.0;
+            for (int a0 = 0; a0 < p.N; a0 += 32) {
+                int a = a0 + lane;
+                double px = 0.0, py = 0.0;
+                bool hit = false;
+                if (a < p.N) {
+                    double vx = cx - xs[a], vy = cy - ys[a];
+                    double d = sqrt(vx * vx + vy * vy);
+                    if (!(d > rad)) {
+                        double fac = 1.0 - rad / (d + 0.001);
+                        px = vx * fac; py = vy * fac; hit = true;
+                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    int l = __ffs(m) - 1;
+                    m &= m - 1;
+                    sx += __shfl_sync(0xffffffffu, px, l);
+                    sy += __shfl_sync(0xffffffffu, py, l);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double wt = p.rock_w[(int64_t)e * p.R + r];
+                rc[2 * r] = cx - sx / wt;
+                rc[2 * r + 1] = cy - sy / wt;
+            }
+        }
+    }
+    __syncthreads();
+    {   // rebuild the rock grid from the new centres
+        const int gcells = p.grid_w * p.grid_h;
         unsigned long long *g = p.rock_grid + (int64_t)e * gcells;
         for (int k = threadIdx.x; k < gcells; k += blockDim.x) g[k] = 0ull;
         __syncthreads();
-    }
-    const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
-    for (int r = warp; r < p.R; r += nwarp) {
-        double *c = p.rock_c + ((int64_t)e * p.R + r) * 2;
-        double cx = c[0], cy = c[1], rad = p.rock_rad[(int64_t)e * p.R + r];
-        double sx = 0.0, sy = 0.0;
-        for (int a0 = 0; a0 < p.N; a0 += 32) {
-            int a = a0 + lane;
-            double px = 0.0, py = 0.0;
-            bool hit = false;
-            if (a < p.N) {
-                double vx = cx - xs[a], vy = cy - ys[a];
-                double d = sqrt(vx * vx + vy * vy);
-                if (!(d > rad)) {
-                    double fac = 1.0 - rad / (d + 0.001);
-                    px = vx * fac; py = vy * fac; hit = true;
-                }
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                int l = __ffs(m) - 1;
-                m &= m - 1;
-                sx += __shfl_sync(0xffffffffu, px, l);
-                sy += __shfl_sync(0xffffffffu, py, l);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double wt = p.rock_w[(int64_t)e * p.R + r];
-            double nx = cx - sx / wt, ny = cy - sy / wt;
-            c[0] = nx;
-            c[1] = ny;
-            rock_grid_mark(p, e, r, nx, ny, rad);
-        }
+        for (int r = threadIdx.x; r < p.R; r += blockDim.x) rock_grid_mark(p, e, r, rc[2 * r], rc[2 * r + 1], rr[r]);
     }
 }
 
@@ -636,7 +693,12 @@ __global__ void __launch_bounds__(256) k_rocks_push_ants(Params p, uint32_t owne
     const double *rc = p.rock_c + (int64_t)e * p.R * 2;
     const double *rr = p.rock_rad + (int64_t)e * p.R;
     double sx = 0.0, sy = 0.0;
-    for (int r = 0; r < p.R; ++r) {
+    // only rocks registered in the ant's grid cell can be within their radius (the grid box is wider than that);
+    // candidates are visited in rock order like np.sum(axis=1)
+    unsigned long long rm = rock_candidates(p, e, x, y);
+    while (rm) {
+        int r = __ffsll((long long)rm) - 1;
+        rm &= rm - 1;
         double vx = rc[2 * r] - x, vy = rc[2 * r + 1] - y;
         double d = sqrt(vx * vx + vy * vy);
         double rad = rr[r];
@@ -649,110 +711,134 @@ __global__ void __launch_bounds__(256) k_rocks_push_ants(Params p, uint32_t owne
     y = pymod(y + sy, (double)p.H);
     p.x[i] = x; p.y[i] = y;
     p.prev_x[i] = x; p.prev_y[i] = y; p.prev_theta[i] = p.theta[i];
-    int64_t eoff = (int64_t)e * p.plane;
-    atomicMax(p.owner + eoff + (int64_t)cell_of(x, p.W) * p.Hp + cell_of(y, p.H), owner_stamp | (uint32_t)a);
+    atomicMax(p.owner + (int64_t)e * p.plane + cell_of(x, p.W) * p.Hp + cell_of(y, p.H), owner_stamp | (uint32_t)a);
     p.reward_state[i] = (uint8_t)((double)p.reward_state[i] * 0.9);
 }
 
 // ------------------------------------------------------------------------------------------------ pheromone field
-// Dense pass for DIFFUSE_FACTOR == 0: walls.py:30 (zero inside walls), pheromone.py:44 reduced to its centre tap
-// (bit-identical to convolve2d with an all-zero ring), pheromone.py:45 threshold, and the whole-plane clamp of
-// pheromone.py:41.  Pure streaming: 16 B read + 16 B written per pair of cells, plus the wall mask.
-__global__ void __launch_bounds__(256) k_evaporate_dense(Params p, int chunks) {
-    const int64_t plane2 = p.plane >> 1;                                       // Hp is even
-    const int64_t ep = blockIdx.x / chunks;                                    // e * P + p
-    const int64_t chunk = blockIdx.x - ep * chunks;
-    const int e = (int)(ep / p.P);
-    double2 *ph = reinterpret_cast<double2 *>(p.phero + ep * p.plane);
-    const uchar2 *wl = reinterpret_cast<const uchar2 *>(p.walls + (int64_t)e * p.plane);
-    const double c = p.filt_center, mx = p.phero_max_val;
-    const bool clamp = p.has_max_val && p.N > 0;
-    for (int64_t j = chunk * blockDim.x + threadIdx.x; j < plane2; j += (int64_t)chunks * blockDim.x) {
-        double2 v = ph[j];
-        if (v.x == 0.0 && v.y == 0.0) continue;
-        uchar2 wv = wl[j];
-        double a = wv.x ? 0.0 : v.x * c;
-        double b = wv.y ? 0.0 : v.y * c;
+// One cell of Walls.update's field zeroing (walls.py:30), Pheromone.update reduced to its centre tap for
+// DIFFUSE_FACTOR == 0 (pheromone.py:44, bit-identical to convolve2d with an all-zero ring), the threshold of
+// pheromone.py:45 and the whole-plane clamp of pheromone.py:41.  Returns true if pheromone remains.
+__device__ __forceinline__ bool evaporate_record(const Params &p, uint8_t *r, double c, double mx, bool clamp) {
+    bool any = false;
+    if (p.P == 2) {
+        double2 v = *reinterpret_cast<double2 *>(r);
+        if (v.x == 0.0 && v.y == 0.0) return false;
+        const bool wl = *rec_wall(p, r) != 0;
+        double a = wl ? 0.0 : v.x * c, b = wl ? 0.0 : v.y * c;
         a = a < 0.01 ? 0.0 : a;
         b = b < 0.01 ? 0.0 : b;
         if (clamp) { a = fmin(a, mx); b = fmin(b, mx); }
-        ph[j] = make_double2(a, b);
+        *reinterpret_cast<double2 *>(r) = make_double2(a, b);
+        any = (a != 0.0) || (b != 0.0);
+    } else {
+        const bool wl = *rec_wall(p, r) != 0;
+        for (int k = 0; k < p.P; ++k) {
+            double v = *rec_phero(r, k);
+            if (v == 0.0) continue;
+            double a = wl ? 0.0 : v * c;
+            a = a < 0.01 ? 0.0 : a;
+            if (clamp) a = fmin(a, mx);
+            *rec_phero(r, k) = a;
+            any |= a != 0.0;
+        }
     }
+    return any;
 }
 
-// Active-tile variant of the same pass: one warp per 16x16 tile, tiles without pheromone are skipped by their
-// activity byte; a tile whose cells all decayed to zero is retired.
-__global__ void __launch_bounds__(256) k_evaporate_tiles(Params p) {
+// Dense pass over every cell of every environment.
+__global__ void __launch_bounds__(256) k_evaporate_dense(Params p) {
+    const int64_t n = (int64_t)p.E * p.plane;
+    const double c = p.filt_center, mx = p.phero_max_val;
+    const bool clamp = p.has_max_val && p.N > 0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        evaporate_record(p, p.cells + (j << p.rec_shift), c, mx, clamp);
+}
+
+// Active-tile variant, two launches: (1) compact the ids of the tiles whose activity byte is set into a list,
+// (2) one warp per listed 16x16 tile: all 8 record loads of a lane are issued before the first store; a tile whose
+// cells all decayed to zero is retired.
+__global__ void __launch_bounds__(256) k_tiles_compact(Params p, uint32_t *__restrict__ list) {
+    const int64_t ntiles = (int64_t)p.E * p.tiles_x * p.tiles_y;
+    const int lane = threadIdx.x & 31;
+    for (int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane); t0 < ntiles;
+         t0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = t0 + lane;
+        const bool on = t < ntiles && p.tile_active[t] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (m == 0) continue;
+        unsigned long long basev = 0;
+        if (lane == 0) basev = atomicAdd(p.tile_counter, (unsigned long long)__popc(m));
+        basev = __shfl_sync(0xffffffffu, basev, 0);
+        if (on) list[basev + __popc(m & ((1u << lane) - 1))] = (uint32_t)t;
+    }
+}
+__global__ void __launch_bounds__(256) k_evaporate_tiles(Params p, const uint32_t *__restrict__ list) {
     const int lane = threadIdx.x & 31;
     const int64_t warp_g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t tiles_per_plane = (int64_t)p.tiles_x * p.tiles_y;
-    const int64_t ntiles = (int64_t)p.E * p.P * tiles_per_plane;
+    const int64_t n = (int64_t)*p.tile_counter;
+    const int tiles_per_env = p.tiles_x * p.tiles_y;
     const double c = p.filt_center, mx = p.phero_max_val;
     const bool clamp = p.has_max_val && p.N > 0;
-    unsigned long long processed = 0;
-    // each warp scans 32 activity bytes at a time, interleaved across warps for balance
-    for (int64_t g = warp_g * 32; g < ntiles; g += nwarps * 32) {
-        int64_t t = g + lane;
-        unsigned act = __ballot_sync(0xffffffffu, t < ntiles && p.tile_active[t] != 0);
-        while (act) {
-            int l = __ffs(act) - 1;
-            act &= act - 1;
-            int64_t tt = g + l;
-            int64_t ep = tt / tiles_per_plane;
-            int64_t tin = tt - ep * tiles_per_plane;
-            int tx = (int)(tin / p.tiles_y), ty = (int)(tin - (int64_t)tx * p.tiles_y);
-            int e = (int)(ep / p.P);
-            // 16 rows x 16 cells: lane -> row = lane / 2 (+ 0), half = lane & 1 (8 cells = 4 double2)
-            int row = tx * kTile + (lane >> 1);
-            int col = ty * kTile + (lane & 1) * 8;
-            bool any = false;
-            if (row < p.W && col < p.Hp) {
-                int64_t off = (int64_t)row * p.Hp + col;
-                double2 *ph = reinterpret_cast<double2 *>(p.phero + ep * p.plane + off);
-                const uchar2 *wl = reinterpret_cast<const uchar2 *>(p.walls + (int64_t)e * p.plane + off);
-                double2 v[4];
+    for (int64_t idx = warp_g; idx < n; idx += nwarps) {
+        const uint32_t tt = list[idx];
+        const int e = (int)(tt / (uint32_t)tiles_per_env);
+        const int tin = (int)(tt - (uint32_t)e * (uint32_t)tiles_per_env);
+        const int tx = tin / p.tiles_y, ty = tin - tx * p.tiles_y;
+        // 16 rows x 16 records: per pass the warp covers 2 rows (lane -> row = pass*2 + lane/16, col = lane%16),
+        // i.e. two contiguous 512-byte runs, every sector fully used
+        bool any = false;
+        if (p.P == 2) {
+            double2 v[kTile / 2];
+            uint8_t wl[kTile / 2];
+            uint8_t *rp[kTile / 2];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = ph[k];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (v[k].x == 0.0 && v[k].y == 0.0) continue;
-                    uchar2 wv = wl[k];
-                    double a = wv.x ? 0.0 : v[k].x * c;
-                    double b = wv.y ? 0.0 : v[k].y * c;
-                    a = a < 0.01 ? 0.0 : a;
-                    b = b < 0.01 ? 0.0 : b;
-                    if (clamp) { a = fmin(a, mx); b = fmin(b, mx); }
-                    ph[k] = make_double2(a, b);
-                    any |= (a != 0.0) || (b != 0.0);
-                }
+            for (int pass = 0; pass < kTile / 2; ++pass) {
+                int row = tx * kTile + pass * 2 + (lane >> 4);
+                row = row < p.W ? row : p.W - 1;                               // clamp: rows past the map repeat the last
+                rp[pass] = rec_at(p, e, row * p.Hp + ty * kTile + (lane & 15));
+                v[pass] = *reinterpret_cast<const double2 *>(rp[pass]);
+                wl[pass] = rp[pass][p.wall_off];
             }
-            if (!__any_sync(0xffffffffu, any) && lane == 0) p.tile_active[tt] = 0;
-            ++processed;
+#pragma unroll
+            for (int pass = 0; pass < kTile / 2; ++pass) {
+                if (v[pass].x == 0.0 && v[pass].y == 0.0) continue;
+                double a = wl[pass] ? 0.0 : v[pass].x * c, b = wl[pass] ? 0.0 : v[pass].y * c;
+                a = a < 0.01 ? 0.0 : a;
+                b = b < 0.01 ? 0.0 : b;
+                if (clamp) { a = fmin(a, mx); b = fmin(b, mx); }
+                *reinterpret_cast<double2 *>(rp[pass]) = make_double2(a, b);
+                any |= (a != 0.0) || (b != 0.0);
+            }
+        } else {
+#pragma unroll 1
+            for (int pass = 0; pass < kTile / 2; ++pass) {
+                int row = tx * kTile + pass * 2 + (lane >> 4);
+                if (row < p.W) any |= evaporate_record(p, rec_at(p, e, row * p.Hp + ty * kTile + (lane & 15)), c, mx, clamp);
+            }
         }
+        if (!__any_sync(0xffffffffu, any) && lane == 0) p.tile_active[tt] = 0;
     }
-    if (lane == 0 && processed) atomicAdd(p.tile_counter, processed);
 }
 
 // Diffusion stencil for DIFFUSE_FACTOR != 0 (pheromone.py:44, 3x3 zero-filled convolution) with the wall
-// zeroing of walls.py:30 applied to the inputs, threshold and clamp; reads `phero`, writes `phero_alt`.
-// Tile of 32 x 32 outputs per block, halo staged in shared memory.
+// zeroing of walls.py:30 applied to the inputs, threshold and clamp; reads the records, writes `phero_alt`
+// (k_diffuse_commit copies it back).  Tile of 32 x 32 outputs per block, halo staged in shared memory.
 constexpr int kStX = 32, kStY = 32;
 __global__ void __launch_bounds__(256) k_diffuse_stencil(Params p, int nbx, int nby) {
     __shared__ double tile[kStX + 2][kStY + 2 + 1];
     const int64_t ep = blockIdx.x / (nbx * nby);
     const int brem = (int)(blockIdx.x - ep * (nbx * nby));
-    const int e = (int)(ep / p.P);
+    const int e = (int)(ep / p.P), k = (int)(ep - (int64_t)e * p.P);
     const int x0 = (brem / nby) * kStX, y0 = (brem % nby) * kStY;
-    const double *src = p.phero + ep * p.plane;
-    const uint8_t *wl = p.walls + (int64_t)e * p.plane;
     for (int t = threadIdx.x; t < (kStX + 2) * (kStY + 2); t += blockDim.x) {
         int lx = t / (kStY + 2), ly = t - lx * (kStY + 2);
         int gx = x0 + lx - 1, gy = y0 + ly - 1;
         double v = 0.0;
         if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
-            int64_t off = (int64_t)gx * p.Hp + gy;
-            v = wl[off] ? 0.0 : src[off];
+            uint8_t *r = rec_at(p, e, gx * p.Hp + gy);
+            v = *rec_wall(p, r) ? 0.0 : *rec_phero(r, k);
         }
         tile[lx][ly] = v;
     }
@@ -775,6 +861,14 @@ __global__ void __launch_bounds__(256) k_diffuse_stencil(Params p, int nbx, int 
         dst[(int64_t)gx * p.Hp + gy] = acc;
     }
 }
+__global__ void __launch_bounds__(256) k_diffuse_commit(Params p) {
+    const int64_t n = (int64_t)p.E * p.plane;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t e = j / p.plane, cell = j - e * p.plane;
+        uint8_t *r = p.cells + (j << p.rec_shift);
+        for (int k = 0; k < p.P; ++k) *rec_phero(r, k) = p.phero_alt[(e * p.P + k) * p.plane + cell];
+    }
+}
 
 // Ants.emit_pheromones -> Pheromone.add_pheromones (ants.py:98-100, pheromone.py:36-41): the owner of each cell
 // adds its activation and clamps to max_val.
@@ -784,18 +878,20 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     int e = (int)(i / p.N);
     int a = (int)(i - (int64_t)e * p.N);
     int cx = cell_of(p.x[i], p.W), cy = cell_of(p.y[i], p.H);
-    int64_t cell = (int64_t)cx * p.Hp + cy;
+    int cell = cx * p.Hp + cy;
     if (p.owner[(int64_t)e * p.plane + cell] != (owner_stamp | (uint32_t)a)) return;
+    uint8_t *r = rec_at(p, e, cell);
+    bool wrote = false;
     for (int k = 0; k < p.P; ++k) {
         double av = p.act[(int64_t)k * p.EN + i];
         if (av == 0.0) continue;
-        double *ph = p.phero + ((int64_t)e * p.P + k) * p.plane + cell;
-        double v = *ph + av;
+        double v = *rec_phero(r, k) + av;
         if (p.has_max_val) v = fmin(v, p.phero_max_val);
-        *ph = v;
-        if (p.tile_active != nullptr)
-            p.tile_active[((int64_t)e * p.P + k) * p.tiles_x * p.tiles_y + (int64_t)(cx / kTile) * p.tiles_y + cy / kTile] = 1;
+        *rec_phero(r, k) = v;
+        wrote = true;
     }
+    if (wrote && p.tile_active != nullptr)
+        p.tile_active[((int64_t)e * p.tiles_x + cx / kTile) * p.tiles_y + cy / kTile] = 1;
 }
 
 // Anthill.update (anthill.py:41-46) for the cells queued by k_food_commit.
@@ -803,7 +899,7 @@ __global__ void __launch_bounds__(256) k_absorb_list(Params p) {
     uint32_t n = *p.absorb_count;
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
         uint32_t e = p.absorb_list[2 * k], c = p.absorb_list[2 * k + 1];
-        unsigned long long *fp = reinterpret_cast<unsigned long long *>(p.food + (int64_t)e * p.plane + c);
+        unsigned long long *fp = reinterpret_cast<unsigned long long *>(rec_food(p, rec_at(p, (int)e, (int)c)));
         double v = __longlong_as_double((long long)atomicExch(fp, 0ull));      // qte -= qte * area
         if (v != 0.0) atomicAdd(p.hill_food + e, v);
     }
@@ -825,7 +921,7 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
         for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
             int cx = x0 + t / bh, cy = y0 + t % bh;
             if (!in_hill(hl, cx, cy)) continue;
-            double *fp = p.food + (int64_t)e * p.plane + (int64_t)cx * p.Hp + cy;
+            double *fp = rec_food(p, rec_at(p, e, cx * p.Hp + cy));
             double v = *fp;
             if (v != 0.0) { acc += v; *fp = v - v; }
         }
@@ -840,36 +936,68 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
 }
 
 // ------------------------------------------------------------------------------------------------ import / export helpers
-__global__ void k_meta_from_explored(Params p, const uint8_t *__restrict__ explored_dense) {
-    int64_t n = (int64_t)p.E * p.W * p.H;
+// dense host-layout arrays <-> record fields.  `dense` is [E][planes_per_env][W][H]; field = plane `k` of them.
+__global__ void k_pack_f64(Params p, const double *__restrict__ dense, int planes_per_env, int k, int byte_off) {
+    const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
-        p.meta[ex * p.Hp + y] = explored_dense[j] ? 0xFFFFu : 0u;
+        int64_t e = ex / p.W;
+        int x = (int)(ex - e * p.W);
+        double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
+        *reinterpret_cast<double *>(rec_at(p, (int)e, x * p.Hp + y) + byte_off) = v;
     }
 }
-__global__ void k_explored_from_meta(Params p, uint8_t *__restrict__ explored_dense) {
-    int64_t n = (int64_t)p.E * p.W * p.H;
+__global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off) {
+    const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
-        explored_dense[j] = (p.meta[ex * p.Hp + y] & 0xFFFFu) ? 1 : 0;
+        int64_t e = ex / p.W;
+        int x = (int)(ex - e * p.W);
+        dense[((e * planes_per_env + k) * p.W + x) * p.H + y] =
+            *reinterpret_cast<const double *>(rec_at(p, (int)e, x * p.Hp + y) + byte_off);
+    }
+}
+// what: 0 = walls (stored as 0/1), 1 = explored (meta low half: 0xFFFF = explored long ago; occupancy cleared)
+__global__ void k_pack_u8(Params p, const uint8_t *__restrict__ dense, int what) {
+    const int64_t n = (int64_t)p.E * p.W * p.H;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t ex = j / p.H;
+        int y = (int)(j - ex * p.H);
+        int64_t e = ex / p.W;
+        int x = (int)(ex - e * p.W);
+        uint8_t *r = rec_at(p, (int)e, x * p.Hp + y);
+        if (what == 0) *rec_wall(p, r) = dense[j] ? 1 : 0;
+        else *rec_meta(p, r) = dense[j] ? 0xFFFFu : 0u;
+    }
+}
+__global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what) {
+    const int64_t n = (int64_t)p.E * p.W * p.H;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t ex = j / p.H;
+        int y = (int)(j - ex * p.H);
+        int64_t e = ex / p.W;
+        int x = (int)(ex - e * p.W);
+        uint8_t *r = rec_at(p, (int)e, x * p.Hp + y);
+        dense[j] = what == 0 ? *rec_wall(p, r) : ((*rec_meta(p, r) & 0xFFFFu) ? 1 : 0);
     }
 }
 // generation counters are 16 bit: before one wraps, fold every live stamp into the "long ago" value
 __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
     int64_t n = (int64_t)p.E * p.plane;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t m = p.meta[j];
+        uint32_t *mp = rec_meta(p, p.cells + (j << p.rec_shift));
+        uint32_t m = *mp;
         uint32_t lo = m & 0xFFFFu, hi = m >> 16;
         if (fold_explored && lo) lo = 0xFFFFu;
         if (clear_occ) hi = 0;
-        p.meta[j] = (hi << 16) | lo;
+        *mp = (hi << 16) | lo;
     }
 }
 __global__ void k_rock_grid_build(Params p) {          // one block per env (after import)
     const int e = blockIdx.x;
-    const int gcells = ((p.W + 31) >> kGridShift) * ((p.H + 31) >> kGridShift);
+    const int gcells = p.grid_w * p.grid_h;
     unsigned long long *g = p.rock_grid + (int64_t)e * gcells;
     for (int k = threadIdx.x; k < gcells; k += blockDim.x) g[k] = 0ull;
     __syncthreads();
@@ -879,19 +1007,20 @@ __global__ void k_rock_grid_build(Params p) {          // one block per env (aft
 }
 __global__ void k_tiles_from_phero(Params p) {
     // mark every tile that holds a non-zero pheromone cell (after import)
-    const int64_t tiles_per_plane = (int64_t)p.tiles_x * p.tiles_y;
-    const int64_t ntiles = (int64_t)p.E * p.P * tiles_per_plane;
+    const int64_t tiles_per_env = (int64_t)p.tiles_x * p.tiles_y;
+    const int64_t ntiles = (int64_t)p.E * tiles_per_env;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += (int64_t)gridDim.x * blockDim.x) {
-        int64_t ep = t / tiles_per_plane;
-        int64_t tin = t - ep * tiles_per_plane;
-        int tx = (int)(tin / p.tiles_y), ty = (int)(tin - (int64_t)tx * p.tiles_y);
+        int e = (int)(t / tiles_per_env);
+        int tin = (int)(t - (int64_t)e * tiles_per_env);
+        int tx = tin / p.tiles_y, ty = tin - tx * p.tiles_y;
         bool any = false;
         for (int dx = 0; dx < kTile && !any; ++dx) {
             int row = tx * kTile + dx;
             if (row >= p.W) break;
-            const double *ph = p.phero + ep * p.plane + (int64_t)row * p.Hp + ty * kTile;
-            for (int dy = 0; dy < kTile; ++dy)
-                if (ty * kTile + dy < p.Hp && ph[dy] != 0.0) { any = true; break; }
+            for (int dy = 0; dy < kTile && !any; ++dy) {
+                uint8_t *r = rec_at(p, e, row * p.Hp + ty * kTile + dy);
+                for (int k = 0; k < p.P; ++k) any |= *rec_phero(r, k) != 0.0;
+            }
         }
         p.tile_active[t] = any ? 1 : 0;
     }
