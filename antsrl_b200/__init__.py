@@ -6,3 +6,10 @@ from ._cabi import AntsError, LIB_PATH, load_library          # noqa: F401
 from .batch import BatchedAnts, make_config, DEFAULT_MASK, KERNEL_FAMILIES   # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def dropin_path():
+    """Directory to put on sys.path in place of the reference checkout: it provides `environment`, `generator` and
+    `utils` with the reference's names and signatures, backed by the CUDA step loop."""
+    import os
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")

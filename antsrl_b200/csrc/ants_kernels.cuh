@@ -586,21 +586,20 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
 }
 
 // CircleObstacles.update, first half (circle_obstacles.py:35-40): ants push rocks.  One block per env.
-// Ant-centric: every ant looks up the rocks registered near it in the rock grid (built from the current
-// centres) and appends its pushes to a shared list; one thread per rock then sums its entries in ant order like
-// np.sum(axis=0) and moves the rock.  If the list overflows, the env falls back to the exhaustive warp-per-rock
-// scan.  Finally the grid is rebuilt from the new centres.
-constexpr int kPushCap = 768;
+//   phase 1 (thread per ant): every ant looks up the rocks registered near it in the rock grid (built from the
+//            current centres) and, for each rock it really touches, sets the bit of its ant-chunk in touch[rock].
+//   phase 2 (warp per rock): the warp walks only the touched chunks, in ant order, adding the pushes with an
+//            ordered ballot loop -- the same summation order as np.sum(axis=0); untouched ants contribute exact 0.
+//   phase 3: the rock grid is rebuilt from the new centres.
 __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
-    __shared__ int s_n;
-    __shared__ int s_rock[kPushCap], s_ant[kPushCap];
-    __shared__ double s_px[kPushCap], s_py[kPushCap];
+    __shared__ uint32_t s_touch[64];                     // ANTS_MAX_ROCKS
     const int e = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
     double *rc = p.rock_c + (int64_t)e * p.R * 2;
     const double *rr = p.rock_rad + (int64_t)e * p.R;
-    if (threadIdx.x == 0) s_n = 0;
+    const int G = ((p.N + 31) / 32 + 31) / 32 * 32;      // ants per chunk: a multiple of 32, at most 32 chunks
+    if (threadIdx.x < 64) s_touch[threadIdx.x] = 0u;
     __syncthreads();
     for (int a = threadIdx.x; a < p.N; a += blockDim.x) {
         const double x = xs[a], y = ys[a];
@@ -609,47 +608,23 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
             int r = __ffsll((long long)rm) - 1;
             rm &= rm - 1;
             double vx = rc[2 * r] - x, vy = rc[2 * r + 1] - y;
-            double d = sqrt(vx * vx + vy * vy);
-            double rad = rr[r];
-            if (!(d > rad)) {
-                double fac = 1.0 - rad / (d + 0.001);
-                int slot = atomicAdd(&s_n, 1);
-                if (slot < kPushCap) { s_rock[slot] = r; s_ant[slot] = a; s_px[slot] = vx * fac; s_py[slot] = vy * fac; }
-            }
+            if (!(sqrt(vx * vx + vy * vy) > rr[r])) atomicOr(&s_touch[r], 1u << (a / G));
         }
     }
     __syncthreads();
-    const int n = s_n;
-    if (n <= kPushCap) {
-        for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
-            double sx = 0.0, sy = 0.0;
-            int last = -1;
-            for (;;) {                                   // entries of rock r in increasing ant order
-                int best = -1, besta = 0x7fffffff;
-                for (int k = 0; k < n; ++k)
-                    if (s_rock[k] == r && s_ant[k] > last && s_ant[k] < besta) { besta = s_ant[k]; best = k; }
-                if (best < 0) break;
-                sx += s_px[best]; sy += s_py[best];
-                last = besta;
-            }
-            if (last >= 0) {
-                double wt = p.rock_w[(int64_t)e * p.R + r];
-                rc[2 * r] = rc[2 * r] - sx / wt;
-                rc[2 * r + 1] = rc[2 * r + 1] - sy / wt;
-            } else {                                     // centers -= 0 / weight
-                rc[2 * r] = rc[2 * r] - 0.0;
-                rc[2 * r + 1] = rc[2 * r + 1] - 0.0;
-            }
-        }
-    } else {
-        for (int r = warp; r < p.R; r += nwarp) {
-            double cx = rc[2 * r], cy = rc[2 * r + 1], rad = rr[r];
-            double sx = 0.0, sy = 0.0;
-            for (int a0 = 0; a0 < p.N; a0 += 32) {
+    for (int r = warp; r < p.R; r += nwarp) {
+        const double cx = rc[2 * r], cy = rc[2 * r + 1], rad = rr[r];
+        double sx = 0.0, sy = 0.0;
+        uint32_t tm = s_touch[r];
+        while (tm) {
+            const int g = __ffs(tm) - 1;
+            tm &= tm - 1;
+            const int a_end = min((g + 1) * G, p.N);
+            for (int a0 = g * G; a0 < a_end; a0 += 32) {
                 int a = a0 + lane;
                 double px = 0.0, py = 0.0;
                 bool hit = false;
-                if (a < p.N) {
+                if (a < a_end) {
                     double vx = cx - xs[a], vy = cy - ys[a];
                     double d = sqrt(vx * vx + vy * vy);
                     if (!(d > rad)) {
@@ -665,12 +640,12 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
                     sy += __shfl_sync(0xffffffffu, py, l);
                 }
             }
-            __syncwarp();
-            if (lane == 0) {
-                double wt = p.rock_w[(int64_t)e * p.R + r];
-                rc[2 * r] = cx - sx / wt;
-                rc[2 * r + 1] = cy - sy / wt;
-            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double wt = p.rock_w[(int64_t)e * p.R + r];
+            rc[2 * r] = cx - sx / wt;
+            rc[2 * r + 1] = cy - sy / wt;
         }
     }
     __syncthreads();

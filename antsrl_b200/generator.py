@@ -68,7 +68,8 @@ class PerlinGenerator:
                                   "CirclesGenerator or any object with generate(w, h) for walls")
 
 
-def generate_state(w, h, n_ants, n_pheromones, n_rocks, food_generator, walls_generator, seed=None, max_hold=5):
+def generate_state(w, h, n_ants, n_pheromones, n_rocks, food_generator, walls_generator, seed=None, max_hold=5,
+                   draw_ant_seed=True):
     """environment_generator.py:52-99 -> one env's initial state dict (shared schema, no env axis)."""
     if seed is not None:
         random.seed(seed)
@@ -101,7 +102,8 @@ def generate_state(w, h, n_ants, n_pheromones, n_rocks, food_generator, walls_ge
     st["x"] = np.mod(x, w)                      # Ants.__init__ -> warp_xy, ants.py:28
     st["y"] = np.mod(y, h)
     st["theta"] = t
-    st["seed"] = np.random.random(n_ants)       # ants.py:41
+    if draw_ant_seed:
+        st["seed"] = np.random.random(n_ants)   # ants.py:41
     st["activation"] = np.zeros((n_ants, n_pheromones))
     st["act_bool"] = True                       # ants.py:83
     st["rw_alias"] = True

@@ -139,5 +139,44 @@ def make_generator_fixtures():
                                                       os.path.getsize(path) / 1024))
 
 
+def make_mainloop_fixture():
+    """main.py's loop on the reference's own generator with the reference's own (untaped) global-RNG collision
+    noise: generate(seed=1000) -> agent.initialize (activate_all_pheromones(10)) -> np.random.seed(777) ->
+    observation -> 80 x [step(random actions); env.update()]."""
+    ref = ref_harness.load_reference()
+    ref_harness.set_diffuse(ref, 0, 0.001)
+    ref.gen.n_rocks = 0
+    reward = ref.rewards.All_Rewards(1, 2, 10, 1, 3)
+    api = ref.api.RLApi(reward, 1, 1, 40 / 180 * np.pi, 0.05, 0.5)
+    g = ref.gen.EnvironmentGenerator(200, 200, 50, 2, 0, ref.maps.CirclesGenerator(20, 5, 10),
+                                     ref.maps.CirclesGenerator(10, 5, 15), 80, seed=1000)
+    env = g.generate(api)
+    api.ants.activate_all_pheromones(np.ones((50, 2)) * 10)         # collect_agent.py:100-102
+    np.random.seed(777)
+    act = np.random.RandomState(4242)
+    ref.walls_proxy.noise_row = None
+    out = {"obs": [], "agent_state": [], "reward": [], "done": [], "xyt": [], "holding": [], "anthill_food": []}
+    obs0, as0, st0 = api.observation()
+    anthill = [o for o in env.objects if type(o).__name__ == "Anthill"][0]
+    for t in range(80):
+        rot = act.randint(0, 3, 50) - 1
+        ph = act.randint(0, 3, 50)
+        obs, ast, rew, done = api.step(rot, ph)
+        ref.walls_proxy.noise_row = None
+        env.update()
+        out["obs"].append(obs.astype(np.float32)); out["agent_state"].append(ast); out["reward"].append(np.array(rew, dtype=float))
+        out["done"].append(done); out["xyt"].append(api.ants.ants.copy()); out["holding"].append(api.ants.holding.copy())
+        out["anthill_food"].append(float(anthill.food))
+    path = os.path.join(HERE, "mainloop_s1000.npz")
+    np.savez_compressed(path, obs0=obs0.astype(np.float32), agent_state0=as0, state0=st0,
+                        final_phero=np.stack([o.phero for o in env.objects if type(o).__name__ == "Pheromone"]),
+                        final_food=[o for o in env.objects if type(o).__name__ == "Food"][0].qte,
+                        final_explored=reward.explored_map.astype(np.uint8), next_global_draw=np.random.random(),
+                        **{k: np.array(v) for k, v in out.items()})
+    print("mainloop_s1000 %.1f KB, delivered food %.0f" % (os.path.getsize(path) / 1024, out["anthill_food"][-1]))
+
+
 if __name__ == "__main__" and (not sys.argv[1:] or "gen" in sys.argv[1:]):
     make_generator_fixtures()
+if __name__ == "__main__" and (not sys.argv[1:] or "mainloop" in sys.argv[1:]):
+    make_mainloop_fixture()

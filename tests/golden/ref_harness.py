@@ -32,6 +32,8 @@ class _WallsNumpyProxy:
 
         def random(self, n):
             o = self._outer
+            if o.noise_row is None:          # untaped: the reference's own draw from the global RNG (walls.py:28)
+                return np.random.random(n)
             mask = o.last_mask
             assert mask is not None and int(mask.sum()) == int(n)
             vals = o.noise_row[mask]
