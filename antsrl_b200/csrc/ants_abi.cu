@@ -71,7 +71,7 @@ struct AntsBatch {
     double *st_reward = nullptr, *st_noise = nullptr;
     uint32_t *h_counts = nullptr;   // pinned: commit_count, absorb_count readback
     uint32_t *tile_list = nullptr;
-    int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128;
+    int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128, perceive_slow_wrap = 0;
 };
 
 namespace {
@@ -189,18 +189,13 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
         const uint32_t magic = (1u << 20) / (uint32_t)p.S2 + 1u;   // f / S2 == (f * magic) >> 20 for f < 2048
         const int threads = b->perceive_threads;
         blocks = (int)cdiv(p.EN, threads);
-#define ANTS_PERCEIVE(L, SF)                                                                               \
-    ants::k_perceive<L, SF><<<blocks, threads, b->perceive_smem, b->stream>>>(                             \
-        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic)
-        if (p.S == 7) {
-            if (layout == 1) ANTS_PERCEIVE(1, 7);
-            else if (layout == 2) ANTS_PERCEIVE(2, 7);
-            else ANTS_PERCEIVE(0, 7);
-        } else {
-            if (layout == 1) ANTS_PERCEIVE(1, 0);
-            else if (layout == 2) ANTS_PERCEIVE(2, 0);
-            else ANTS_PERCEIVE(0, 0);
-        }
+#define ANTS_PERCEIVE(L)                                                                                   \
+    ants::k_perceive<L><<<blocks, threads, b->perceive_smem, b->stream>>>(                                 \
+        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, \
+        b->perceive_slow_wrap)
+        if (layout == 1) ANTS_PERCEIVE(1);
+        else if (layout == 2) ANTS_PERCEIVE(2);
+        else ANTS_PERCEIVE(0);
 #undef ANTS_PERCEIVE
     }
     b->rw_alias = 0;
@@ -403,8 +398,10 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     memset(&p, 0, sizeof p);
     p.E = cfg->n_envs; p.N = cfg->n_ants; p.W = cfg->w; p.H = cfg->h; p.P = cfg->n_phero; p.R = cfg->n_rocks;
     p.Hp = (int)(cdiv(cfg->h, 16) * 16);
+    p.Wp = (int)(cdiv(cfg->w, 16) * 16);
+    p.nby = p.Hp / 8;
     p.EN = (int64_t)p.E * p.N;
-    p.plane = (int64_t)p.W * p.Hp;
+    p.plane = (int64_t)p.Wp * p.Hp;
     p.radius = cfg->radius; p.S = 2 * cfg->radius + 1; p.S2 = p.S * p.S; p.C = cfg->n_channels;
     p.has_mask = cfg->has_mask;
     p.rule_n = 0;
@@ -495,12 +492,18 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         b->perceive_group = g;
         int threads = ants::kPerceiveThreads;
         auto smem_for = [&](int t) {
-            return (int)((t / 32) * g * sc_bytes + (t * p.S2 + 1) * 4 + t * sizeof(ants::AntPrep) + p.S * 8 + t * 4 +
-                         p.S2 + 64);
+            return (int)((((t / 32) * g * p.S2 * p.C + 3) & ~3) * 4 + t * sizeof(ants::AntPrep) +
+                         p.S2 * sizeof(ants::SampleTab) + t * 4 + p.S2 + 64);
         };
         while (threads > 32 && smem_for(threads) > 100 * 1024) threads >>= 1;
         b->perceive_threads = threads;
         b->perceive_smem = smem_for(threads);
+        // sample offsets reach at most radius*DELTA*sqrt(2) + |fwd_delta| + 1 cells from the ant: one conditional
+        // add/subtract wraps them unless the map is smaller than that
+        double reach = p.radius * cfg->delta * 1.5 + fabs(cfg->fwd_delta) + 2.0;
+        b->perceive_slow_wrap = (p.W <= reach || p.H <= reach) ? 1 : 0;
+        // fewer resident blocks leave more of the 228 KB SM array to the L1 cache, which serves the record re-reads
+        if (const char *x = getenv("ANTS_PERCEIVE_PAD_SMEM")) b->perceive_smem += atoi(x);
     }
     {   // straight-line perception code for the generator's default channel list (with / without rocks)
         const int std6[6] = {ANTS_CH_ANTS, ANTS_CH_PHERO, ANTS_CH_PHERO, ANTS_CH_ANTHILL, ANTS_CH_WALLS, ANTS_CH_FOOD};
@@ -512,10 +515,9 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     }
     if (b->perceive_smem > 48 * 1024) {
         cudaError_t e = cudaSuccess;
-        const void *fns[6] = {(const void *)ants::k_perceive<0, 0>, (const void *)ants::k_perceive<1, 0>,
-                              (const void *)ants::k_perceive<2, 0>, (const void *)ants::k_perceive<0, 7>,
-                              (const void *)ants::k_perceive<1, 7>, (const void *)ants::k_perceive<2, 7>};
-        for (int k = 0; k < 6 && e == cudaSuccess; ++k)
+        const void *fns[3] = {(const void *)ants::k_perceive<0>, (const void *)ants::k_perceive<1>,
+                              (const void *)ants::k_perceive<2>};
+        for (int k = 0; k < 3 && e == cudaSuccess; ++k)
             e = cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
         if (e != cudaSuccess) {
             ants_destroy(b);

@@ -27,8 +27,9 @@ constexpr int kGridShift = 4;             // rock grid cell = 16 x 16 map cells
 
 struct Params {
     int32_t E, N, W, H, Hp, P, R;
+    int32_t Wp, nby;                       // padded width (multiple of 8), 8x8 blocks per map row of blocks (Hp / 8)
     int64_t EN;                            // E * N
-    int64_t plane;                         // W * Hp cells per env
+    int64_t plane;                         // Wp * Hp cells per env
     int32_t radius, S, S2, C;
     int32_t has_mask;
     int32_t ch_kind[kMaxCh];
@@ -96,6 +97,11 @@ __device__ __forceinline__ bool in_hill(const int32_t *hl, int cx, int cy) {   /
 __device__ __forceinline__ int wrap_coord(int v, int n) {
     if (v < 0) v += n; else if (v >= n) v -= n;
     return ((unsigned)v < (unsigned)n) ? v : imod(v, n);
+}
+// Cells are stored in 8 x 8 blocks (64 records = 2 KB contiguous, for DRAM row locality of the 7x7 perception
+// windows): index of cell (x, y) inside its environment.
+__device__ __forceinline__ int cidx(const Params &p, int x, int y) {
+    return ((((x >> 3) * p.nby) + (y >> 3)) << 6) | ((x & 7) << 3) | (y & 7);
 }
 // cell record accessors
 __device__ __forceinline__ uint8_t *rec_at(const Params &p, int e, int cell) {
@@ -178,7 +184,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     double hold = p.holding[i];
     int m_old = p.mandibles[i] != 0;
     int pcx = cell_of(p.prev_x[i], p.W), pcy = cell_of(p.prev_y[i], p.H);      // RL_api.py:178
-    int pcell = pcx * p.Hp + pcy;
+    int pcell = cidx(p, pcx, pcy);
     double f = *rec_food(p, rec_at(p, e, pcell));
     const int32_t *hl = p.hill + 4 * e;
     bool hill = in_hill(hl, cell_of(x, p.W), cell_of(y, p.H));                  // RL_api.py:184
@@ -215,7 +221,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     x = pymod(x + c * fwd, (double)p.W);                                        // ants.py:69-80
     y = pymod(y + s * fwd, (double)p.H);
     p.x[i] = x; p.y[i] = y; p.theta[i] = th;
-    uint8_t *orec = rec_at(p, e, cell_of(x, p.W) * p.Hp + cell_of(y, p.H));
+    uint8_t *orec = rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H)));
     reinterpret_cast<uint16_t *>(rec_meta(p, orec))[1] = (uint16_t)occ_gen;
 }
 
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(256) k_occ_stamp(Params p, uint32_t occ_gen) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
-    uint8_t *orec = rec_at(p, e, cell_of(p.x[i], p.W) * p.Hp + cell_of(p.y[i], p.H));
+    uint8_t *orec = rec_at(p, e, cidx(p, cell_of(p.x[i], p.W), cell_of(p.y[i], p.H)));
     reinterpret_cast<uint16_t *>(rec_meta(p, orec))[1] = (uint16_t)occ_gen;
 }
 
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
         int e = (int)(i / p.N);
         int a = (int)(i - (int64_t)e * p.N);
         int pcx = cell_of(p.prev_x[i], p.W), pcy = cell_of(p.prev_y[i], p.H);
-        int pcell = pcx * p.Hp + pcy;
+        int pcell = cidx(p, pcx, pcy);
         if (p.owner[(int64_t)e * p.plane + pcell] != (owner_stamp | (uint32_t)a)) continue;
         double *fp = rec_food(p, rec_at(p, e, pcell));
         double nv = *fp + p.food_delta[i];
@@ -258,54 +264,58 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
 // LAYOUT 0: any perceived_objects list (switch per channel)
 // LAYOUT 1: the generator's default list [ants, phero0, phero1, anthill, walls, food] (environment_generator.py:64-99)
 // LAYOUT 2: the same plus rocks as 7th channel
-// SFIX: perception window side known at compile time (7 = the default 7x7 window), 0 = run-time side.
 //
 // Block = blockDim.x threads = as many consecutive ants; warp w owns ants [32w, 32w+32) from start to end (no
 // block barrier after the table load).
-//   phase A (thread per ant): f64 trigonometry of the rotated sampling frame; ALL sample cells of the ant,
-//            round(rot(theta + pi/2) * offset + xy_f) mod (W,H), with the products cos*offset / sin*offset
-//            computed once per row / column, packed (x << 16 | y) into shared memory; reward terms that do not
-//            need the exploration count; agent_state / state outputs; candidate rocks from the rock grid.
+//   phase A (thread per ant): f64 trigonometry of the rotated sampling frame (cos/sin(theta + pi/2), shifted
+//            position) into a 96-byte shared-memory record per ant; reward terms that do not need the exploration
+//            count; agent_state / state outputs; candidate rocks from the rock grid.
 //   phase B (warp, flat sample index): the warp walks its ants in chunks of `group` ants; the chunk's
-//            group*S2 samples are spread over the 32 lanes and processed in batches of U lane-slots whose record
-//            loads (one 32-byte sector per sample) are all issued before any is consumed; analytic anthill disc,
-//            exact rock test on the candidates; per-lane packed exploration counters; the chunk's
+//            group*S2 samples are spread over the 32 lanes and processed in batches of U lane-slots: sample cell =
+//            round_half_even(rot * offset + xy_f) mod (W,H) in f64, then the record loads (one 32-byte sector per
+//            sample) of the whole batch are issued before any is consumed; analytic anthill disc, exact rock test
+//            on the candidates; exploration counts by warp-uniform ballot splitting; the chunk's
 //            (group x S2 x C) f32 tile is staged in shared memory and leaves with ONE TMA bulk store.
 //   phase C (thread per ant): reward epilogue and Ants.give_reward.
 constexpr int kPerceiveThreads = 128;
 constexpr int kMaxGroup = 4;                // ants per staged chunk (4 ants: bytes are always a multiple of 16)
 
-struct AntPrep {
-    double r_other, mult;        // reward terms without the exploration count; exploration multiplier
-    unsigned long long rocks;    // candidate rocks (from the rock grid)
+struct AntPrep {                            // 96 bytes per ant, shared memory
+    double ct, st;               // cos / sin(theta + pi/2)
+    double xf, yf;               // position shifted forward by perception_fwd_delta
     const uint8_t *cells;        // records of the ant's environment
-    int e, pad;
+    unsigned long long rocks;    // candidate rocks (from the rock grid)
+    int hx, hy, hr2, e;          // anthill centre, radius^2; environment index
+    double r_other, mult;        // reward terms without the exploration count; exploration multiplier
+};
+struct SampleTab {                          // per sample of the window: offsets (RL_api.py:92-93)
+    double px, py;
 };
 
-template <int LAYOUT, int SFIX>
-__global__ void __launch_bounds__(kPerceiveThreads)
+template <int LAYOUT>
+__global__ void __launch_bounds__(kPerceiveThreads, 6)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
-           int group, uint32_t s2_magic) {
+           int group, uint32_t s2_magic, int slow_wrap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int S = SFIX ? SFIX : p.S;
-    const int S2 = S * S, C = p.C;
+    const int S = p.S, S2 = p.S2, C = p.C;
     const int SC = S2 * C;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     float *s_obs = reinterpret_cast<float *>(smem_raw);                        // [warps][group][S2*C], 16 B aligned
-    uint32_t *s_cell = reinterpret_cast<uint32_t *>(s_obs + nwarps * group * SC);   // [threads][S2]
-    AntPrep *prep = reinterpret_cast<AntPrep *>(s_cell + nthreads * S2 + ((nthreads * S2) & 1));
-    double *s_off = reinterpret_cast<double *>(prep + nthreads);               // [S] = (k - r) * DELTA
-    int *s_cnt = reinterpret_cast<int *>(s_off + S);
+    AntPrep *prep = reinterpret_cast<AntPrep *>(s_obs + ((nwarps * group * SC + 3) & ~3));
+    SampleTab *s_tab = reinterpret_cast<SampleTab *>(prep + nthreads);         // [S2]
+    int *s_cnt = reinterpret_cast<int *>(s_tab + S2);
     uint8_t *s_mask = reinterpret_cast<uint8_t *>(s_cnt + nthreads);
 
     const int tid = threadIdx.x;
-    for (int k = tid; k < S2; k += nthreads) s_mask[k] = p.has_mask ? p.mask[k] : 1;
-    for (int k = tid; k < S; k += nthreads) s_off[k] = p.samp_off[k];
-    __syncthreads();
+    for (int k = tid; k < S2; k += nthreads) {
+        s_mask[k] = p.has_mask ? p.mask[k] : 1;
+        s_tab[k].px = p.samp_off[k % S];       // X = off[j], Y = off[i] for sample k = i * S + j
+        s_tab[k].py = p.samp_off[k / S];
+    }
     const int64_t base = (int64_t)blockIdx.x * nthreads;
 
-    // ---- phase A
+    // ---- phase A (thread per ant)
     {
         const int64_t i = base + tid;
         s_cnt[tid] = 0;
@@ -315,41 +325,14 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             double s0, c0, st, ct;
             sincos(th, &s0, &c0);
             sincos(th + 3.141592653589793 * 0.5, &st, &ct);                    // RL_api.py:101,107-108
-            double xf = x, yf = y;
-            if (p.fwd_delta != 0.0) { xf = x + c0 * p.fwd_delta; yf = y + s0 * p.fwd_delta; }   // :103-104
-            // sample cells, RL_api.py:110-119: rel_x = cos*X - sin*Y, rel_y = sin*X + cos*Y with X = off[j],
-            // Y = off[i]; abs = round_half_even(rel + xy_f) mod (W, H)
-            uint32_t *mycell = s_cell + tid * S2;
-            if (SFIX) {
-                double cX[SFIX ? SFIX : 1], sX[SFIX ? SFIX : 1];
-#pragma unroll
-                for (int j = 0; j < SFIX; ++j) { const double o = s_off[j]; cX[j] = ct * o; sX[j] = st * o; }
-#pragma unroll 1
-                for (int ii = 0; ii < SFIX; ++ii) {
-                    const double o = s_off[ii];
-                    const double sY = st * o, cY = ct * o;
-#pragma unroll
-                    for (int j = 0; j < SFIX; ++j) {
-                        const int ix = wrap_coord(__double2int_rn((cX[j] - sY) + xf), p.W);
-                        const int iy = wrap_coord(__double2int_rn((sX[j] + cY) + yf), p.H);
-                        mycell[ii * SFIX + j] = ((uint32_t)ix << 16) | (uint32_t)iy;
-                    }
-                }
-            } else {
-                for (int ii = 0; ii < S; ++ii) {
-                    const double oy = s_off[ii];
-                    const double sY = st * oy, cY = ct * oy;
-                    for (int j = 0; j < S; ++j) {
-                        const double ox = s_off[j];
-                        const int ix = wrap_coord(__double2int_rn((ct * ox - sY) + xf), p.W);
-                        const int iy = wrap_coord(__double2int_rn((st * ox + cY) + yf), p.H);
-                        mycell[ii * S + j] = ((uint32_t)ix << 16) | (uint32_t)iy;
-                    }
-                }
-            }
             AntPrep q;
-            q.e = e; q.pad = 0;
+            q.ct = ct; q.st = st;
+            q.xf = x; q.yf = y;
+            if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // :103-104
+            q.e = e;
             q.cells = p.cells + (((int64_t)e * p.plane) << p.rec_shift);
+            const int32_t *hl = p.hill + 4 * e;
+            q.hx = hl[0]; q.hy = hl[1]; q.hr2 = hl[3];
             // reward.observation, reward_custom.py
             const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
             const double d = hold - hprev;
@@ -357,8 +340,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             if (p.reward_kind == 0) {                                          // All_Rewards, :79-106
                 const double r_food = d < 0.0 ? 0.0 : d;
                 const double r_hill = d < 0.0 ? 1.0 : 0.0;
-                const int32_t *hl = p.hill + 4 * e;
-                const double ddx = x - (double)hl[0], ddy = y - (double)hl[1];
+                const double ddx = x - (double)q.hx, ddy = y - (double)q.hy;
                 const double nd = sqrt(ddx * ddx + ddy * ddy);
                 const double heading = (p.rw_prev_dist[i] > nd && hold > 0.0) ? 0.1 : 0.0;
                 p.rw_prev_dist[i] = nd;
@@ -369,7 +351,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 q.r_other = d < 0.0 ? 10.0 : d;
                 p.rw_holding_prev[i] = hold;
             }
-            q.rocks = (p.R > 0 && (LAYOUT == 2 || LAYOUT == 0)) ? rock_candidates(p, e, xf, yf) : 0ull;
+            q.rocks = (p.R > 0 && (LAYOUT == 2 || LAYOUT == 0)) ? rock_candidates(p, e, q.xf, q.yf) : 0ull;
             prep[tid] = q;
             agent_state[2 * i] = (float)hold;                                  // RL_api.py:160-162
             agent_state[2 * i + 1] = (float)p.seed[i];
@@ -385,12 +367,12 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
     const bool has_mask = p.has_mask != 0;
     const bool explore_on = p.explore_on != 0;
     const int food_off = p.food_off, meta_off = p.meta_off, wall_off = p.wall_off, rec_shift = p.rec_shift;
-    __syncwarp();
+    const int W = p.W, H = p.H, nby = p.nby;
+    __syncthreads();
 
-    // ---- phase B
+    // ---- phase B (warp, flat sample index; the warp owns ants [32 warp, 32 warp + 32) of the block)
     const int warp = tid >> 5, lane = tid & 31;
     float *wobs = s_obs + warp * group * SC;
-    const uint32_t *wcell = s_cell + warp * 32 * S2;
     const AntPrep *wprep = prep + warp * 32;
     constexpr int U = 4;                       // lane-slots per batch: all record loads of a batch are in flight together
     for (int g = 0; g < 32; g += group) {
@@ -403,9 +385,9 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
         if (lane == 0) bulk_store_wait_read();
         __syncwarp();
         const int iters = (nsamp + 31) >> 5;
-        uint32_t cnt_packed = 0;               // per-lane exploration counts, one byte per ant of the chunk
+        uint32_t cnt_packed = 0;               // exploration counts of the chunk's ants, one byte each (warp-uniform)
         for (int it0 = 0; it0 < iters; it0 += U) {
-            uint32_t cw[U];
+            uint32_t xy[U];
             const uint8_t *rp[U];
             uint4 lo[U], hi[U];                // record halves (P == 2 fast path) or generic fields packed likewise
 #pragma unroll
@@ -413,9 +395,20 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 const int f_raw = (it0 + u) * 32 + lane;
                 const int f = f_raw < nsamp ? f_raw : 0;                       // idle lanes / slots shadow sample 0
                 const int aj = (int)(((uint32_t)f * s2_magic) >> 20);         // f / S2
-                cw[u] = wcell[g * S2 + f];
-                const int cell = (int)(cw[u] >> 16) * p.Hp + (int)(cw[u] & 0xFFFFu);
-                rp[u] = wprep[g + aj].cells + ((int64_t)cell << rec_shift);
+                const int s = f - aj * S2;
+                const AntPrep &q = wprep[g + aj];
+                const SampleTab t = s_tab[s];
+                // sample cell, RL_api.py:110-119: round_half_even(rot(theta + pi/2) * offset + xy_f) mod (W, H)
+                const double rx = q.ct * t.px - q.st * t.py;
+                const double ry = q.st * t.px + q.ct * t.py;
+                int ix = __double2int_rn(rx + q.xf), iy = __double2int_rn(ry + q.yf);
+                if (slow_wrap) { ix = imod(ix, W); iy = imod(iy, H); }
+                else {
+                    ix = ix < 0 ? ix + W : (ix >= W ? ix - W : ix);
+                    iy = iy < 0 ? iy + H : (iy >= H ? iy - H : iy);
+                }
+                xy[u] = ((uint32_t)ix << 16) | (uint32_t)iy;
+                rp[u] = q.cells + ((int64_t)(((((ix >> 3) * nby) + (iy >> 3)) << 6) | ((ix & 7) << 3) | (iy & 7)) << rec_shift);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -432,26 +425,41 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int f_raw = (it0 + u) * 32 + lane;
-                const bool valid = f_raw < nsamp;
-                if (!valid) continue;
-                const int f = f_raw;
-                const int aj = (int)(((uint32_t)f * s2_magic) >> 20);
-                const int s = f - aj * S2;
-                const int ix = (int)(cw[u] >> 16), iy = (int)(cw[u] & 0xFFFFu);
+                const int f0 = (it0 + u) * 32;                                 // warp-uniform
+                if (f0 >= nsamp) break;
+                const int f = f0 + lane;
+                const bool valid = f < nsamp;
                 const uint32_t mt = hi[u].z;
-                const double fd = __hiloint2double((int)hi[u].y, (int)hi[u].x);
-                const bool wl = (hi[u].w & 0xFFu) != 0;
                 if (explore_on) {
                     const uint32_t eg = mt & 0xFFFFu;
-                    if ((eg == 0u) || (eg == obs_gen)) cnt_packed += 1u << (8 * aj);       // gather-before-scatter, Q7
-                    if (eg == 0u)
+                    const bool unexplored = valid && ((eg == 0u) || (eg == obs_gen));     // gather-before-scatter, Q7
+                    if (valid && eg == 0u)
                         *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(rp[u]) + meta_off) = (uint16_t)obs_gen;
+                    // the slot's lanes belong to consecutive ants: split the ballot at the ant boundaries (uniform)
+                    uint32_t votes = __ballot_sync(0xffffffffu, unexplored);
+                    int a_lo = (int)(((uint32_t)f0 * s2_magic) >> 20);
+                    int covered = 0;
+                    while (covered < 32) {
+                        int span = (a_lo + 1) * S2 - (f0 + covered);           // lanes left in ant a_lo
+                        span = span < 32 - covered ? span : 32 - covered;
+                        uint32_t m = span >= 32 ? 0xffffffffu : (((1u << span) - 1u) << covered);
+                        cnt_packed += (uint32_t)__popc(votes & m) << (8 * a_lo);
+                        covered += span;
+                        ++a_lo;
+                        if (a_lo >= n_in) break;
+                    }
                 }
+                if (!valid) continue;
+                const int aj = (int)(((uint32_t)f * s2_magic) >> 20);
+                const int s = f - aj * S2;
+                const int ix = (int)(xy[u] >> 16), iy = (int)(xy[u] & 0xFFFFu);
+                const double fd = __hiloint2double((int)hi[u].y, (int)hi[u].x);
+                const bool wl = (hi[u].w & 0xFFu) != 0;
                 const bool vis = s_mask[s] != 0;
                 float *o = wobs + f * C;
                 const AntPrep &q = wprep[g + aj];
-                const int32_t *hl = p.hill + 4 * q.e;
+                const int hdx = q.hx - ix, hdy = q.hy - iy;
+                const bool hill = hdx * hdx + hdy * hdy <= q.hr2;              // anthill.py:31-33 on integers
                 // mask * (perception + 1) - 1 (RL_api.py:147-148): the +1-1 round trip changes a value by at most
                 // 2^-53 absolute, far below the resolution of the f32 observation, so visible samples pass through.
                 if (LAYOUT != 0) {
@@ -460,7 +468,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                     float v0 = ((mt >> 16) == occ_gen) ? 1.f : 0.f;                                   // :136-142
                     float v1 = (float)(ph0 * inv_max);                                                // :124-125
                     float v2 = (float)(ph1 * inv_max);
-                    float v3 = in_hill(hl, ix, iy) ? 1.f : 0.f;                                       // :130-131
+                    float v3 = hill ? 1.f : 0.f;                                                      // :130-131
                     float v4 = wl ? 1.f : 0.f;                                                        // :128-129
                     float v5 = (float)fd;                                                             // :126-127
                     float v6 = 0.f;
@@ -486,7 +494,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                         switch (p.ch_kind[c]) {
                             case 0: v = ((mt >> 16) == occ_gen) ? 1.0 : 0.0; break;
                             case 1: v = *reinterpret_cast<const double *>(rp[u] + 8 * p.ch_arg[c]) * inv_max; break;
-                            case 2: v = in_hill(hl, ix, iy) ? 1.0 : 0.0; break;
+                            case 2: v = hill ? 1.0 : 0.0; break;
                             case 3: v = wl ? 1.0 : 0.0; break;
                             case 4: v = fd; break;
                             default: {
@@ -507,18 +515,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 }
             }
         }
-        // exploration counts of the chunk: byte-wise warp reduction of the packed per-lane counters
-        if (explore_on) {
-#pragma unroll
-            for (int sh = 16; sh > 0; sh >>= 1) {
-                // split into even / odd bytes so that sums up to 255 per ant cannot carry into a neighbour
-                uint32_t ev = cnt_packed & 0x00FF00FFu, od = (cnt_packed >> 8) & 0x00FF00FFu;
-                ev += __shfl_xor_sync(0xffffffffu, ev, sh);
-                od += __shfl_xor_sync(0xffffffffu, od, sh);
-                cnt_packed = (ev & 0x00FF00FFu) | ((od & 0x00FF00FFu) << 8);
-            }
-            if (lane < n_in) s_cnt[warp * 32 + g + lane] = (int)((cnt_packed >> (8 * lane)) & 0xFFu);
-        }
+        if (explore_on && lane < n_in) s_cnt[warp * 32 + g + lane] = (int)((cnt_packed >> (8 * lane)) & 0xFFu);
         // flush the staged (n_in x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
         float *dst = obs + i0 * SC;
         const uint32_t bytes = (uint32_t)(n_in * SC * 4);
@@ -572,7 +569,7 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
     int e = (int)(i / p.N);
     int a = (int)(i - (int64_t)e * p.N);
     double x = p.x[i], y = p.y[i], th = p.theta[i];
-    if (*rec_wall(p, rec_at(p, e, cell_of(x, p.W) * p.Hp + cell_of(y, p.H)))) {
+    if (*rec_wall(p, rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H))))) {
         x = p.prev_x[i]; y = p.prev_y[i];
         double u = noise ? noise[i] : philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)a);
         th += u - 0.5;                                                         // not re-wrapped (Q3)
@@ -580,7 +577,7 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
     }
     if (finish) {
         p.prev_x[i] = x; p.prev_y[i] = y; p.prev_theta[i] = th;
-        atomicMax(p.owner + (int64_t)e * p.plane + cell_of(x, p.W) * p.Hp + cell_of(y, p.H), owner_stamp | (uint32_t)a);
+        atomicMax(p.owner + (int64_t)e * p.plane + cidx(p, cell_of(x, p.W), cell_of(y, p.H)), owner_stamp | (uint32_t)a);
         p.reward_state[i] = (uint8_t)((double)p.reward_state[i] * 0.9);        // ants.py:130
     }
 }
@@ -686,7 +683,7 @@ __global__ void __launch_bounds__(256) k_rocks_push_ants(Params p, uint32_t owne
     y = pymod(y + sy, (double)p.H);
     p.x[i] = x; p.y[i] = y;
     p.prev_x[i] = x; p.prev_y[i] = y; p.prev_theta[i] = p.theta[i];
-    atomicMax(p.owner + (int64_t)e * p.plane + cell_of(x, p.W) * p.Hp + cell_of(y, p.H), owner_stamp | (uint32_t)a);
+    atomicMax(p.owner + (int64_t)e * p.plane + cidx(p, cell_of(x, p.W), cell_of(y, p.H)), owner_stamp | (uint32_t)a);
     p.reward_state[i] = (uint8_t)((double)p.reward_state[i] * 0.9);
 }
 
@@ -761,23 +758,25 @@ __global__ void __launch_bounds__(256) k_evaporate_tiles(Params p, const uint32_
         const int e = (int)(tt / (uint32_t)tiles_per_env);
         const int tin = (int)(tt - (uint32_t)e * (uint32_t)tiles_per_env);
         const int tx = tin / p.tiles_y, ty = tin - tx * p.tiles_y;
-        // 16 rows x 16 records: per pass the warp covers 2 rows (lane -> row = pass*2 + lane/16, col = lane%16),
-        // i.e. two contiguous 512-byte runs, every sector fully used
+        // a 16 x 16 tile is 2 x 2 blocks of 8 x 8 cells, each block 64 contiguous records: per pass the warp covers
+        // half a block (32 records = 1 KB contiguous), every sector fully used
         bool any = false;
+        const int bx0 = tx * 2, by0 = ty * 2;
         if (p.P == 2) {
-            double2 v[kTile / 2];
-            uint8_t wl[kTile / 2];
-            uint8_t *rp[kTile / 2];
+            double2 v[8];
+            uint8_t wl[8];
+            uint8_t *rp[8];
 #pragma unroll
-            for (int pass = 0; pass < kTile / 2; ++pass) {
-                int row = tx * kTile + pass * 2 + (lane >> 4);
-                row = row < p.W ? row : p.W - 1;                               // clamp: rows past the map repeat the last
-                rp[pass] = rec_at(p, e, row * p.Hp + ty * kTile + (lane & 15));
+            for (int pass = 0; pass < 8; ++pass) {
+                int bx = bx0 + (pass >> 2);
+                bx = bx < (p.Wp >> 3) ? bx : (p.Wp >> 3) - 1;                  // tiles past the map repeat the last block row
+                const int by = by0 + ((pass >> 1) & 1);
+                rp[pass] = rec_at(p, e, ((bx * p.nby + by) << 6) + (pass & 1) * 32 + lane);
                 v[pass] = *reinterpret_cast<const double2 *>(rp[pass]);
                 wl[pass] = rp[pass][p.wall_off];
             }
 #pragma unroll
-            for (int pass = 0; pass < kTile / 2; ++pass) {
+            for (int pass = 0; pass < 8; ++pass) {
                 if (v[pass].x == 0.0 && v[pass].y == 0.0) continue;
                 double a = wl[pass] ? 0.0 : v[pass].x * c, b = wl[pass] ? 0.0 : v[pass].y * c;
                 a = a < 0.01 ? 0.0 : a;
@@ -788,9 +787,10 @@ __global__ void __launch_bounds__(256) k_evaporate_tiles(Params p, const uint32_
             }
         } else {
 #pragma unroll 1
-            for (int pass = 0; pass < kTile / 2; ++pass) {
-                int row = tx * kTile + pass * 2 + (lane >> 4);
-                if (row < p.W) any |= evaporate_record(p, rec_at(p, e, row * p.Hp + ty * kTile + (lane & 15)), c, mx, clamp);
+            for (int pass = 0; pass < 8; ++pass) {
+                const int bx = bx0 + (pass >> 2), by = by0 + ((pass >> 1) & 1);
+                if (bx < (p.Wp >> 3))
+                    any |= evaporate_record(p, rec_at(p, e, ((bx * p.nby + by) << 6) + (pass & 1) * 32 + lane), c, mx, clamp);
             }
         }
         if (!__any_sync(0xffffffffu, any) && lane == 0) p.tile_active[tt] = 0;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(256) k_diffuse_stencil(Params p, int nbx, int 
         int gx = x0 + lx - 1, gy = y0 + ly - 1;
         double v = 0.0;
         if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
-            uint8_t *r = rec_at(p, e, gx * p.Hp + gy);
+            uint8_t *r = rec_at(p, e, cidx(p, gx, gy));
             v = *rec_wall(p, r) ? 0.0 : *rec_phero(r, k);
         }
         tile[lx][ly] = v;
@@ -837,11 +837,14 @@ __global__ void __launch_bounds__(256) k_diffuse_stencil(Params p, int nbx, int 
     }
 }
 __global__ void __launch_bounds__(256) k_diffuse_commit(Params p) {
-    const int64_t n = (int64_t)p.E * p.plane;
+    const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        int64_t e = j / p.plane, cell = j - e * p.plane;
-        uint8_t *r = p.cells + (j << p.rec_shift);
-        for (int k = 0; k < p.P; ++k) *rec_phero(r, k) = p.phero_alt[(e * p.P + k) * p.plane + cell];
+        int64_t ex = j / p.H;
+        int y = (int)(j - ex * p.H);
+        int64_t e = ex / p.W;
+        int x = (int)(ex - e * p.W);
+        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
+        for (int k = 0; k < p.P; ++k) *rec_phero(r, k) = p.phero_alt[(e * p.P + k) * p.plane + (int64_t)x * p.Hp + y];
     }
 }
 
@@ -853,7 +856,7 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     int e = (int)(i / p.N);
     int a = (int)(i - (int64_t)e * p.N);
     int cx = cell_of(p.x[i], p.W), cy = cell_of(p.y[i], p.H);
-    int cell = cx * p.Hp + cy;
+    int cell = cidx(p, cx, cy);
     if (p.owner[(int64_t)e * p.plane + cell] != (owner_stamp | (uint32_t)a)) return;
     uint8_t *r = rec_at(p, e, cell);
     bool wrote = false;
@@ -896,7 +899,7 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
         for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
             int cx = x0 + t / bh, cy = y0 + t % bh;
             if (!in_hill(hl, cx, cy)) continue;
-            double *fp = rec_food(p, rec_at(p, e, cx * p.Hp + cy));
+            double *fp = rec_food(p, rec_at(p, e, cidx(p, cx, cy)));
             double v = *fp;
             if (v != 0.0) { acc += v; *fp = v - v; }
         }
@@ -920,7 +923,7 @@ __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int plane
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
-        *reinterpret_cast<double *>(rec_at(p, (int)e, x * p.Hp + y) + byte_off) = v;
+        *reinterpret_cast<double *>(rec_at(p, (int)e, cidx(p, x, y)) + byte_off) = v;
     }
 }
 __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off) {
@@ -931,7 +934,7 @@ __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_pe
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         dense[((e * planes_per_env + k) * p.W + x) * p.H + y] =
-            *reinterpret_cast<const double *>(rec_at(p, (int)e, x * p.Hp + y) + byte_off);
+            *reinterpret_cast<const double *>(rec_at(p, (int)e, cidx(p, x, y)) + byte_off);
     }
 }
 // what: 0 = walls (stored as 0/1), 1 = explored (meta low half: 0xFFFF = explored long ago; occupancy cleared)
@@ -942,7 +945,7 @@ __global__ void k_pack_u8(Params p, const uint8_t *__restrict__ dense, int what)
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
-        uint8_t *r = rec_at(p, (int)e, x * p.Hp + y);
+        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
         if (what == 0) *rec_wall(p, r) = dense[j] ? 1 : 0;
         else *rec_meta(p, r) = dense[j] ? 0xFFFFu : 0u;
     }
@@ -954,7 +957,7 @@ __global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what) {
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
-        uint8_t *r = rec_at(p, (int)e, x * p.Hp + y);
+        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
         dense[j] = what == 0 ? *rec_wall(p, r) : ((*rec_meta(p, r) & 0xFFFFu) ? 1 : 0);
     }
 }
@@ -993,7 +996,7 @@ __global__ void k_tiles_from_phero(Params p) {
             int row = tx * kTile + dx;
             if (row >= p.W) break;
             for (int dy = 0; dy < kTile && !any; ++dy) {
-                uint8_t *r = rec_at(p, e, row * p.Hp + ty * kTile + dy);
+                uint8_t *r = rec_at(p, e, cidx(p, row, ty * kTile + dy));
                 for (int k = 0; k < p.P; ++k) any |= *rec_phero(r, k) != 0.0;
             }
         }

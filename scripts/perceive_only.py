@@ -6,7 +6,8 @@ import numpy as np, torch
 import bench
 from antsrl_b200 import BatchedAnts
 from antsrl_b200.generator import stack_states
-wl = bench.WORKLOADS[os.environ.get("WL", "cfg4")]
+wl = dict(bench.WORKLOADS[os.environ.get("WL", "cfg4")])
+if os.environ.get("N_ANTS"): wl["n_ants"] = int(os.environ["N_ANTS"])
 E = int(os.environ.get("ENVS", "256"))
 gen = bench.make_generator(wl, 1000)
 states = bench.generate_states_parallel(wl, 1000, 0, E)
