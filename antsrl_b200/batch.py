@@ -21,7 +21,7 @@ DEFAULT_MASK = np.array([[0, 0, 1, 1, 1, 0, 0],
                          [0, 0, 1, 1, 1, 0, 0]], dtype=bool)    # environment_generator.py:35-41
 
 _REWARD_KINDS = {"all": _cabi.REWARD_ALL, "explore": _cabi.REWARD_EXPLORE, "food": _cabi.REWARD_FOOD}
-_EVAP_MODES = {"dense": _cabi.EVAP_DENSE, "tiles": _cabi.EVAP_ACTIVE_TILES}
+_EVAP_MODES = {"dense": _cabi.EVAP_DENSE, "tiles": _cabi.EVAP_ACTIVE_TILES, "lazy": _cabi.EVAP_LAZY}
 KERNEL_FAMILIES = ("move", "food_commit", "perceive", "collide", "rocks", "evaporate", "deposit", "absorb", "misc")
 
 

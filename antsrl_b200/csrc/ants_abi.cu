@@ -58,6 +58,7 @@ struct AntsBatch {
     uint32_t obs_gen = 0, occ_gen = 0, owner_phase = 0;
     int64_t timestep = 1;
     int rw_alias = 1, act_bool = 1, prev_synced = 1, needs_sweep = 1;
+    uint32_t lazy_now = 0;          // updates since the last timestamp fold (lazy evaporation), < 4096
     AntsStats stats;
     // profiling
     int profiling = 0;
@@ -192,7 +193,7 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
 #define ANTS_PERCEIVE(L)                                                                                   \
     ants::k_perceive<L><<<blocks, threads, b->perceive_smem, b->stream>>>(                                 \
         p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, \
-        b->perceive_slow_wrap)
+        b->perceive_slow_wrap, b->lazy_now)
         if (layout == 1) ANTS_PERCEIVE(1);
         else if (layout == 2) ANTS_PERCEIVE(2);
         else ANTS_PERCEIVE(0);
@@ -272,7 +273,16 @@ int do_update(AntsBatch *b, const double *d_noise) {
     }
     // 1b + 4. wall zeroing of the field (walls.py:30) and Pheromone.update (order 0)
     if (p.P > 0) {
-        if (b->cfg.diffuse_factor != 0.0) {
+        if (p.lazy) {
+            // no pass over the field: values are evaluated at read time from their write timestamps
+            if (b->lazy_now >= 4094u) {     // fold before the 12-bit counter wraps
+                LaunchScope ls(b, F_EVAP);
+                ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now);
+                b->lazy_now = 0;
+            }
+            b->lazy_now += 1;
+            b->stats.active_tiles = 0;
+        } else if (b->cfg.diffuse_factor != 0.0) {
             int nbx = (int)cdiv(p.W, ants::kStX), nby = (int)cdiv(p.H, ants::kStY);
             {
                 LaunchScope ls(b, F_EVAP);
@@ -301,7 +311,7 @@ int do_update(AntsBatch *b, const double *d_noise) {
         // 6. Ants.update (order 999): deposit
         {
             LaunchScope ls(b, F_DEPOSIT);
-            ants::k_deposit_commit<<<blocks, 256, 0, b->stream>>>(p, phase << 16);
+            ants::k_deposit_commit<<<blocks, 256, 0, b->stream>>>(p, phase << 16, b->lazy_now);
         }
         TRY(check_launch("k_deposit_commit"));
     }
@@ -421,6 +431,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     // cell record: { f64 phero[P]; f64 food; u32 meta; u8 wall; pad } in 32 B (P <= 2) or 64 B
     p.food_off = 8 * p.P; p.meta_off = 8 * p.P + 8; p.wall_off = 8 * p.P + 12;
     p.rec_shift = (8 * p.P + 16 <= 32) ? 5 : 6;
+    p.ts_off = 8 * p.P + 16;
     p.grid_w = (int)cdiv(p.W, 1 << ants::kGridShift);
     p.grid_h = (int)cdiv(p.H, 1 << ants::kGridShift);
     p.delta = cfg->delta; p.fwd_delta = cfg->fwd_delta; p.reward_threshold = cfg->reward_threshold;
@@ -437,6 +448,8 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         p.filt_center = centre * keep;
     }
     p.phero_max_val = cfg->phero_max_val; p.max_hold = cfg->max_hold;
+    p.lazy = (cfg->evap_mode == ANTS_EVAP_LAZY && cfg->diffuse_factor == 0.0 && p.P > 0) ? 1 : 0;
+    p.log2_keep = p.filt_center > 0.0 ? log2(p.filt_center) : -1e300;
     p.rng_seed = cfg->rng_seed; p.env_id_base = cfg->env_id_base;
 
     int rc = ANTS_OK;
@@ -465,6 +478,8 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
     A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
     A(dev_alloc(b, &p.tile_counter, 1));
+    double *d_table = nullptr;
+    A(dev_alloc(b, &d_table, 4096));
     b->stats.total_tiles = (int64_t)p.E * p.tiles_x * p.tiles_y;
     // perception tables, RL_api.py:92-93: coords[i][j] = ((j - r) * DELTA, (i - r) * DELTA)
     double *d_off = nullptr;
@@ -483,6 +498,16 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         cudaMemcpy(d_off, off.data(), p.S * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(d_mask, mk.data(), p.S2, cudaMemcpyHostToDevice);
         p.samp_off = d_off; p.mask = d_mask;
+        // pheromone.py:44-45 applied k times to max_val, with the reference's rounding at every step
+        std::vector<double> tab(4096);
+        volatile double v = cfg->has_max_val ? cfg->phero_max_val : 0.0;
+        for (int k = 0; k < 4096; ++k) {
+            tab[k] = v;
+            volatile double nv = v * p.filt_center;
+            v = nv < 0.01 ? 0.0 : nv;
+        }
+        cudaMemcpy(d_table, tab.data(), 4096 * sizeof(double), cudaMemcpyHostToDevice);
+        p.decay_table = d_table;
     }
     {   // ants per staged chunk: as many as fit ~12 KB per warp, keeping the chunk a multiple of 16 B and the
         // flat sample index below 2048 (magic division); threads per block: as many warps as fit ~100 KB
@@ -604,7 +629,7 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     }
     if (s->phero && p.P > 0) {
         CK(cudaMemcpyAsync(d_tmp, s->phero, ncell * 8 * p.P, cudaMemcpyHostToDevice, st));
-        for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k);
+        for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now);
         TRY(check_launch("k_pack_f64"));
         if (p.tile_active) {
             ants::k_tiles_from_phero<<<148 * 4, 256, 0, st>>>(p);
@@ -613,7 +638,7 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     }
     if (s->food) {
         CK(cudaMemcpyAsync(d_tmp, s->food, ncell * 8, cudaMemcpyHostToDevice, st));
-        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off);
+        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off, -1, 0u);
         TRY(check_launch("k_pack_f64"));
         b->needs_sweep = 1;
     }
@@ -688,12 +713,12 @@ int ants_export_state(AntsBatch *b, AntsHostState *s) {
         if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "export scratch of %zu bytes: %s", need, cudaGetErrorString(me));
     }
     if (s->phero && p.P > 0) {
-        for (int k = 0; k < p.P; ++k) ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k);
+        for (int k = 0; k < p.P; ++k) ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now);
         TRY(check_launch("k_unpack_f64"));
         CK(cudaMemcpyAsync(s->phero, d_tmp, ncell * 8 * p.P, cudaMemcpyDeviceToHost, st));
     }
     if (s->food) {
-        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off);
+        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off, -1, 0u);
         TRY(check_launch("k_unpack_f64"));
         CK(cudaMemcpyAsync(s->food, d_tmp, ncell * 8, cudaMemcpyDeviceToHost, st));
     }

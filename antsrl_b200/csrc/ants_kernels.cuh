@@ -44,6 +44,10 @@ struct Params {
     double delta, fwd_delta, reward_threshold, max_speed, max_rot_speed, csr, bsr;
     double f_explore, f_food, f_anthill, f_explore_hold, f_heading;
     double filt_center, filt_ring, phero_max_val, max_hold;
+    double log2_keep;                      // log2(filt_center): lazy decay of values that are not on the table
+    int32_t lazy;                          // 1 = pheromone values carry write timestamps, no evaporation pass
+    int32_t ts_off;                        // P > 2: byte offset of the u16 timestamps (P <= 2: packed next to the wall byte)
+    const double *decay_table;             // [4096] max_val decayed k times exactly like the reference
     uint64_t rng_seed;
     int64_t env_id_base;
     // ants, [E*N]
@@ -111,6 +115,37 @@ __device__ __forceinline__ double *rec_phero(uint8_t *r, int k) { return reinter
 __device__ __forceinline__ double *rec_food(const Params &p, uint8_t *r) { return reinterpret_cast<double *>(r + p.food_off); }
 __device__ __forceinline__ uint32_t *rec_meta(const Params &p, uint8_t *r) { return reinterpret_cast<uint32_t *>(r + p.meta_off); }
 __device__ __forceinline__ uint8_t *rec_wall(const Params &p, uint8_t *r) { return r + p.wall_off; }
+
+// ---- lazy pheromone decay (DIFFUSE_FACTOR == 0).  A stored value v was written at update `ts` (12 bits); its
+// value after update `now` is v decayed k = now - ts times as pheromone.py:44-45 does it (multiply by
+// (1 - EVAP), zero below 0.01), and zero inside walls (walls.py:30).  Saturated deposits (v == max_val, the
+// reference's 256 > max_val = 255 case) read a table built with the reference's exact repeated rounding; other
+// values use v * 2^(k log2 c), within ~1e-13 relative of the repeated product.  The host folds all timestamps
+// before the 12-bit counter wraps.
+__device__ __forceinline__ uint32_t rec_ts(const Params &p, const uint8_t *r, int k) {
+    if (p.P <= 2) {
+        uint32_t w = *reinterpret_cast<const uint32_t *>(r + p.wall_off);      // [wall u8][ts0 12b][ts1 12b]
+        return (w >> (8 + 12 * k)) & 0xFFFu;
+    }
+    return *reinterpret_cast<const uint16_t *>(r + p.ts_off + 2 * k);
+}
+__device__ __forceinline__ void rec_set_ts(const Params &p, uint8_t *r, int k, uint32_t ts) {
+    if (p.P <= 2) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(r + p.wall_off);
+        *w = (*w & ~(0xFFFu << (8 + 12 * k))) | ((ts & 0xFFFu) << (8 + 12 * k));
+    } else {
+        *reinterpret_cast<uint16_t *>(r + p.ts_off + 2 * k) = (uint16_t)(ts & 0xFFFu);
+    }
+}
+__device__ __forceinline__ double lazy_value(const Params &p, double v, uint32_t ts, uint32_t now, bool wall) {
+    if (v == 0.0) return 0.0;
+    const uint32_t k = (now - ts) & 0xFFFu;
+    if (k == 0u) return v;
+    if (wall) return 0.0;
+    if (p.has_max_val && v == p.phero_max_val) return p.decay_table[k];
+    const double r = v * exp2((double)k * p.log2_keep);
+    return r < 0.01 ? 0.0 : r;
+}
 
 // Philox4x32-10, counter (ant, step, env, 0), key (seed_lo, seed_hi) -> one double in [0,1) built like
 // numpy's random_sample: ((a >> 5) * 2^26 + (b >> 6)) / 2^53.  Mirrored by oracle.philox_uniform.
@@ -296,7 +331,7 @@ template <int LAYOUT>
 __global__ void __launch_bounds__(kPerceiveThreads, 6)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
-           int group, uint32_t s2_magic, int slow_wrap) {
+           int group, uint32_t s2_magic, int slow_wrap, uint32_t now) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = p.S, S2 = p.S2, C = p.C;
     const int SC = S2 * C;
@@ -463,8 +498,12 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 // mask * (perception + 1) - 1 (RL_api.py:147-148): the +1-1 round trip changes a value by at most
                 // 2^-53 absolute, far below the resolution of the f32 observation, so visible samples pass through.
                 if (LAYOUT != 0) {
-                    const double ph0 = __hiloint2double((int)lo[u].y, (int)lo[u].x);
-                    const double ph1 = __hiloint2double((int)lo[u].w, (int)lo[u].z);
+                    double ph0 = __hiloint2double((int)lo[u].y, (int)lo[u].x);
+                    double ph1 = __hiloint2double((int)lo[u].w, (int)lo[u].z);
+                    if (p.lazy) {
+                        ph0 = lazy_value(p, ph0, (hi[u].w >> 8) & 0xFFFu, now, wl);
+                        ph1 = lazy_value(p, ph1, (hi[u].w >> 20) & 0xFFFu, now, wl);
+                    }
                     float v0 = ((mt >> 16) == occ_gen) ? 1.f : 0.f;                                   // :136-142
                     float v1 = (float)(ph0 * inv_max);                                                // :124-125
                     float v2 = (float)(ph1 * inv_max);
@@ -493,7 +532,12 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                         double v;
                         switch (p.ch_kind[c]) {
                             case 0: v = ((mt >> 16) == occ_gen) ? 1.0 : 0.0; break;
-                            case 1: v = *reinterpret_cast<const double *>(rp[u] + 8 * p.ch_arg[c]) * inv_max; break;
+                            case 1: {
+                                v = *reinterpret_cast<const double *>(rp[u] + 8 * p.ch_arg[c]);
+                                if (p.lazy) v = lazy_value(p, v, rec_ts(p, rp[u], p.ch_arg[c]), now, wl);
+                                v *= inv_max;
+                                break;
+                            }
                             case 2: v = hill ? 1.0 : 0.0; break;
                             case 3: v = wl ? 1.0 : 0.0; break;
                             case 4: v = fd; break;
@@ -850,7 +894,7 @@ __global__ void __launch_bounds__(256) k_diffuse_commit(Params p) {
 
 // Ants.emit_pheromones -> Pheromone.add_pheromones (ants.py:98-100, pheromone.py:36-41): the owner of each cell
 // adds its activation and clamps to max_val.
-__global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner_stamp) {
+__global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner_stamp, uint32_t now) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
@@ -863,9 +907,12 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     for (int k = 0; k < p.P; ++k) {
         double av = p.act[(int64_t)k * p.EN + i];
         if (av == 0.0) continue;
-        double v = *rec_phero(r, k) + av;
+        double old = *rec_phero(r, k);
+        if (p.lazy) old = lazy_value(p, old, rec_ts(p, r, k), now, *rec_wall(p, r) != 0);   // evaporated up to this update
+        double v = old + av;
         if (p.has_max_val) v = fmin(v, p.phero_max_val);
         *rec_phero(r, k) = v;
+        if (p.lazy) rec_set_ts(p, r, k, now);
         wrote = true;
     }
     if (wrote && p.tile_active != nullptr)
@@ -915,7 +962,8 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
 
 // ------------------------------------------------------------------------------------------------ import / export helpers
 // dense host-layout arrays <-> record fields.  `dense` is [E][planes_per_env][W][H]; field = plane `k` of them.
-__global__ void k_pack_f64(Params p, const double *__restrict__ dense, int planes_per_env, int k, int byte_off) {
+__global__ void k_pack_f64(Params p, const double *__restrict__ dense, int planes_per_env, int k, int byte_off,
+                           int phero_k, uint32_t now) {
     const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
@@ -923,18 +971,26 @@ __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int plane
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
-        *reinterpret_cast<double *>(rec_at(p, (int)e, cidx(p, x, y)) + byte_off) = v;
+        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
+        if (phero_k >= 0 && p.lazy) {
+            if (p.has_max_val) v = fmin(v, p.phero_max_val);                   // pheromone.py:41 (applied at import)
+            rec_set_ts(p, r, phero_k, now);
+        }
+        *reinterpret_cast<double *>(r + byte_off) = v;
     }
 }
-__global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off) {
+__global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off,
+                             int phero_k, uint32_t now) {
     const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
-        dense[((e * planes_per_env + k) * p.W + x) * p.H + y] =
-            *reinterpret_cast<const double *>(rec_at(p, (int)e, cidx(p, x, y)) + byte_off);
+        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
+        double v = *reinterpret_cast<const double *>(r + byte_off);
+        if (phero_k >= 0 && p.lazy) v = lazy_value(p, v, rec_ts(p, r, phero_k), now, *rec_wall(p, r) != 0);
+        dense[((e * planes_per_env + k) * p.W + x) * p.H + y] = v;
     }
 }
 // what: 0 = walls (stored as 0/1), 1 = explored (meta low half: 0xFFFF = explored long ago; occupancy cleared)
@@ -971,6 +1027,19 @@ __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
         if (fold_explored && lo) lo = 0xFFFFu;
         if (clear_occ) hi = 0;
         *mp = (hi << 16) | lo;
+    }
+}
+// lazy mode: materialise every pheromone value at `now` and reset its timestamp to 0 (before the counter wraps)
+__global__ void k_lazy_fold(Params p, uint32_t now) {
+    int64_t n = (int64_t)p.E * p.plane;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        uint8_t *r = p.cells + (j << p.rec_shift);
+        const bool wl = *rec_wall(p, r) != 0;
+        for (int k = 0; k < p.P; ++k) {
+            double v = *rec_phero(r, k);
+            if (v != 0.0) *rec_phero(r, k) = lazy_value(p, v, rec_ts(p, r, k), now, wl);
+            rec_set_ts(p, r, k, 0u);
+        }
     }
 }
 __global__ void k_rock_grid_build(Params p) {          // one block per env (after import)

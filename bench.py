@@ -364,7 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
-    ap.add_argument("--evap", default="tiles", choices=["tiles", "dense"])
+    ap.add_argument("--evap", default="lazy", choices=["lazy", "tiles", "dense"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -44,8 +44,13 @@ enum { ANTS_CH_ANTS = 0, ANTS_CH_PHERO = 1, ANTS_CH_ANTHILL = 2, ANTS_CH_WALLS =
        ANTS_CH_ROCKS = 5 };
 /* reward_custom.py: All_Rewards (:43), ExplorationReward (:8), Food_Reward (:28) */
 enum { ANTS_REWARD_ALL = 0, ANTS_REWARD_EXPLORE = 1, ANTS_REWARD_FOOD = 2 };
-/* pheromone field maintenance: dense pass over every cell, or only over tiles that hold pheromone */
-enum { ANTS_EVAP_DENSE = 0, ANTS_EVAP_ACTIVE_TILES = 1 };
+/* pheromone field maintenance (DIFFUSE_FACTOR == 0; a non-zero factor always runs the dense stencil):
+ *   DENSE        a pass over every cell each update, exactly pheromone.py:43-45
+ *   ACTIVE_TILES the same arithmetic, only over 16x16 tiles that hold pheromone (bit-identical to DENSE)
+ *   LAZY         no pass at all: each value carries the update index at which it was written and is decayed when
+ *                read (saturated max_val deposits through a table with the reference's exact rounding, other
+ *                values as v * (1-EVAP)^k, ~1e-13 relative from the repeated product) */
+enum { ANTS_EVAP_DENSE = 0, ANTS_EVAP_ACTIVE_TILES = 1, ANTS_EVAP_LAZY = 2 };
 
 typedef struct AntsConfig {
     int32_t abi_version;             /* must be ANTS_ABI_VERSION */

@@ -21,7 +21,7 @@ def _variants(kw, n):
 
 
 @pytest.mark.parametrize("name,kw", GOLDEN_SCENARIOS, ids=[n for n, _ in GOLDEN_SCENARIOS])
-@pytest.mark.parametrize("evap_mode", ["dense", "tiles"])
+@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy"])
 def test_cuda_matches_oracle_every_step(name, kw, evap_mode):
     """3 envs per scenario family (different seeds), device-pointer API, taped collision noise."""
     kw = dict(kw)
@@ -114,7 +114,7 @@ def test_large_batch_properties():
     cfg, init, tape = make_scenario(seed=900, w=256, h=256, n_ants=256, steps=30, n_walls=16, n_food=26,
                                     wall_r=(5, 15), food_r=(5, 10))
     E = 64
-    for mode in ("dense", "tiles"):
+    for mode in ("dense", "tiles", "lazy"):
         b = BatchedAnts(cfg, E, evap_mode=mode)
         b.import_state(stack_init(cfg, [init] * E))
         b.observe()
