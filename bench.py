@@ -7,7 +7,7 @@ One "step" = one pass of the hot path over the whole batch: RLApi.step(actions_t
 Philox collision noise).  value = envs x ants x steps / time, whole job over all ranks (weak scaling: the per-GPU
 shard is fixed; N = 8 of the default workload is BASELINE.json configs[3]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg2] [--envs E] [--evap tiles|dense]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg2] [--envs E] [--evap lazy|tiles|dense]
     python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
 
 Extra JSON keys: roofline (dominant kernel vs measured HBM peak), cpu_baseline (oracle on host cores, bounded
@@ -67,16 +67,45 @@ def generate_states_parallel(wl, steps, first_env, n_envs):
 
 # ----------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML every ~5 ms; nvidia-smi fallback)."""
+    SMI_Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+        try:
+            r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda name: "Active" if r & getattr(n, name, 0) else "Not Active"
+        return [sm, self.max_sm, pw, flag("nvmlClocksThrottleReasonHwSlowdown"),
+                flag("nvmlClocksThrottleReasonHwThermalSlowdown"), flag("nvmlClocksThrottleReasonSwThermalSlowdown"),
+                flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                    self._stop.wait(0.005)
+                    continue
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.SMI_Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [x.strip() for x in out.strip().split(",")]
                 if len(parts) >= 7:
@@ -100,10 +129,11 @@ class ClockSampler:
         sm = sorted(float(r[0]) for r in self.rows)
         reasons = []
         for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
-            if any(r[col].lower().startswith("active") for r in self.rows):
+            if any(str(r[col]).lower().startswith("active") for r in self.rows):
                 reasons.append(name)
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows)}
+                "samples": len(self.rows), "power_w_max": max(float(r[2]) for r in self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
@@ -154,6 +184,8 @@ def algorithmic_bytes(fam, wl, E, C, stats):
         per_ant = 49 * C * 4 + 8 + 8 + 49 * (8 * P + 8 + 1 + 1 + 1) + 82
         return EN * per_ant
     if fam == "evaporate":
+        if stats.get("evap_mode") == "lazy":
+            return 0
         if stats.get("evap_mode") == "tiles":
             return stats["active_tiles"] * 256 * (16 + 1)
         return E * W * H * (16 * P + 1)
@@ -166,6 +198,19 @@ def algorithmic_bytes(fam, wl, E, C, stats):
     if fam == "rocks":
         return EN * (16 + 16 + 24) + E * wl["n_rocks"] * 48
     return 0
+
+
+def ncu_traffic(fam, n_ants):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/latest_traffic.json,
+    written by scripts/profile_summary.py: dram__bytes_read.sum + dram__bytes_write.sum per ant x ants)."""
+    path = os.path.join(ROOT, "profiles", "latest_traffic.json")
+    try:
+        d = json.load(open(path))
+        if d.get("kernel", "").replace("k_", "") == fam:
+            return d["dram_bytes_per_ant"] * n_ants
+    except Exception:
+        pass
+    return None
 
 
 def load_peaks():
@@ -192,7 +237,7 @@ def run_ours(args):
     E = args.envs or wl["envs_per_gpu"]
     N = wl["n_ants"]
     K, W_ = args.steps, args.warmup
-    total_steps = W_ + K + args.e2e_steps + K + 4
+    total_steps = W_ + 2 * K + args.e2e_steps + 8
 
     t_setup = time.perf_counter()
     gen = make_generator(wl, total_steps + 10)
@@ -267,7 +312,7 @@ def run_ours(args):
         dom_ms_per_launch = kernels[dom]["ms_per_step"]
     achieved = abytes / (dom_ms_per_launch / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom, E * N), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": abytes, "ms_per_launch": dom_ms_per_launch}
     # whole-step view: algorithmic bytes of every family per step / step time
     step_bytes = sum(algorithmic_bytes(f, wl, E, C, st) for f in kernels)
@@ -359,8 +404,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
