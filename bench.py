@@ -232,6 +232,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = WORKLOADS[args.workload]
     E = args.envs or wl["envs_per_gpu"]

@@ -138,3 +138,55 @@ def test_large_batch_properties():
         assert st["explored"].sum() > prev_explored
         assert total0 > 0
         b.close()
+
+
+ODD_CONFIGS = [
+    # radius 1 (9 samples: several ants per lane-slot), one pheromone, no mask, few channels, tiny ant count
+    ("r1_p1", dict(seed=31, w=20, h=24, n_ants=7, n_phero=1, steps=25, radius=1, mask=None, fwd_delta=0,
+                   channels=["phero0", "food"], none_ph_every=1, n_walls=2, n_food=3, wall_r=(2, 4), food_r=(2, 4))),
+    # three pheromones -> 64-byte cell records; activations set through activate_all_pheromones only
+    ("p3", dict(seed=32, w=40, h=40, n_ants=33, n_phero=3, steps=30, none_ph_every=1,
+                channels=["ants", "phero2", "phero0", "anthill", "walls", "food", "phero1"])),
+    # map smaller than the perception reach: samples wrap more than once (slow wrap path)
+    ("tiny_map", dict(seed=33, w=9, h=11, n_ants=5, steps=25, n_walls=1, n_food=2, wall_r=(1, 2), food_r=(1, 2))),
+    # 11x11 window (121 samples), explore reward, ant count straddling block boundaries
+    ("r5_n130", dict(seed=34, w=64, h=48, n_ants=130, steps=20, radius=5, mask=None, fwd_delta=2,
+                     channels=["walls", "ants", "food"], reward_kind="explore")),
+    # no pheromones at all
+    ("p0", dict(seed=35, w=32, h=32, n_ants=20, n_phero=0, steps=20, none_ph_every=1, channels=["ants", "walls", "food", "anthill"])),
+    # rocks with a non-default channel list (generic perception path) on a non-square map
+    ("rocks_generic", dict(seed=36, w=72, h=56, n_ants=40, n_rocks=5, steps=30,
+                           channels=["rocks", "food", "ants", "phero1", "walls"])),
+]
+
+
+@pytest.mark.parametrize("name,kw", ODD_CONFIGS, ids=[n for n, _ in ODD_CONFIGS])
+@pytest.mark.parametrize("evap_mode", ["dense", "lazy"])
+def test_odd_configurations(name, kw, evap_mode):
+    rep = run_parity(_variants(kw, 3), evap_mode=evap_mode)
+    assert rep["state_checks"] == kw["steps"]
+
+
+def test_lazy_timestamp_fold():
+    """More updates than the 12-bit timestamp range: the fold pass keeps the lazily decayed field equal to the
+    eagerly evaporated one (compared between two handles of the CUDA path itself, 4200 updates)."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    cfg, init, tape = make_scenario(seed=41, w=32, h=32, n_ants=16, steps=8)
+    outs = {}
+    for mode in ("tiles", "lazy"):
+        b = BatchedAnts(cfg, 2, evap_mode=mode, rng_seed=5)
+        b.import_state(stack_init(cfg, [init, init]))
+        b.observe()
+        for t in range(4200):
+            k = t % 8
+            if t < 40:
+                rot = torch.from_numpy(np.stack([tape["rot"][k]] * 2)).cuda()
+                ph = torch.from_numpy(np.stack([tape["ph"][k]] * 2)).cuda()
+                b.step(rot, ph)
+            b.update(None)
+        outs[mode] = b.export_state(keys=("phero", "x"))
+        b.close()
+    assert np.array_equal(outs["tiles"]["x"], outs["lazy"]["x"])
+    assert outs["tiles"]["phero"].max() > 0
+    np.testing.assert_allclose(outs["lazy"]["phero"], outs["tiles"]["phero"], rtol=1e-9, atol=0)
