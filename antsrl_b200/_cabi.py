@@ -11,6 +11,7 @@ MAX_PHERO, MAX_CHANNELS, MAX_RADIUS, MAX_SAMPLES, MAX_ROCKS, MAX_ANTS = 4, 16, 7
 CH_ANTS, CH_PHERO, CH_ANTHILL, CH_WALLS, CH_FOOD, CH_ROCKS = range(6)
 REWARD_ALL, REWARD_EXPLORE, REWARD_FOOD = range(3)
 EVAP_DENSE, EVAP_ACTIVE_TILES, EVAP_LAZY = 0, 1, 2
+REC_F64, REC_COMPACT = 0, 1
 
 EXPORTED_SYMBOLS = [
     "ants_abi_version", "ants_last_error", "ants_create", "ants_destroy", "ants_set_stream", "ants_synchronize",
@@ -35,7 +36,7 @@ class AntsConfig(C.Structure):
         ("diffuse_factor", C.c_double), ("evap_factor", C.c_double),
         ("has_max_val", C.c_int32), ("phero_max_val", C.c_double), ("max_hold", C.c_double),
         ("rng_seed", C.c_uint64), ("env_id_base", C.c_int64),
-        ("evap_mode", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("evap_mode", C.c_int32), ("record_format", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 

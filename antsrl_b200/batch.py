@@ -57,7 +57,7 @@ def _channel_code(name):
             "rocks": _cabi.CH_ROCKS}[name], 0
 
 
-def build_c_config(cfg, n_envs, device=0, evap_mode="dense", rng_seed=0, env_id_base=0, delta=1.1):
+def build_c_config(cfg, n_envs, device=0, evap_mode="dense", rng_seed=0, env_id_base=0, delta=1.1, record="f64"):
     c = AntsConfig()
     c.abi_version = _cabi.ABI_VERSION
     c.device = int(device)
@@ -92,6 +92,7 @@ def build_c_config(cfg, n_envs, device=0, evap_mode="dense", rng_seed=0, env_id_
     c.max_hold = cfg["max_hold"]
     c.rng_seed, c.env_id_base = int(rng_seed), int(env_id_base)
     c.evap_mode = _EVAP_MODES[evap_mode]
+    c.record_format = {"f64": _cabi.REC_F64, "compact": _cabi.REC_COMPACT}[record]
     return c
 
 
@@ -102,7 +103,8 @@ _STATE_U8 = ("mandibles", "reward_state", "explored", "walls")
 
 
 class BatchedAnts:
-    def __init__(self, cfg, n_envs, device=0, evap_mode="dense", rng_seed=0, env_id_base=0, use_torch_stream=True):
+    def __init__(self, cfg, n_envs, device=0, evap_mode="dense", rng_seed=0, env_id_base=0, use_torch_stream=True,
+                 record="f64"):
         import torch
         if not torch.cuda.is_available():
             raise AntsError("antsrl_b200 needs a CUDA device; there is no CPU fallback")
@@ -114,7 +116,7 @@ class BatchedAnts:
         self.S = 2 * cfg["radius"] + 1
         self.C = len(cfg["channels"])
         self.device = torch.device("cuda", device)
-        self._c_cfg = build_c_config(cfg, n_envs, device, evap_mode, rng_seed, env_id_base)
+        self._c_cfg = build_c_config(cfg, n_envs, device, evap_mode, rng_seed, env_id_base, record=record)
         h = C.c_void_p()
         check(self.lib, self.lib.ants_create(C.byref(self._c_cfg), C.byref(h)))
         self._h = h

@@ -157,7 +157,7 @@ int check_launch(const char *what) {
 }
 
 uint32_t next_obs_gen(AntsBatch *b) {
-    if (b->obs_gen >= 0xFFFDu) {   // fold live stamps into "explored long ago" before the counter wraps
+    if (b->obs_gen >= b->p.explored_old - 2u) {   // fold live stamps into "explored long ago" before the counter wraps
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 1, 0);
         b->obs_gen = 0;
@@ -165,7 +165,7 @@ uint32_t next_obs_gen(AntsBatch *b) {
     return ++b->obs_gen;
 }
 uint32_t next_occ_gen(AntsBatch *b) {
-    if (b->occ_gen >= 0xFFFEu) {
+    if (b->occ_gen >= (b->p.rec16 ? 0xFEu : 0xFFFEu)) {
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 0, 1);
         b->occ_gen = 0;
@@ -190,13 +190,19 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
         const uint32_t magic = (1u << 20) / (uint32_t)p.S2 + 1u;   // f / S2 == (f * magic) >> 20 for f < 2048
         const int threads = b->perceive_threads;
         blocks = (int)cdiv(p.EN, threads);
-#define ANTS_PERCEIVE(L)                                                                                   \
-    ants::k_perceive<L><<<blocks, threads, b->perceive_smem, b->stream>>>(                                 \
+#define ANTS_PERCEIVE(L, R16)                                                                              \
+    ants::k_perceive<L, R16><<<blocks, threads, b->perceive_smem, b->stream>>>(                            \
         p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, \
         b->perceive_slow_wrap, b->lazy_now)
-        if (layout == 1) ANTS_PERCEIVE(1);
-        else if (layout == 2) ANTS_PERCEIVE(2);
-        else ANTS_PERCEIVE(0);
+        if (p.rec16) {
+            if (layout == 1) ANTS_PERCEIVE(1, true);
+            else if (layout == 2) ANTS_PERCEIVE(2, true);
+            else ANTS_PERCEIVE(0, true);
+        } else {
+            if (layout == 1) ANTS_PERCEIVE(1, false);
+            else if (layout == 2) ANTS_PERCEIVE(2, false);
+            else ANTS_PERCEIVE(0, false);
+        }
 #undef ANTS_PERCEIVE
     }
     b->rw_alias = 0;
@@ -275,7 +281,7 @@ int do_update(AntsBatch *b, const double *d_noise) {
     if (p.P > 0) {
         if (p.lazy) {
             // no pass over the field: values are evaluated at read time from their write timestamps
-            if (b->lazy_now >= 4094u) {     // fold before the 12-bit counter wraps
+            if (b->lazy_now >= p.ts_mask - 1u) {     // fold before the timestamp counter wraps
                 LaunchScope ls(b, F_EVAP);
                 ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now);
                 b->lazy_now = 0;
@@ -431,6 +437,18 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     // cell record: { f64 phero[P]; f64 food; u32 meta; u8 wall; pad } in 32 B (P <= 2) or 64 B
     p.food_off = 8 * p.P; p.meta_off = 8 * p.P + 8; p.wall_off = 8 * p.P + 12;
     p.rec_shift = (8 * p.P + 16 <= 32) ? 5 : 6;
+    p.rec16 = 0; p.ts_mask = 0xFFFu; p.explored_old = 0xFFFFu;
+    if (cfg->record_format == ANTS_REC_COMPACT) {
+        if (!(cfg->evap_mode == ANTS_EVAP_LAZY && cfg->diffuse_factor == 0.0 && p.P >= 1 && p.P <= 2)) {
+            ants_destroy(b);
+            return fail(ANTS_E_ARG, "compact records need evap_mode LAZY, no diffusion and 1 or 2 pheromones");
+        }
+        p.rec16 = 1; p.rec_shift = 4; p.ts_mask = 0xFFu; p.explored_old = 0x7Fu;
+    } else if (cfg->record_format != ANTS_REC_F64) {
+        int bad = cfg->record_format;
+        ants_destroy(b);
+        return fail(ANTS_E_ARG, "unknown record_format %d", bad);
+    }
     p.ts_off = 8 * p.P + 16;
     p.grid_w = (int)cdiv(p.W, 1 << ants::kGridShift);
     p.grid_h = (int)cdiv(p.H, 1 << ants::kGridShift);
@@ -540,9 +558,10 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     }
     if (b->perceive_smem > 48 * 1024) {
         cudaError_t e = cudaSuccess;
-        const void *fns[3] = {(const void *)ants::k_perceive<0>, (const void *)ants::k_perceive<1>,
-                              (const void *)ants::k_perceive<2>};
-        for (int k = 0; k < 3 && e == cudaSuccess; ++k)
+        const void *fns[6] = {(const void *)ants::k_perceive<0, false>, (const void *)ants::k_perceive<1, false>,
+                              (const void *)ants::k_perceive<2, false>, (const void *)ants::k_perceive<0, true>,
+                              (const void *)ants::k_perceive<1, true>, (const void *)ants::k_perceive<2, true>};
+        for (int k = 0; k < 6 && e == cudaSuccess; ++k)
             e = cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, b->perceive_smem);
         if (e != cudaSuccess) {
             ants_destroy(b);

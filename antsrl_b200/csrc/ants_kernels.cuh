@@ -38,7 +38,9 @@ struct Params {
     int32_t rule_op[kMaxCh];               // mandible rule in perceived_objects order: 0 = food OR, 1 = anthill AND
     int32_t reward_kind, explore_on, has_max_val;
     int32_t tiles_x, tiles_y;              // activity tiles per env
-    int32_t rec_shift;                     // log2(record bytes): 5 or 6
+    int32_t rec_shift;                     // log2(record bytes): 4 (compact), 5 or 6
+    int32_t rec16;                         // 1 = compact 16-byte record {f32 ph0, f32 ph1, f32 food, u8 occ, u8 wall|explored, u8 ts0, u8 ts1}
+    uint32_t ts_mask, explored_old;        // timestamp range (0xFFF / 0xFF); "explored long ago" stamp (0xFFFF / 0x7F)
     int32_t food_off, meta_off, wall_off;  // byte offsets inside a record (phero k at 8k)
     int32_t grid_w, grid_h;                // rock grid dims
     double delta, fwd_delta, reward_threshold, max_speed, max_rot_speed, csr, bsr;
@@ -111,10 +113,41 @@ __device__ __forceinline__ int cidx(const Params &p, int x, int y) {
 __device__ __forceinline__ uint8_t *rec_at(const Params &p, int e, int cell) {
     return p.cells + (((int64_t)e * p.plane + cell) << p.rec_shift);
 }
+// (f64 records only: the eager evaporation / stencil kernels)
 __device__ __forceinline__ double *rec_phero(uint8_t *r, int k) { return reinterpret_cast<double *>(r) + k; }
-__device__ __forceinline__ double *rec_food(const Params &p, uint8_t *r) { return reinterpret_cast<double *>(r + p.food_off); }
-__device__ __forceinline__ uint32_t *rec_meta(const Params &p, uint8_t *r) { return reinterpret_cast<uint32_t *>(r + p.meta_off); }
 __device__ __forceinline__ uint8_t *rec_wall(const Params &p, uint8_t *r) { return r + p.wall_off; }
+// field access for both record formats.  Compact record (lazy mode, P <= 2), 16 bytes = half a sector:
+//   [0] f32 phero0  [4] f32 phero1  [8] f32 food  [12] u8 occ_gen  [13] u8 (wall << 7 | explored_gen)  [14],[15] u8 ts
+__device__ __forceinline__ double ld_food(const Params &p, const uint8_t *r) {
+    return p.rec16 ? (double)*reinterpret_cast<const float *>(r + 8) : *reinterpret_cast<const double *>(r + p.food_off);
+}
+__device__ __forceinline__ void st_food(const Params &p, uint8_t *r, double v) {
+    if (p.rec16) *reinterpret_cast<float *>(r + 8) = (float)v; else *reinterpret_cast<double *>(r + p.food_off) = v;
+}
+__device__ __forceinline__ double ld_phero(const Params &p, const uint8_t *r, int k) {
+    return p.rec16 ? (double)reinterpret_cast<const float *>(r)[k] : reinterpret_cast<const double *>(r)[k];
+}
+__device__ __forceinline__ void st_phero(const Params &p, uint8_t *r, int k, double v) {
+    if (p.rec16) reinterpret_cast<float *>(r)[k] = (float)v; else reinterpret_cast<double *>(r)[k] = v;
+}
+__device__ __forceinline__ bool ld_wall(const Params &p, const uint8_t *r) {
+    return p.rec16 ? (r[13] >> 7) != 0 : r[p.wall_off] != 0;
+}
+__device__ __forceinline__ void st_wall(const Params &p, uint8_t *r, bool w) {
+    if (p.rec16) r[13] = (uint8_t)((r[13] & 0x7F) | (w ? 0x80 : 0)); else r[p.wall_off] = w ? 1 : 0;
+}
+__device__ __forceinline__ void st_occ(const Params &p, uint8_t *r, uint32_t gen) {
+    if (p.rec16) r[12] = (uint8_t)gen; else reinterpret_cast<uint16_t *>(r + p.meta_off)[1] = (uint16_t)gen;
+}
+__device__ __forceinline__ uint32_t ld_occ(const Params &p, const uint8_t *r) {
+    return p.rec16 ? r[12] : reinterpret_cast<const uint16_t *>(r + p.meta_off)[1];
+}
+__device__ __forceinline__ uint32_t ld_explored(const Params &p, const uint8_t *r) {
+    return p.rec16 ? (r[13] & 0x7Fu) : reinterpret_cast<const uint16_t *>(r + p.meta_off)[0];
+}
+__device__ __forceinline__ void st_explored(const Params &p, uint8_t *r, uint32_t gen) {
+    if (p.rec16) r[13] = (uint8_t)((r[13] & 0x80) | (gen & 0x7F)); else reinterpret_cast<uint16_t *>(r + p.meta_off)[0] = (uint16_t)gen;
+}
 
 // ---- lazy pheromone decay (DIFFUSE_FACTOR == 0).  A stored value v was written at update `ts` (12 bits); its
 // value after update `now` is v decayed k = now - ts times as pheromone.py:44-45 does it (multiply by
@@ -123,6 +156,7 @@ __device__ __forceinline__ uint8_t *rec_wall(const Params &p, uint8_t *r) { retu
 // values use v * 2^(k log2 c), within ~1e-13 relative of the repeated product.  The host folds all timestamps
 // before the 12-bit counter wraps.
 __device__ __forceinline__ uint32_t rec_ts(const Params &p, const uint8_t *r, int k) {
+    if (p.rec16) return r[14 + k];
     if (p.P <= 2) {
         uint32_t w = *reinterpret_cast<const uint32_t *>(r + p.wall_off);      // [wall u8][ts0 12b][ts1 12b]
         return (w >> (8 + 12 * k)) & 0xFFFu;
@@ -130,6 +164,7 @@ __device__ __forceinline__ uint32_t rec_ts(const Params &p, const uint8_t *r, in
     return *reinterpret_cast<const uint16_t *>(r + p.ts_off + 2 * k);
 }
 __device__ __forceinline__ void rec_set_ts(const Params &p, uint8_t *r, int k, uint32_t ts) {
+    if (p.rec16) { r[14 + k] = (uint8_t)ts; return; }
     if (p.P <= 2) {
         uint32_t *w = reinterpret_cast<uint32_t *>(r + p.wall_off);
         *w = (*w & ~(0xFFFu << (8 + 12 * k))) | ((ts & 0xFFFu) << (8 + 12 * k));
@@ -139,7 +174,7 @@ __device__ __forceinline__ void rec_set_ts(const Params &p, uint8_t *r, int k, u
 }
 __device__ __forceinline__ double lazy_value(const Params &p, double v, uint32_t ts, uint32_t now, bool wall) {
     if (v == 0.0) return 0.0;
-    const uint32_t k = (now - ts) & 0xFFFu;
+    const uint32_t k = (now - ts) & p.ts_mask;
     if (k == 0u) return v;
     if (wall) return 0.0;
     if (p.has_max_val && v == p.phero_max_val) return p.decay_table[k];
@@ -220,7 +255,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     int m_old = p.mandibles[i] != 0;
     int pcx = cell_of(p.prev_x[i], p.W), pcy = cell_of(p.prev_y[i], p.H);      // RL_api.py:178
     int pcell = cidx(p, pcx, pcy);
-    double f = *rec_food(p, rec_at(p, e, pcell));
+    double f = ld_food(p, rec_at(p, e, pcell));
     const int32_t *hl = p.hill + 4 * e;
     bool hill = in_hill(hl, cell_of(x, p.W), cell_of(y, p.H));                  // RL_api.py:184
     int m = m_old;
@@ -257,7 +292,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     y = pymod(y + s * fwd, (double)p.H);
     p.x[i] = x; p.y[i] = y; p.theta[i] = th;
     uint8_t *orec = rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H)));
-    reinterpret_cast<uint16_t *>(rec_meta(p, orec))[1] = (uint16_t)occ_gen;
+    st_occ(p, orec, occ_gen);
 }
 
 // Occupancy stamp alone, for a stand-alone observation() (main.py:88).
@@ -266,7 +301,7 @@ __global__ void __launch_bounds__(256) k_occ_stamp(Params p, uint32_t occ_gen) {
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
     uint8_t *orec = rec_at(p, e, cidx(p, cell_of(p.x[i], p.W), cell_of(p.y[i], p.H)));
-    reinterpret_cast<uint16_t *>(rec_meta(p, orec))[1] = (uint16_t)occ_gen;
+    st_occ(p, orec, occ_gen);
 }
 
 // ------------------------------------------------------------------------------------------------ step, part 2
@@ -281,9 +316,10 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
         int pcx = cell_of(p.prev_x[i], p.W), pcy = cell_of(p.prev_y[i], p.H);
         int pcell = cidx(p, pcx, pcy);
         if (p.owner[(int64_t)e * p.plane + pcell] != (owner_stamp | (uint32_t)a)) continue;
-        double *fp = rec_food(p, rec_at(p, e, pcell));
-        double nv = *fp + p.food_delta[i];
-        *fp = nv;
+        uint8_t *fr = rec_at(p, e, pcell);
+        double nv = ld_food(p, fr) + p.food_delta[i];
+        st_food(p, fr, nv);
+        nv = ld_food(p, fr);                                                   // as stored (f32 in compact records)
         if (nv != 0.0 && in_hill(p.hill + 4 * e, pcx, pcy)) {
             uint32_t s = atomicAdd(p.absorb_count, 1u);
             p.absorb_list[2 * s] = (uint32_t)e;
@@ -327,7 +363,7 @@ struct SampleTab {                          // per sample of the window: offsets
     double px, py;
 };
 
-template <int LAYOUT>
+template <int LAYOUT, bool REC16>
 __global__ void __launch_bounds__(kPerceiveThreads, 6)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
@@ -447,10 +483,13 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (LAYOUT != 0) {             // P == 2: {ph0, ph1} | {food, meta, wall}
+                if (REC16) {                   // compact record: the whole cell in one 128-bit load
+                    lo[u] = *reinterpret_cast<const uint4 *>(rp[u]);
+                    hi[u] = make_uint4(0u, 0u, 0u, 0u);
+                } else if (LAYOUT != 0) {      // P == 2: {ph0, ph1} | {food, meta, wall + timestamps}
                     lo[u] = *reinterpret_cast<const uint4 *>(rp[u]);
                     hi[u] = *reinterpret_cast<const uint4 *>(rp[u] + 16);
-                } else {                       // generic record: gather the fields into the same register shape
+                } else {                       // generic f64 record: gather the fields into the same register shape
                     const double fdv = *reinterpret_cast<const double *>(rp[u] + food_off);
                     const uint32_t mtv = *reinterpret_cast<const uint32_t *>(rp[u] + meta_off);
                     const uint32_t wlv = *(rp[u] + wall_off);
@@ -464,12 +503,30 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 if (f0 >= nsamp) break;
                 const int f = f0 + lane;
                 const bool valid = f < nsamp;
-                const uint32_t mt = hi[u].z;
+                // fields of the record, whatever its format
+                uint32_t occ, eg, ts0, ts1;
+                bool wl;
+                double fd, ph0 = 0.0, ph1 = 0.0;
+                if (REC16) {
+                    const uint32_t pk = lo[u].w;
+                    occ = pk & 0xFFu; eg = (pk >> 8) & 0x7Fu; wl = ((pk >> 15) & 1u) != 0; ts0 = (pk >> 16) & 0xFFu; ts1 = pk >> 24;
+                    ph0 = (double)__uint_as_float(lo[u].x); ph1 = (double)__uint_as_float(lo[u].y);
+                    fd = (double)__uint_as_float(lo[u].z);
+                } else {
+                    occ = hi[u].z >> 16; eg = hi[u].z & 0xFFFFu; wl = (hi[u].w & 0xFFu) != 0;
+                    ts0 = (hi[u].w >> 8) & 0xFFFu; ts1 = (hi[u].w >> 20) & 0xFFFu;
+                    fd = __hiloint2double((int)hi[u].y, (int)hi[u].x);
+                    if (LAYOUT != 0) {
+                        ph0 = __hiloint2double((int)lo[u].y, (int)lo[u].x);
+                        ph1 = __hiloint2double((int)lo[u].w, (int)lo[u].z);
+                    }
+                }
                 if (explore_on) {
-                    const uint32_t eg = mt & 0xFFFFu;
                     const bool unexplored = valid && ((eg == 0u) || (eg == obs_gen));     // gather-before-scatter, Q7
-                    if (valid && eg == 0u)
-                        *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(rp[u]) + meta_off) = (uint16_t)obs_gen;
+                    if (valid && eg == 0u) {
+                        if (REC16) const_cast<uint8_t *>(rp[u])[13] = (uint8_t)((wl ? 0x80u : 0u) | obs_gen);
+                        else *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(rp[u]) + meta_off) = (uint16_t)obs_gen;
+                    }
                     // the slot's lanes belong to consecutive ants: split the ballot at the ant boundaries (uniform)
                     uint32_t votes = __ballot_sync(0xffffffffu, unexplored);
                     int a_lo = (int)(((uint32_t)f0 * s2_magic) >> 20);
@@ -488,8 +545,6 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 const int aj = (int)(((uint32_t)f * s2_magic) >> 20);
                 const int s = f - aj * S2;
                 const int ix = (int)(xy[u] >> 16), iy = (int)(xy[u] & 0xFFFFu);
-                const double fd = __hiloint2double((int)hi[u].y, (int)hi[u].x);
-                const bool wl = (hi[u].w & 0xFFu) != 0;
                 const bool vis = s_mask[s] != 0;
                 float *o = wobs + f * C;
                 const AntPrep &q = wprep[g + aj];
@@ -498,13 +553,11 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 // mask * (perception + 1) - 1 (RL_api.py:147-148): the +1-1 round trip changes a value by at most
                 // 2^-53 absolute, far below the resolution of the f32 observation, so visible samples pass through.
                 if (LAYOUT != 0) {
-                    double ph0 = __hiloint2double((int)lo[u].y, (int)lo[u].x);
-                    double ph1 = __hiloint2double((int)lo[u].w, (int)lo[u].z);
                     if (p.lazy) {
-                        ph0 = lazy_value(p, ph0, (hi[u].w >> 8) & 0xFFFu, now, wl);
-                        ph1 = lazy_value(p, ph1, (hi[u].w >> 20) & 0xFFFu, now, wl);
+                        ph0 = lazy_value(p, ph0, ts0, now, wl);
+                        ph1 = lazy_value(p, ph1, ts1, now, wl);
                     }
-                    float v0 = ((mt >> 16) == occ_gen) ? 1.f : 0.f;                                   // :136-142
+                    float v0 = (occ == occ_gen) ? 1.f : 0.f;                                          // :136-142
                     float v1 = (float)(ph0 * inv_max);                                                // :124-125
                     float v2 = (float)(ph1 * inv_max);
                     float v3 = hill ? 1.f : 0.f;                                                      // :130-131
@@ -531,9 +584,9 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                     for (int c = 0; c < C; ++c) {
                         double v;
                         switch (p.ch_kind[c]) {
-                            case 0: v = ((mt >> 16) == occ_gen) ? 1.0 : 0.0; break;
+                            case 0: v = (occ == occ_gen) ? 1.0 : 0.0; break;
                             case 1: {
-                                v = *reinterpret_cast<const double *>(rp[u] + 8 * p.ch_arg[c]);
+                                v = ld_phero(p, rp[u], p.ch_arg[c]);
                                 if (p.lazy) v = lazy_value(p, v, rec_ts(p, rp[u], p.ch_arg[c]), now, wl);
                                 v *= inv_max;
                                 break;
@@ -613,7 +666,7 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
     int e = (int)(i / p.N);
     int a = (int)(i - (int64_t)e * p.N);
     double x = p.x[i], y = p.y[i], th = p.theta[i];
-    if (*rec_wall(p, rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H))))) {
+    if (ld_wall(p, rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H))))) {
         x = p.prev_x[i]; y = p.prev_y[i];
         double u = noise ? noise[i] : philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)a);
         th += u - 0.5;                                                         // not re-wrapped (Q3)
@@ -907,11 +960,11 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     for (int k = 0; k < p.P; ++k) {
         double av = p.act[(int64_t)k * p.EN + i];
         if (av == 0.0) continue;
-        double old = *rec_phero(r, k);
-        if (p.lazy) old = lazy_value(p, old, rec_ts(p, r, k), now, *rec_wall(p, r) != 0);   // evaporated up to this update
+        double old = ld_phero(p, r, k);
+        if (p.lazy) old = lazy_value(p, old, rec_ts(p, r, k), now, ld_wall(p, r));          // evaporated up to this update
         double v = old + av;
         if (p.has_max_val) v = fmin(v, p.phero_max_val);
-        *rec_phero(r, k) = v;
+        st_phero(p, r, k, v);
         if (p.lazy) rec_set_ts(p, r, k, now);
         wrote = true;
     }
@@ -924,8 +977,10 @@ __global__ void __launch_bounds__(256) k_absorb_list(Params p) {
     uint32_t n = *p.absorb_count;
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
         uint32_t e = p.absorb_list[2 * k], c = p.absorb_list[2 * k + 1];
-        unsigned long long *fp = reinterpret_cast<unsigned long long *>(rec_food(p, rec_at(p, (int)e, (int)c)));
-        double v = __longlong_as_double((long long)atomicExch(fp, 0ull));      // qte -= qte * area
+        uint8_t *fr = rec_at(p, (int)e, (int)c);
+        double v;                                                              // qte -= qte * area
+        if (p.rec16) v = (double)__uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(fr + 8), 0u));
+        else v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(fr + p.food_off), 0ull));
         if (v != 0.0) atomicAdd(p.hill_food + e, v);
     }
     __syncthreads();
@@ -946,9 +1001,9 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
         for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
             int cx = x0 + t / bh, cy = y0 + t % bh;
             if (!in_hill(hl, cx, cy)) continue;
-            double *fp = rec_food(p, rec_at(p, e, cidx(p, cx, cy)));
-            double v = *fp;
-            if (v != 0.0) { acc += v; *fp = v - v; }
+            uint8_t *fr = rec_at(p, e, cidx(p, cx, cy));
+            double v = ld_food(p, fr);
+            if (v != 0.0) { acc += v; st_food(p, fr, v - v); }
         }
     }
     red[threadIdx.x] = acc;
@@ -972,11 +1027,15 @@ __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int plane
         int x = (int)(ex - e * p.W);
         double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        if (phero_k >= 0 && p.lazy) {
-            if (p.has_max_val) v = fmin(v, p.phero_max_val);                   // pheromone.py:41 (applied at import)
-            rec_set_ts(p, r, phero_k, now);
+        if (phero_k >= 0) {
+            if (p.lazy) {
+                if (p.has_max_val) v = fmin(v, p.phero_max_val);               // pheromone.py:41 (applied at import)
+                rec_set_ts(p, r, phero_k, now);
+            }
+            st_phero(p, r, phero_k, v);
+        } else {
+            st_food(p, r, v);
         }
-        *reinterpret_cast<double *>(r + byte_off) = v;
     }
 }
 __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off,
@@ -988,8 +1047,8 @@ __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_pe
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        double v = *reinterpret_cast<const double *>(r + byte_off);
-        if (phero_k >= 0 && p.lazy) v = lazy_value(p, v, rec_ts(p, r, phero_k), now, *rec_wall(p, r) != 0);
+        double v = phero_k >= 0 ? ld_phero(p, r, phero_k) : ld_food(p, r);
+        if (phero_k >= 0 && p.lazy) v = lazy_value(p, v, rec_ts(p, r, phero_k), now, ld_wall(p, r));
         dense[((e * planes_per_env + k) * p.W + x) * p.H + y] = v;
     }
 }
@@ -1002,8 +1061,8 @@ __global__ void k_pack_u8(Params p, const uint8_t *__restrict__ dense, int what)
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        if (what == 0) *rec_wall(p, r) = dense[j] ? 1 : 0;
-        else *rec_meta(p, r) = dense[j] ? 0xFFFFu : 0u;
+        if (what == 0) st_wall(p, r, dense[j] != 0);
+        else { st_explored(p, r, dense[j] ? p.explored_old : 0u); st_occ(p, r, 0u); }
     }
 }
 __global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what) {
@@ -1014,19 +1073,16 @@ __global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what) {
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        dense[j] = what == 0 ? *rec_wall(p, r) : ((*rec_meta(p, r) & 0xFFFFu) ? 1 : 0);
+        dense[j] = what == 0 ? (ld_wall(p, r) ? 1 : 0) : (ld_explored(p, r) ? 1 : 0);
     }
 }
 // generation counters are 16 bit: before one wraps, fold every live stamp into the "long ago" value
 __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
     int64_t n = (int64_t)p.E * p.plane;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t *mp = rec_meta(p, p.cells + (j << p.rec_shift));
-        uint32_t m = *mp;
-        uint32_t lo = m & 0xFFFFu, hi = m >> 16;
-        if (fold_explored && lo) lo = 0xFFFFu;
-        if (clear_occ) hi = 0;
-        *mp = (hi << 16) | lo;
+        uint8_t *r = p.cells + (j << p.rec_shift);
+        if (fold_explored && ld_explored(p, r)) st_explored(p, r, p.explored_old);
+        if (clear_occ) st_occ(p, r, 0u);
     }
 }
 // lazy mode: materialise every pheromone value at `now` and reset its timestamp to 0 (before the counter wraps)
@@ -1034,10 +1090,10 @@ __global__ void k_lazy_fold(Params p, uint32_t now) {
     int64_t n = (int64_t)p.E * p.plane;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         uint8_t *r = p.cells + (j << p.rec_shift);
-        const bool wl = *rec_wall(p, r) != 0;
+        const bool wl = ld_wall(p, r);
         for (int k = 0; k < p.P; ++k) {
-            double v = *rec_phero(r, k);
-            if (v != 0.0) *rec_phero(r, k) = lazy_value(p, v, rec_ts(p, r, k), now, wl);
+            double v = ld_phero(p, r, k);
+            if (v != 0.0) st_phero(p, r, k, lazy_value(p, v, rec_ts(p, r, k), now, wl));
             rec_set_ts(p, r, k, 0u);
         }
     }

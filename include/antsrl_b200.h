@@ -52,6 +52,13 @@ enum { ANTS_REWARD_ALL = 0, ANTS_REWARD_EXPLORE = 1, ANTS_REWARD_FOOD = 2 };
  *                values as v * (1-EVAP)^k, ~1e-13 relative from the repeated product) */
 enum { ANTS_EVAP_DENSE = 0, ANTS_EVAP_ACTIVE_TILES = 1, ANTS_EVAP_LAZY = 2 };
 
+/* map cell record in HBM:
+ *   F64      { f64 phero[P]; f64 food; u32 meta; u8 wall; timestamps }  32 B (P <= 2) / 64 B: every evap mode
+ *   COMPACT  { f32 phero0; f32 phero1; f32 food; 4 x u8 stamps }        16 B: two cells per DRAM sector.  Needs
+ *            ANTS_EVAP_LAZY, P <= 2 and no diffusion.  Saturated (max_val) deposits stay bit-exact through the
+ *            decay table; other pheromone values and non-integer food are rounded to f32 (6e-8 relative). */
+enum { ANTS_REC_F64 = 0, ANTS_REC_COMPACT = 1 };
+
 typedef struct AntsConfig {
     int32_t abi_version;             /* must be ANTS_ABI_VERSION */
     int32_t device;                  /* CUDA device ordinal */
@@ -82,7 +89,8 @@ typedef struct AntsConfig {
     uint64_t rng_seed;
     int64_t env_id_base;
     int32_t evap_mode;               /* ANTS_EVAP_* */
-    int32_t reserved[7];
+    int32_t record_format;           /* ANTS_REC_* */
+    int32_t reserved[6];
 } AntsConfig;
 
 /* Host-side SoA view of the whole batch for import/export.  NULL members are skipped. */

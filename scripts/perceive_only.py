@@ -11,7 +11,7 @@ if os.environ.get("N_ANTS"): wl["n_ants"] = int(os.environ["N_ANTS"])
 E = int(os.environ.get("ENVS", "256"))
 gen = bench.make_generator(wl, 1000)
 states = bench.generate_states_parallel(wl, 1000, 0, E)
-b = BatchedAnts(gen.cfg, E, evap_mode=os.environ.get("EVAP", "tiles"))
+b = BatchedAnts(gen.cfg, E, evap_mode=os.environ.get("EVAP", "lazy"), record=os.environ.get("REC", "f64"))
 b.import_state(stack_states(states, "all"))
 b.activate_all_pheromones(np.ones((E, wl["n_ants"], 2)) * 10.0)
 rs = np.random.RandomState(1)

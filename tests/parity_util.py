@@ -63,7 +63,7 @@ def _np(a):
 
 
 def run_parity(scenarios, evap_mode="dense", state_every=1, use_host_api=False, noise_mode="tape", rng_seed=7,
-               env_id_base=0):
+               env_id_base=0, record="f64"):
     """scenarios: list of (cfg, init, tape) sharing cfg and tape length.  Runs main.py's loop order
     (observation; T x [step; update]) on the GPU batch and on one oracle per env, comparing everything."""
     import torch
@@ -72,7 +72,7 @@ def run_parity(scenarios, evap_mode="dense", state_every=1, use_host_api=False, 
     cfg = scenarios[0][0]
     E = len(scenarios)
     oracles = [OracleEnv(c, i) for c, i, _ in scenarios]
-    batch = BatchedAnts(cfg, E, evap_mode=evap_mode, rng_seed=rng_seed, env_id_base=env_id_base)
+    batch = BatchedAnts(cfg, E, evap_mode=evap_mode, rng_seed=rng_seed, env_id_base=env_id_base, record=record)
     batch.import_state(stack_init(cfg, [i for _, i, _ in scenarios]))
     dev = batch.device
     T = scenarios[0][2]["rot"].shape[0]

@@ -21,12 +21,18 @@ def _variants(kw, n):
 
 
 @pytest.mark.parametrize("name,kw", GOLDEN_SCENARIOS, ids=[n for n, _ in GOLDEN_SCENARIOS])
-@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy"])
+@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy", "lazy_compact"])
 def test_cuda_matches_oracle_every_step(name, kw, evap_mode):
-    """3 envs per scenario family (different seeds), device-pointer API, taped collision noise."""
+    """3 envs per scenario family (different seeds), device-pointer API, taped collision noise; every evaporation
+    mode and both cell-record formats."""
     kw = dict(kw)
     kw["steps"] = min(kw["steps"], 40)
-    rep = run_parity(_variants(kw, 3), evap_mode=evap_mode)
+    record = "f64"
+    if evap_mode == "lazy_compact":
+        if kw.get("diffuse_factor", 0.0) != 0.0:
+            pytest.skip("compact records exist for the lazy (diffusion-free) field only")
+        evap_mode, record = "lazy", "compact"
+    rep = run_parity(_variants(kw, 3), evap_mode=evap_mode, record=record)
     assert rep["kernel_launches"] > 0
 
 
@@ -114,8 +120,9 @@ def test_large_batch_properties():
     cfg, init, tape = make_scenario(seed=900, w=256, h=256, n_ants=256, steps=30, n_walls=16, n_food=26,
                                     wall_r=(5, 15), food_r=(5, 10))
     E = 64
-    for mode in ("dense", "tiles", "lazy"):
-        b = BatchedAnts(cfg, E, evap_mode=mode)
+    for mode in ("dense", "tiles", "lazy", "compact"):
+        b = BatchedAnts(cfg, E, evap_mode="lazy" if mode == "compact" else mode,
+                        record="compact" if mode == "compact" else "f64")
         b.import_state(stack_init(cfg, [init] * E))
         b.observe()
         total0 = init["food"].sum()
@@ -161,9 +168,14 @@ ODD_CONFIGS = [
 
 
 @pytest.mark.parametrize("name,kw", ODD_CONFIGS, ids=[n for n, _ in ODD_CONFIGS])
-@pytest.mark.parametrize("evap_mode", ["dense", "lazy"])
+@pytest.mark.parametrize("evap_mode", ["dense", "lazy", "lazy_compact"])
 def test_odd_configurations(name, kw, evap_mode):
-    rep = run_parity(_variants(kw, 3), evap_mode=evap_mode)
+    record = "f64"
+    if evap_mode == "lazy_compact":
+        if kw.get("n_phero", 2) not in (1, 2):
+            pytest.skip("compact records hold one or two pheromones")
+        evap_mode, record = "lazy", "compact"
+    rep = run_parity(_variants(kw, 3), evap_mode=evap_mode, record=record)
     assert rep["state_checks"] == kw["steps"]
 
 
@@ -174,8 +186,9 @@ def test_lazy_timestamp_fold():
     from antsrl_b200 import BatchedAnts
     cfg, init, tape = make_scenario(seed=41, w=32, h=32, n_ants=16, steps=8)
     outs = {}
-    for mode in ("tiles", "lazy"):
-        b = BatchedAnts(cfg, 2, evap_mode=mode, rng_seed=5)
+    for mode in ("tiles", "lazy", "compact"):
+        b = BatchedAnts(cfg, 2, evap_mode="lazy" if mode == "compact" else mode, rng_seed=5,
+                        record="compact" if mode == "compact" else "f64")
         b.import_state(stack_init(cfg, [init, init]))
         b.observe()
         for t in range(4200):
@@ -190,3 +203,5 @@ def test_lazy_timestamp_fold():
     assert np.array_equal(outs["tiles"]["x"], outs["lazy"]["x"])
     assert outs["tiles"]["phero"].max() > 0
     np.testing.assert_allclose(outs["lazy"]["phero"], outs["tiles"]["phero"], rtol=1e-9, atol=0)
+    assert np.array_equal(outs["tiles"]["x"], outs["compact"]["x"])
+    np.testing.assert_allclose(outs["compact"]["phero"], outs["tiles"]["phero"], rtol=1e-5, atol=0)
