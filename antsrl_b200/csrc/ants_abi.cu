@@ -58,7 +58,8 @@ struct AntsBatch {
     uint32_t obs_gen = 0, occ_gen = 0, owner_phase = 0;
     int64_t timestep = 1;
     int rw_alias = 1, act_bool = 1, prev_synced = 1, needs_sweep = 1;
-    uint32_t lazy_now = 0;          // updates since the last timestamp fold (lazy evaporation), < 4096
+    uint32_t lazy_now = 0;          // updates since the last fold of plain values (lazy evaporation), small counter
+    uint32_t lazy_abs = 0;          // updates since creation / the last unboxing fold (22 bits)
     AntsStats stats;
     // profiling
     int profiling = 0;
@@ -193,7 +194,7 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
 #define ANTS_PERCEIVE(L, R16)                                                                              \
     ants::k_perceive<L, R16><<<blocks, threads, b->perceive_smem, b->stream>>>(                            \
         p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, \
-        b->perceive_slow_wrap, b->lazy_now)
+        b->perceive_slow_wrap, b->lazy_now, b->lazy_abs)
         if (p.rec16) {
             if (layout == 1) ANTS_PERCEIVE(1, true);
             else if (layout == 2) ANTS_PERCEIVE(2, true);
@@ -281,12 +282,15 @@ int do_update(AntsBatch *b, const double *d_noise) {
     if (p.P > 0) {
         if (p.lazy) {
             // no pass over the field: values are evaluated at read time from their write timestamps
-            if (b->lazy_now >= p.ts_mask - 1u) {     // fold before the timestamp counter wraps
+            const bool unbox = b->lazy_abs >= ants::kBoxMask - 2u;
+            if (b->lazy_now >= p.ts_mask - 1u || unbox) {     // fold before a counter wraps
                 LaunchScope ls(b, F_EVAP);
-                ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now);
+                ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now, b->lazy_abs, unbox ? 1 : 0);
                 b->lazy_now = 0;
+                if (unbox) b->lazy_abs = 0;
             }
             b->lazy_now += 1;
+            b->lazy_abs += 1;
             b->stats.active_tiles = 0;
         } else if (b->cfg.diffuse_factor != 0.0) {
             int nbx = (int)cdiv(p.W, ants::kStX), nby = (int)cdiv(p.H, ants::kStY);
@@ -317,7 +321,7 @@ int do_update(AntsBatch *b, const double *d_noise) {
         // 6. Ants.update (order 999): deposit
         {
             LaunchScope ls(b, F_DEPOSIT);
-            ants::k_deposit_commit<<<blocks, 256, 0, b->stream>>>(p, phase << 16, b->lazy_now);
+            ants::k_deposit_commit<<<blocks, 256, 0, b->stream>>>(p, phase << 16, b->lazy_now, b->lazy_abs);
         }
         TRY(check_launch("k_deposit_commit"));
     }
@@ -496,8 +500,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
     A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
     A(dev_alloc(b, &p.tile_counter, 1));
-    double *d_table = nullptr;
-    A(dev_alloc(b, &d_table, 4096));
+
     b->stats.total_tiles = (int64_t)p.E * p.tiles_x * p.tiles_y;
     // perception tables, RL_api.py:92-93: coords[i][j] = ((j - r) * DELTA, (i - r) * DELTA)
     double *d_off = nullptr;
@@ -516,15 +519,31 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         cudaMemcpy(d_off, off.data(), p.S * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(d_mask, mk.data(), p.S2, cudaMemcpyHostToDevice);
         p.samp_off = d_off; p.mask = d_mask;
-        // pheromone.py:44-45 applied k times to max_val, with the reference's rounding at every step
-        std::vector<double> tab(4096);
+        // pheromone.py:44-45 applied k times to max_val, with the reference's rounding at every step, until 0
+        const int kTabCap = 16384;
+        std::vector<double> tab;
+        std::vector<float> tobs;
         volatile double v = cfg->has_max_val ? cfg->phero_max_val : 0.0;
-        for (int k = 0; k < 4096; ++k) {
-            tab[k] = v;
+        volatile double inv = cfg->has_max_val && cfg->phero_max_val != 0.0 ? 1.0 / cfg->phero_max_val : 0.0;
+        for (int k = 0; k < kTabCap; ++k) {
+            const double vv = v;
+            tab.push_back(vv);
+            volatile double ob = vv * inv;
+            tobs.push_back((float)ob);
+            if (v == 0.0) break;
             volatile double nv = v * p.filt_center;
             v = nv < 0.01 ? 0.0 : nv;
         }
-        cudaMemcpy(d_table, tab.data(), 4096 * sizeof(double), cudaMemcpyHostToDevice);
+        p.tab_len = (int)tab.size();
+        double *d_table = nullptr;
+        float *d_tobs = nullptr;
+        if (dev_alloc(b, &d_table, p.tab_len) != ANTS_OK || dev_alloc(b, &d_tobs, p.tab_len) != ANTS_OK) {
+            ants_destroy(b);
+            return ANTS_E_ALLOC;
+        }
+        cudaMemcpy(d_table, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_tobs, tobs.data(), tobs.size() * sizeof(float), cudaMemcpyHostToDevice);
+        p.decay_obs = d_tobs;
         p.decay_table = d_table;
     }
     {   // ants per staged chunk: as many as fit ~12 KB per warp, keeping the chunk a multiple of 16 B and the
@@ -648,7 +667,7 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     }
     if (s->phero && p.P > 0) {
         CK(cudaMemcpyAsync(d_tmp, s->phero, ncell * 8 * p.P, cudaMemcpyHostToDevice, st));
-        for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now);
+        for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs);
         TRY(check_launch("k_pack_f64"));
         if (p.tile_active) {
             ants::k_tiles_from_phero<<<148 * 4, 256, 0, st>>>(p);
@@ -657,7 +676,7 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     }
     if (s->food) {
         CK(cudaMemcpyAsync(d_tmp, s->food, ncell * 8, cudaMemcpyHostToDevice, st));
-        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off, -1, 0u);
+        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off, -1, 0u, 0u);
         TRY(check_launch("k_pack_f64"));
         b->needs_sweep = 1;
     }
@@ -732,12 +751,12 @@ int ants_export_state(AntsBatch *b, AntsHostState *s) {
         if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "export scratch of %zu bytes: %s", need, cudaGetErrorString(me));
     }
     if (s->phero && p.P > 0) {
-        for (int k = 0; k < p.P; ++k) ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now);
+        for (int k = 0; k < p.P; ++k) ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs);
         TRY(check_launch("k_unpack_f64"));
         CK(cudaMemcpyAsync(s->phero, d_tmp, ncell * 8 * p.P, cudaMemcpyDeviceToHost, st));
     }
     if (s->food) {
-        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off, -1, 0u);
+        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off, -1, 0u, 0u);
         TRY(check_launch("k_unpack_f64"));
         CK(cudaMemcpyAsync(s->food, d_tmp, ncell * 8, cudaMemcpyDeviceToHost, st));
     }

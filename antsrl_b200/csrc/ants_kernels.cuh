@@ -49,7 +49,9 @@ struct Params {
     double log2_keep;                      // log2(filt_center): lazy decay of values that are not on the table
     int32_t lazy;                          // 1 = pheromone values carry write timestamps, no evaporation pass
     int32_t ts_off;                        // P > 2: byte offset of the u16 timestamps (P <= 2: packed next to the wall byte)
-    const double *decay_table;             // [4096] max_val decayed k times exactly like the reference
+    const double *decay_table;             // [tab_len] max_val decayed k times exactly like the reference
+    const float *decay_obs;                // [tab_len] (float)(decay_table[k] / max_val): what the f32 observation shows
+    int32_t tab_len;                       // entries until the table reaches 0 (capped)
     uint64_t rng_seed;
     int64_t env_id_base;
     // ants, [E*N]
@@ -149,12 +151,24 @@ __device__ __forceinline__ void st_explored(const Params &p, uint8_t *r, uint32_
     if (p.rec16) r[13] = (uint8_t)((r[13] & 0x80) | (gen & 0x7F)); else reinterpret_cast<uint16_t *>(r + p.meta_off)[0] = (uint16_t)gen;
 }
 
-// ---- lazy pheromone decay (DIFFUSE_FACTOR == 0).  A stored value v was written at update `ts` (12 bits); its
-// value after update `now` is v decayed k = now - ts times as pheromone.py:44-45 does it (multiply by
-// (1 - EVAP), zero below 0.01), and zero inside walls (walls.py:30).  Saturated deposits (v == max_val, the
-// reference's 256 > max_val = 255 case) read a table built with the reference's exact repeated rounding; other
-// values use v * 2^(k log2 c), within ~1e-13 relative of the repeated product.  The host folds all timestamps
-// before the 12-bit counter wraps.
+// ---- lazy pheromone decay (DIFFUSE_FACTOR == 0): no pass over the field, values are decoded when read.
+// A stored pheromone field is one of
+//   0                      nothing
+//   boxed(t)               quiet NaN whose 22-bit payload is the absolute update index t at which a SATURATED
+//                          deposit (value == max_val: the reference's 256 > 255 case) was written.  Its value
+//                          after update `now_abs` is decay_table[now_abs - t], the table holding max_val decayed
+//                          k times with the reference's own rounding and < 0.01 cut (pheromone.py:44-45) -- bit
+//                          exact for the whole episode, never folded.
+//   plain value v          any other value, with a small write timestamp ts (8 or 12 bits); decays as
+//                          v * 2^(k log2 c), k = now - ts (~1e-13 relative from the repeated product); the host
+//                          folds plain values before the small counter wraps.
+// Inside walls everything reads 0 one update after it was written (walls.py:30).
+constexpr uint32_t kBoxMask = 0x3FFFFFu;   // 22-bit absolute step
+__device__ __forceinline__ bool is_boxed32(uint32_t b) { return (b & 0xFFC00000u) == 0x7FC00000u; }
+__device__ __forceinline__ uint32_t box32(uint32_t t) { return 0x7FC00000u | (t & kBoxMask); }
+__device__ __forceinline__ bool is_boxed64(unsigned long long b) { return (b >> 32 & 0xFFF80000u) == 0x7FF80000u; }
+__device__ __forceinline__ unsigned long long box64(uint32_t t) { return 0x7FF8000000000000ull | (t & kBoxMask); }
+
 __device__ __forceinline__ uint32_t rec_ts(const Params &p, const uint8_t *r, int k) {
     if (p.rec16) return r[14 + k];
     if (p.P <= 2) {
@@ -172,14 +186,45 @@ __device__ __forceinline__ void rec_set_ts(const Params &p, uint8_t *r, int k, u
         *reinterpret_cast<uint16_t *>(r + p.ts_off + 2 * k) = (uint16_t)(ts & 0xFFFu);
     }
 }
-__device__ __forceinline__ double lazy_value(const Params &p, double v, uint32_t ts, uint32_t now, bool wall) {
+// value of a saturated deposit of age `age` updates
+__device__ __forceinline__ double boxed_value(const Params &p, uint32_t age, bool wall) {
+    if (wall && age) return 0.0;
+    return age < (uint32_t)p.tab_len ? p.decay_table[age] : 0.0;
+}
+// value of a plain stored number
+__device__ __forceinline__ double plain_value(const Params &p, double v, uint32_t ts, uint32_t now, bool wall) {
     if (v == 0.0) return 0.0;
     const uint32_t k = (now - ts) & p.ts_mask;
     if (k == 0u) return v;
     if (wall) return 0.0;
-    if (p.has_max_val && v == p.phero_max_val) return p.decay_table[k];
     const double r = v * exp2((double)k * p.log2_keep);
     return r < 0.01 ? 0.0 : r;
+}
+// current value of pheromone k of record r (any format; eager modes store plain numbers without decay)
+__device__ __forceinline__ double phero_value(const Params &p, const uint8_t *r, int k, uint32_t now, uint32_t now_abs) {
+    if (p.rec16) {
+        const uint32_t b = reinterpret_cast<const uint32_t *>(r)[k];
+        if (b == 0u) return 0.0;
+        const bool wl = (r[13] >> 7) != 0;
+        if (is_boxed32(b)) return boxed_value(p, (now_abs - b) & kBoxMask, wl);
+        return plain_value(p, (double)__uint_as_float(b), r[14 + k], now, wl);
+    }
+    const unsigned long long b = reinterpret_cast<const unsigned long long *>(r)[k];
+    if (!p.lazy) return __longlong_as_double((long long)b);
+    if (b == 0ull) return 0.0;
+    const bool wl = r[p.wall_off] != 0;
+    if (is_boxed64(b)) return boxed_value(p, (now_abs - (uint32_t)b) & kBoxMask, wl);
+    return plain_value(p, __longlong_as_double((long long)b), rec_ts(p, r, k), now, wl);
+}
+// store a pheromone value that is current at (now, now_abs)
+__device__ __forceinline__ void phero_store(const Params &p, uint8_t *r, int k, double v, uint32_t now, uint32_t now_abs) {
+    if (p.lazy && p.has_max_val && v == p.phero_max_val) {
+        if (p.rec16) reinterpret_cast<uint32_t *>(r)[k] = box32(now_abs);
+        else reinterpret_cast<unsigned long long *>(r)[k] = box64(now_abs);
+        return;
+    }
+    if (p.rec16) reinterpret_cast<float *>(r)[k] = (float)v; else reinterpret_cast<double *>(r)[k] = v;
+    if (p.lazy) rec_set_ts(p, r, k, now);
 }
 
 // Philox4x32-10, counter (ant, step, env, 0), key (seed_lo, seed_hi) -> one double in [0,1) built like
@@ -367,7 +412,7 @@ template <int LAYOUT, bool REC16>
 __global__ void __launch_bounds__(kPerceiveThreads, 6)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
-           int group, uint32_t s2_magic, int slow_wrap, uint32_t now) {
+           int group, uint32_t s2_magic, int slow_wrap, uint32_t now, uint32_t now_abs) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = p.S, S2 = p.S2, C = p.C;
     const int SC = S2 * C;
@@ -504,22 +549,16 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 const int f = f0 + lane;
                 const bool valid = f < nsamp;
                 // fields of the record, whatever its format
-                uint32_t occ, eg, ts0, ts1;
+                uint32_t occ, eg;
                 bool wl;
-                double fd, ph0 = 0.0, ph1 = 0.0;
+                float fdf;                     // food as the f32 observation shows it
                 if (REC16) {
                     const uint32_t pk = lo[u].w;
-                    occ = pk & 0xFFu; eg = (pk >> 8) & 0x7Fu; wl = ((pk >> 15) & 1u) != 0; ts0 = (pk >> 16) & 0xFFu; ts1 = pk >> 24;
-                    ph0 = (double)__uint_as_float(lo[u].x); ph1 = (double)__uint_as_float(lo[u].y);
-                    fd = (double)__uint_as_float(lo[u].z);
+                    occ = pk & 0xFFu; eg = (pk >> 8) & 0x7Fu; wl = ((pk >> 15) & 1u) != 0;
+                    fdf = __uint_as_float(lo[u].z);
                 } else {
                     occ = hi[u].z >> 16; eg = hi[u].z & 0xFFFFu; wl = (hi[u].w & 0xFFu) != 0;
-                    ts0 = (hi[u].w >> 8) & 0xFFFu; ts1 = (hi[u].w >> 20) & 0xFFFu;
-                    fd = __hiloint2double((int)hi[u].y, (int)hi[u].x);
-                    if (LAYOUT != 0) {
-                        ph0 = __hiloint2double((int)lo[u].y, (int)lo[u].x);
-                        ph1 = __hiloint2double((int)lo[u].w, (int)lo[u].z);
-                    }
+                    fdf = (float)__hiloint2double((int)hi[u].y, (int)hi[u].x);
                 }
                 if (explore_on) {
                     const bool unexplored = valid && ((eg == 0u) || (eg == obs_gen));     // gather-before-scatter, Q7
@@ -553,16 +592,31 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 // mask * (perception + 1) - 1 (RL_api.py:147-148): the +1-1 round trip changes a value by at most
                 // 2^-53 absolute, far below the resolution of the f32 observation, so visible samples pass through.
                 if (LAYOUT != 0) {
-                    if (p.lazy) {
-                        ph0 = lazy_value(p, ph0, ts0, now, wl);
-                        ph1 = lazy_value(p, ph1, ts1, now, wl);
+                    // pheromone channels, RL_api.py:124-125: zero and saturated-deposit fields (the common cases)
+                    // decode without f64; anything else goes through phero_value
+                    float v1, v2;
+                    if (REC16) {
+                        const uint32_t b0 = lo[u].x, b1 = lo[u].y;
+                        if (b0 == 0u) v1 = 0.f;
+                        else if (is_boxed32(b0) && !wl) { uint32_t age = (now_abs - b0) & kBoxMask; v1 = age < (uint32_t)p.tab_len ? p.decay_obs[age] : 0.f; }
+                        else v1 = (float)(phero_value(p, rp[u], 0, now, now_abs) * inv_max);
+                        if (b1 == 0u) v2 = 0.f;
+                        else if (is_boxed32(b1) && !wl) { uint32_t age = (now_abs - b1) & kBoxMask; v2 = age < (uint32_t)p.tab_len ? p.decay_obs[age] : 0.f; }
+                        else v2 = (float)(phero_value(p, rp[u], 1, now, now_abs) * inv_max);
+                    } else {
+                        const unsigned long long b0 = ((unsigned long long)lo[u].y << 32) | lo[u].x;
+                        const unsigned long long b1 = ((unsigned long long)lo[u].w << 32) | lo[u].z;
+                        if (b0 == 0ull) v1 = 0.f;
+                        else if (p.lazy && is_boxed64(b0) && !wl) { uint32_t age = (now_abs - lo[u].x) & kBoxMask; v1 = age < (uint32_t)p.tab_len ? p.decay_obs[age] : 0.f; }
+                        else v1 = (float)(phero_value(p, rp[u], 0, now, now_abs) * inv_max);
+                        if (b1 == 0ull) v2 = 0.f;
+                        else if (p.lazy && is_boxed64(b1) && !wl) { uint32_t age = (now_abs - lo[u].z) & kBoxMask; v2 = age < (uint32_t)p.tab_len ? p.decay_obs[age] : 0.f; }
+                        else v2 = (float)(phero_value(p, rp[u], 1, now, now_abs) * inv_max);
                     }
                     float v0 = (occ == occ_gen) ? 1.f : 0.f;                                          // :136-142
-                    float v1 = (float)(ph0 * inv_max);                                                // :124-125
-                    float v2 = (float)(ph1 * inv_max);
                     float v3 = hill ? 1.f : 0.f;                                                      // :130-131
                     float v4 = wl ? 1.f : 0.f;                                                        // :128-129
-                    float v5 = (float)fd;                                                             // :126-127
+                    float v5 = fdf;                                                                   // :126-127
                     float v6 = 0.f;
                     if (LAYOUT == 2) {                                                                // :132-135
                         unsigned long long rm = q.rocks;
@@ -585,15 +639,10 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                         double v;
                         switch (p.ch_kind[c]) {
                             case 0: v = (occ == occ_gen) ? 1.0 : 0.0; break;
-                            case 1: {
-                                v = ld_phero(p, rp[u], p.ch_arg[c]);
-                                if (p.lazy) v = lazy_value(p, v, rec_ts(p, rp[u], p.ch_arg[c]), now, wl);
-                                v *= inv_max;
-                                break;
-                            }
+                            case 1: v = phero_value(p, rp[u], p.ch_arg[c], now, now_abs) * inv_max; break;
                             case 2: v = hill ? 1.0 : 0.0; break;
                             case 3: v = wl ? 1.0 : 0.0; break;
-                            case 4: v = fd; break;
+                            case 4: v = (double)fdf; break;
                             default: {
                                 v = 0.0;
                                 unsigned long long rm = q.rocks;
@@ -947,7 +996,7 @@ __global__ void __launch_bounds__(256) k_diffuse_commit(Params p) {
 
 // Ants.emit_pheromones -> Pheromone.add_pheromones (ants.py:98-100, pheromone.py:36-41): the owner of each cell
 // adds its activation and clamps to max_val.
-__global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner_stamp, uint32_t now) {
+__global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner_stamp, uint32_t now, uint32_t now_abs) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
@@ -960,12 +1009,9 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     for (int k = 0; k < p.P; ++k) {
         double av = p.act[(int64_t)k * p.EN + i];
         if (av == 0.0) continue;
-        double old = ld_phero(p, r, k);
-        if (p.lazy) old = lazy_value(p, old, rec_ts(p, r, k), now, ld_wall(p, r));          // evaporated up to this update
-        double v = old + av;
+        double v = phero_value(p, r, k, now, now_abs) + av;                    // (lazy: evaporated up to this update)
         if (p.has_max_val) v = fmin(v, p.phero_max_val);
-        st_phero(p, r, k, v);
-        if (p.lazy) rec_set_ts(p, r, k, now);
+        phero_store(p, r, k, v, now, now_abs);
         wrote = true;
     }
     if (wrote && p.tile_active != nullptr)
@@ -1018,7 +1064,7 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
 // ------------------------------------------------------------------------------------------------ import / export helpers
 // dense host-layout arrays <-> record fields.  `dense` is [E][planes_per_env][W][H]; field = plane `k` of them.
 __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int planes_per_env, int k, int byte_off,
-                           int phero_k, uint32_t now) {
+                           int phero_k, uint32_t now, uint32_t now_abs) {
     const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
@@ -1028,18 +1074,15 @@ __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int plane
         double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
         if (phero_k >= 0) {
-            if (p.lazy) {
-                if (p.has_max_val) v = fmin(v, p.phero_max_val);               // pheromone.py:41 (applied at import)
-                rec_set_ts(p, r, phero_k, now);
-            }
-            st_phero(p, r, phero_k, v);
+            if (p.lazy && p.has_max_val) v = fmin(v, p.phero_max_val);         // pheromone.py:41 (applied at import)
+            phero_store(p, r, phero_k, v, now, now_abs);
         } else {
             st_food(p, r, v);
         }
     }
 }
 __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off,
-                             int phero_k, uint32_t now) {
+                             int phero_k, uint32_t now, uint32_t now_abs) {
     const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
@@ -1047,8 +1090,7 @@ __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_pe
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        double v = phero_k >= 0 ? ld_phero(p, r, phero_k) : ld_food(p, r);
-        if (phero_k >= 0 && p.lazy) v = lazy_value(p, v, rec_ts(p, r, phero_k), now, ld_wall(p, r));
+        double v = phero_k >= 0 ? phero_value(p, r, phero_k, now, now_abs) : ld_food(p, r);
         dense[((e * planes_per_env + k) * p.W + x) * p.H + y] = v;
     }
 }
@@ -1085,15 +1127,20 @@ __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
         if (clear_occ) st_occ(p, r, 0u);
     }
 }
-// lazy mode: materialise every pheromone value at `now` and reset its timestamp to 0 (before the counter wraps)
-__global__ void k_lazy_fold(Params p, uint32_t now) {
+// lazy mode: re-base every PLAIN pheromone value to timestamp 0 (before the small counter wraps); boxed saturated
+// deposits are left alone unless `unbox` is set (the 22-bit absolute counter is about to wrap)
+__global__ void k_lazy_fold(Params p, uint32_t now, uint32_t now_abs, int unbox) {
     int64_t n = (int64_t)p.E * p.plane;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         uint8_t *r = p.cells + (j << p.rec_shift);
-        const bool wl = ld_wall(p, r);
         for (int k = 0; k < p.P; ++k) {
-            double v = ld_phero(p, r, k);
-            if (v != 0.0) st_phero(p, r, k, lazy_value(p, v, rec_ts(p, r, k), now, wl));
+            bool boxed, zero;
+            if (p.rec16) { uint32_t b = reinterpret_cast<const uint32_t *>(r)[k]; boxed = is_boxed32(b); zero = b == 0u; }
+            else { unsigned long long b = reinterpret_cast<const unsigned long long *>(r)[k]; boxed = is_boxed64(b); zero = b == 0ull; }
+            if (zero || (boxed && !unbox)) { if (!boxed) rec_set_ts(p, r, k, 0u); continue; }
+            const double v = phero_value(p, r, k, now, now_abs);
+            // written as a plain number valid at timestamp 0 (never re-boxed: it is no longer max_val unless age 0)
+            if (p.rec16) reinterpret_cast<float *>(r)[k] = (float)v; else reinterpret_cast<double *>(r)[k] = v;
             rec_set_ts(p, r, k, 0u);
         }
     }

@@ -143,6 +143,7 @@ class BatchedEnvironmentGenerator:
                                self.walls_generator, seed=self.seed_base + first_env + e) for e in range(n_envs)]
 
     def generate(self, n_envs, device=0, first_env=0, float_activation=True, **batch_kw):
+        batch_kw.setdefault("evap_mode", "lazy")
         """-> BatchedAnts holding envs [first_env, first_env + n_envs) (global ids, for sharding)."""
         from .batch import BatchedAnts
         states = self.generate_states(n_envs, first_env)

@@ -245,7 +245,9 @@ def run_ours(args):
     states = generate_states_parallel(wl, total_steps + 10, rank * E, E)
     from antsrl_b200 import BatchedAnts
     from antsrl_b200.generator import stack_states
-    batch = BatchedAnts(gen.cfg, E, device=local_rank, evap_mode=args.evap, rng_seed=20261018, env_id_base=rank * E)
+    record = args.record if args.evap == "lazy" else "f64"
+    batch = BatchedAnts(gen.cfg, E, device=local_rank, evap_mode=args.evap, rng_seed=20261018, env_id_base=rank * E,
+                        record=record)
     batch.import_state(stack_states(states, gen.cfg["reward_kind"]))
     del states
     batch.activate_all_pheromones(np.ones((E, N, wl["n_phero"])) * 10.0)      # agent.initialize, collect_agent.py:100
@@ -367,8 +369,10 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "envs_per_gpu": E, "envs_total": E * world,
                        "ants_per_env": N, "map": [wl["w"], wl["h"]], "pheromones": wl["n_phero"], "rocks": wl["n_rocks"],
-                       "obs": "7x7x%d f32" % C, "evaporation": st["evap_mode"],
-                       "precision": "f64 positions/fields, f32 obs", "l2": "state per GPU (%.1f GB) >> 126 MB L2"
+                       "obs": "7x7x%d f32" % C, "evaporation": st["evap_mode"], "cell_record": record,
+                       "precision": "f64 positions / headings / sample coordinates; %s; f32 obs" % (
+                           "16 B cell records (f32 pheromone, bit-exact for saturated deposits via the decay table; f32 food)"
+                           if record == "compact" else "f64 fields"), "l2": "state per GPU (%.1f GB) >> 126 MB L2"
                        % (st["device_bytes"] / 1e9), "parallelism": "env-sharded x%d, no per-step collective" % world,
                        "noise": "in-kernel Philox", "actions": "uniform random, pre-recorded tape on device"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "kernels": kernels,
@@ -411,6 +415,8 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--evap", default="lazy", choices=["lazy", "tiles", "dense"])
+    ap.add_argument("--record", default="compact", choices=["compact", "f64"],
+                    help="cell record format (compact = 16 B, lazy mode only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
