@@ -157,6 +157,18 @@ int check_launch(const char *what) {
     return ANTS_OK;
 }
 
+// 16-bit (f64 records) or 7/8-bit (compact records) generation counters: before either wraps, ONE pass folds
+// every live exploration stamp into "explored long ago" and clears the occupancy stamps.  Called at the start of
+// observe / step, before any stamp of the new generation is written.
+void maybe_fold_generations(AntsBatch *b) {
+    const uint32_t obs_lim = b->p.explored_old - 2u, occ_lim = b->p.rec16 ? 0xFEu : 0xFFFEu;
+    if (b->obs_gen + 1u >= obs_lim || b->occ_gen + 1u >= occ_lim) {
+        LaunchScope ls(b, F_MISC);
+        ants::k_meta_renormalize<<<148 * 16, 256, 0, b->stream>>>(b->p, 1, 1);
+        b->obs_gen = 0;
+        b->occ_gen = 0;
+    }
+}
 uint32_t next_obs_gen(AntsBatch *b) {
     if (b->obs_gen >= b->p.explored_old - 2u) {   // fold live stamps into "explored long ago" before the counter wraps
         LaunchScope ls(b, F_MISC);
@@ -213,6 +225,7 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
 int do_observe(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward) {
     if (!d_obs || !d_as) return fail(ANTS_E_ARG, "ants_observe: obs and agent_state buffers are required");
     const Params &p = b->p;
+    maybe_fold_generations(b);
     uint32_t occ = next_occ_gen(b);
     {
         LaunchScope ls(b, F_MOVE);
@@ -231,6 +244,7 @@ int do_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs,
     if (d_ph && p.P != 2)
         return fail(ANTS_E_ARG, "pheromone actions need exactly two pheromones (ants.py:92-96), have %d", p.P);
     CK(cudaMemsetAsync(p.commit_count, 0, sizeof(uint32_t), b->stream));
+    maybe_fold_generations(b);
     uint32_t phase = next_owner_phase(b);
     uint32_t occ = next_occ_gen(b);
     int blocks = (int)cdiv(p.EN, 256);
@@ -500,6 +514,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
     A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
     A(dev_alloc(b, &p.tile_counter, 1));
+    A(dev_alloc(b, &p.plain_flag, 1));
 
     b->stats.total_tiles = (int64_t)p.E * p.tiles_x * p.tiles_y;
     // perception tables, RL_api.py:92-93: coords[i][j] = ((j - r) * DELTA, (i - r) * DELTA)

@@ -75,6 +75,7 @@ struct Params {
     uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food of a cell this step
     uint32_t *absorb_list, *absorb_count;  // (env, cell) pairs of food lying inside the anthill disc
     unsigned long long *tile_counter;      // tiles processed by the evaporation kernel
+    uint32_t *plain_flag;                  // lazy mode: set once any plain (non-saturated) pheromone value is stored
 };
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -224,7 +225,10 @@ __device__ __forceinline__ void phero_store(const Params &p, uint8_t *r, int k, 
         return;
     }
     if (p.rec16) reinterpret_cast<float *>(r)[k] = (float)v; else reinterpret_cast<double *>(r)[k] = v;
-    if (p.lazy) rec_set_ts(p, r, k, now);
+    if (p.lazy) {
+        rec_set_ts(p, r, k, now);
+        if (v != 0.0 && *p.plain_flag == 0u) *p.plain_flag = 1u;
+    }
 }
 
 // Philox4x32-10, counter (ant, step, env, 0), key (seed_lo, seed_hi) -> one double in [0,1) built like
@@ -1123,13 +1127,14 @@ __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
     int64_t n = (int64_t)p.E * p.plane;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         uint8_t *r = p.cells + (j << p.rec_shift);
-        if (fold_explored && ld_explored(p, r)) st_explored(p, r, p.explored_old);
-        if (clear_occ) st_occ(p, r, 0u);
+        if (fold_explored) { uint32_t g = ld_explored(p, r); if (g != 0u && g != p.explored_old) st_explored(p, r, p.explored_old); }
+        if (clear_occ && ld_occ(p, r) != 0u) st_occ(p, r, 0u);
     }
 }
 // lazy mode: re-base every PLAIN pheromone value to timestamp 0 (before the small counter wraps); boxed saturated
 // deposits are left alone unless `unbox` is set (the 22-bit absolute counter is about to wrap)
 __global__ void k_lazy_fold(Params p, uint32_t now, uint32_t now_abs, int unbox) {
+    if (!unbox && *p.plain_flag == 0u) return;         // only saturated (boxed) deposits exist: nothing to re-base
     int64_t n = (int64_t)p.E * p.plane;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         uint8_t *r = p.cells + (j << p.rec_shift);
