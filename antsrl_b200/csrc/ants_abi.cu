@@ -355,15 +355,6 @@ int do_update(AntsBatch *b, const double *d_noise) {
     return ANTS_OK;
 }
 
-bool is_device_accessible_host(const void *ptr) {
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
 int ensure_staging(AntsBatch *b) {
     if (b->st_obs) return ANTS_OK;
     const Params &p = b->p;

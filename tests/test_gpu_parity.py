@@ -205,3 +205,31 @@ def test_lazy_timestamp_fold():
     np.testing.assert_allclose(outs["lazy"]["phero"], outs["tiles"]["phero"], rtol=1e-9, atol=0)
     assert np.array_equal(outs["tiles"]["x"], outs["compact"]["x"])
     np.testing.assert_allclose(outs["compact"]["phero"], outs["tiles"]["phero"], rtol=1e-5, atol=0)
+
+
+def test_rollout_equals_step_update_loop():
+    """ants_rollout (device-resident action tapes, C loop) == the same steps issued one by one."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    scen = [make_scenario(seed=800 + e, w=48, h=48, n_ants=40, steps=12, n_walls=6) for e in range(3)]
+    cfg = scen[0][0]
+    rot = torch.from_numpy(np.stack([[s[2]["rot"][t] for s in scen] for t in range(12)])).cuda().contiguous()
+    ph = torch.from_numpy(np.stack([[s[2]["ph"][t] for s in scen] for t in range(12)])).cuda().contiguous()
+    outs = []
+    for mode in ("loop", "rollout"):
+        b = BatchedAnts(cfg, 3, evap_mode="lazy", record="compact", rng_seed=3)
+        b.import_state(stack_init(cfg, [i for _, i, _ in scen]))
+        b.observe()
+        if mode == "loop":
+            for t in range(12):
+                obs, ast, rew, _ = b.step(rot[t], ph[t])
+                b.update(None)
+        else:
+            obs, ast, rew = b.rollout(rot, ph)
+        st = b.export_state()
+        outs.append((obs.cpu().numpy().copy(), rew.cpu().numpy().copy(), st))
+        b.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for k, v in outs[0][2].items():
+        if isinstance(v, np.ndarray):
+            assert np.array_equal(v, outs[1][2][k]), k
