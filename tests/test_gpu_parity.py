@@ -233,3 +233,41 @@ def test_rollout_equals_step_update_loop():
     for k, v in outs[0][2].items():
         if isinstance(v, np.ndarray):
             assert np.array_equal(v, outs[1][2][k]), k
+
+
+@pytest.mark.parametrize("record", ["compact", "f64"])
+def test_full_size_env_matches_oracle(record):
+    """BASELINE configs[3] dimensions (1024x1024 map, 1024 ants, 64 rocks, 7x7x7 obs) for two envs generated by the
+    drop-in generator (seeds 1000, 1001), 12 steps with Philox collision noise, compared with the oracle."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from antsrl_b200.generator import BatchedEnvironmentGenerator, CirclesGenerator, stack_states
+    from oracle.antsrl_oracle import OracleEnv, philox_uniform
+    from parity_util import compare_state
+    gen = BatchedEnvironmentGenerator(1024, 1024, 1024, 2, 64, CirclesGenerator(320, 5, 10), CirclesGenerator(400, 5, 15),
+                                      max_steps=100, seed_base=1000)
+    states = gen.generate_states(2, 0)
+    cfg = gen.cfg
+    oracles = [OracleEnv(cfg, s) for s in states]
+    batch = BatchedAnts(cfg, 2, evap_mode="lazy", record=record, rng_seed=11)
+    batch.import_state(stack_states(states, "all"))
+    act = np.ones((2, 1024, 2)) * 10.0
+    batch.activate_all_pheromones(act)
+    for o in oracles:
+        o.activate_all_pheromones(act[0])
+    obs, ast, st, rew = batch.observe()
+    ref = [o.observation() for o in oracles]
+    assert_close(obs.cpu().numpy(), np.stack([r[0] for r in ref]), "obs0")
+    rs = np.random.RandomState(5)
+    for t in range(12):
+        rot = (rs.randint(0, 3, (2, 1024)) - 1).astype(np.int8)
+        ph = rs.randint(0, 3, (2, 1024)).astype(np.int8)
+        refs = [o.step(rot[e].astype(np.int64), ph[e].astype(np.int64)) for e, o in enumerate(oracles)]
+        obs, ast, rew, done = batch.step(torch.from_numpy(rot).cuda(), torch.from_numpy(ph).cuda())
+        assert_close(obs.cpu().numpy(), np.stack([r[0] for r in refs]), "obs %d" % t)
+        assert_close(rew.cpu().numpy(), np.stack([r[2] for r in refs]), "reward %d" % t)
+        for e, o in enumerate(oracles):
+            o.update(philox_uniform(11, e, int(o.s["timestep"]), 1024))
+        batch.update(None)
+    compare_state(batch.export_state(), oracles, "final (1024x1024)", cfg)
+    batch.close()
