@@ -271,3 +271,42 @@ def test_full_size_env_matches_oracle(record):
         batch.update(None)
     compare_state(batch.export_state(), oracles, "final (1024x1024)", cfg)
     batch.close()
+
+
+def _random_config(rng):
+    """A random small configuration of the whole path (map, ants, perception window, channels, reward, speeds)."""
+    w, h = int(rng.randint(12, 70)), int(rng.randint(12, 70))
+    n_rocks = int(rng.choice([0, 0, 3]))
+    n_phero = 2
+    radius = int(rng.choice([1, 2, 3, 3, 4]))
+    s = 2 * radius + 1
+    mask = None if rng.rand() < 0.3 else (rng.rand(s, s) < 0.75)
+    pool = ["ants", "phero0", "phero1", "anthill", "walls", "food"] + (["rocks"] if n_rocks else [])
+    if rng.rand() < 0.5:
+        channels = None
+    else:
+        k = int(rng.randint(2, len(pool) + 1))
+        channels = [pool[i] for i in rng.permutation(len(pool))[:k]]
+    reward_kind = str(rng.choice(["all", "all", "explore", "food"]))
+    kw = dict(seed=int(rng.randint(1, 10 ** 6)), w=w, h=h, n_ants=int(rng.randint(1, 90)), n_rocks=n_rocks,
+              n_phero=n_phero, steps=int(rng.randint(8, 22)), n_walls=int(rng.randint(0, 5)), n_food=int(rng.randint(1, 7)),
+              wall_r=(1, max(2, min(w, h) // 8)), food_r=(1, max(2, min(w, h) // 8)), radius=radius, mask=mask,
+              fwd_delta=float(rng.choice([0, 2, 4])), reward_kind=reward_kind,
+              reward_factors=tuple(float(x) for x in rng.choice([0, 1, 2, 5], size=5)),
+              reward_threshold=float(rng.choice([0.5, 1.0, 3.0])), max_speed=float(rng.choice([0.6, 1.0, 1.9])),
+              max_rot_speed=float(rng.uniform(0.2, 1.2)), carry_speed_reduction=float(rng.choice([0.05, 0.3])),
+              backward_speed_reduction=float(rng.choice([0.5, 0.8])), evap_factor=float(rng.choice([0.001, 0.05])),
+              float_food=bool(rng.rand() < 0.3), act_float=bool(rng.rand() < 0.7),
+              none_rot_every=int(rng.choice([0, 0, 4])), none_ph_every=int(rng.choice([0, 0, 5])))
+    if channels is not None:
+        kw["channels"] = channels
+    return kw
+
+
+@pytest.mark.parametrize("case", range(24))
+def test_random_configurations(case):
+    """Seeded fuzz over the configuration space; record format and evaporation mode rotate with the case."""
+    rng = np.random.RandomState(9000 + case)
+    kw = _random_config(rng)
+    mode, record = [("dense", "f64"), ("tiles", "f64"), ("lazy", "f64"), ("lazy", "compact")][case % 4]
+    run_parity(_variants(kw, 2), evap_mode=mode, record=record)
