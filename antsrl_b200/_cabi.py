@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libantsrl_b200.so")
+LIB_PATH = os.environ.get("ANTS_LIB") or os.path.join(_HERE, "lib", "libantsrl_b200.so")   # ANTS_LIB: experiment builds
 
 ABI_VERSION = 1
 MAX_PHERO, MAX_CHANNELS, MAX_RADIUS, MAX_SAMPLES, MAX_ROCKS, MAX_ANTS = 4, 16, 7, 225, 64, 65535

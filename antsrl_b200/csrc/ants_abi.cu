@@ -74,6 +74,7 @@ struct AntsBatch {
     uint32_t *h_counts = nullptr;   // pinned: commit_count, absorb_count readback
     uint32_t *tile_list = nullptr;
     int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128, perceive_slow_wrap = 0;
+    int perceive_rows = 0, rows_smem = 0;   // 1 = k_perceive_rows serves this configuration (default channel list, 7x7 window)
 };
 
 namespace {
@@ -203,6 +204,17 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
         const uint32_t magic = (1u << 20) / (uint32_t)p.S2 + 1u;   // f / S2 == (f * magic) >> 20 for f < 2048
         const int threads = b->perceive_threads;
         blocks = (int)cdiv(p.EN, threads);
+        if (b->perceive_rows) {
+            const int rblocks = (int)cdiv(p.EN, ants::kRowsThreads);
+#define ANTS_ROWS(L, R16)                                                                                   \
+    ants::k_perceive_rows<L, R16, 7><<<rblocks, ants::kRowsThreads, b->rows_smem, b->stream>>>(             \
+        p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias,                            \
+        b->lazy_now, b->lazy_abs, dbg)
+            static int dbg = getenv("ANTS_DBG") ? atoi(getenv("ANTS_DBG")) : 0;
+            if (p.rec16) { if (layout == 2) ANTS_ROWS(2, true); else ANTS_ROWS(1, true); }
+            else { if (layout == 2) ANTS_ROWS(2, false); else ANTS_ROWS(1, false); }
+#undef ANTS_ROWS
+        } else
 #define ANTS_PERCEIVE(L, R16)                                                                              \
     ants::k_perceive<L, R16><<<blocks, threads, b->perceive_smem, b->stream>>>(                            \
         p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, magic, \
@@ -522,6 +534,12 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         }
         if (cfg->has_mask)
             for (int k = 0; k < p.S2; ++k) mk[k] = cfg->mask[k] ? 1 : 0;
+        for (int k = 0; k < 16; ++k) {
+            p.off_c[k] = k < p.S ? off[k] : 0.0;
+            uint32_t bits = 0;
+            for (int j = 0; k < p.S && j < p.S; ++j) bits |= (uint32_t)(mk[k * p.S + j] ? 1u : 0u) << j;
+            p.mask_rows[k] = bits;
+        }
         cudaMemcpy(d_off, off.data(), p.S * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(d_mask, mk.data(), p.S2, cudaMemcpyHostToDevice);
         p.samp_off = d_off; p.mask = d_mask;
@@ -580,6 +598,13 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         ok = ok && p.ch_arg[1] == 0 && p.ch_arg[2] == 1;
         if (ok && p.C == 7) ok = p.ch_kind[6] == ANTS_CH_ROCKS;
         b->perceive_layout = ok ? (p.C == 7 ? 2 : 1) : 0;
+    }
+    {   // the row-per-lane kernel serves the default channel lists with the default 7x7 window
+        const int C = p.C;
+        b->perceive_rows = (b->perceive_layout != 0 && p.S == 7 && !b->perceive_slow_wrap &&
+                            !getenv("ANTS_PERCEIVE_GENERIC")) ? 1 : 0;
+        b->rows_smem = (ants::kRowsThreads / 32) * ants::kRowsGroup * p.S2 * C * 4 +
+                       ants::kRowsThreads * (int)sizeof(ants::RowPrep) + ants::kRowsThreads * p.S;
     }
     if (b->perceive_smem > 48 * 1024) {
         cudaError_t e = cudaSuccess;

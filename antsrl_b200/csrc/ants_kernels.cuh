@@ -70,6 +70,8 @@ struct Params {
     unsigned long long *rock_grid;         // [E][grid_w][grid_h] bitmask of rocks near each 16x16 block
     const double *samp_off;                // [S] = (k - r) * DELTA  (RL_api.py:92-93)
     const uint8_t *mask;                   // [S2]
+    double off_c[16];                      // the same offsets in the kernel-parameter constant bank
+    uint32_t mask_rows[16];                // bit j of entry i = mask[i][j] (all ones without a mask)
     // scratch
     double *food_delta;                    // [E*N]
     uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food of a cell this step
@@ -1182,3 +1184,5 @@ __global__ void k_tiles_from_phero(Params p) {
 }
 
 }  // namespace ants
+
+#include "ants_perceive_rows.cuh"

@@ -1,0 +1,351 @@
+// ants_perceive_rows.cuh -- the perception + reward kernel for the generator's default channel list
+// (RL_api.py:96-165, reward_custom.py:79-106, ants.py:119-121), "row per lane" mapping.
+//
+// The generic kernel (k_perceive in ants_kernels.cuh) spreads a chunk's samples over the lanes by a flat sample
+// index: every sample re-derives its ant and its window position and re-reads the ant's frame from shared memory,
+// and the exploration counts need a ballot split at the ant boundaries -- ncu showed ~490 warp instructions per ant
+// with the issue slots as the limiter.  Here a warp still owns 32 consecutive ants and walks them in chunks of 4
+// (the bulk-store granule: 4 * S*S * C * 4 bytes is always a multiple of 16), but lane l of the chunk is
+//     ant  a = l / S        row  i = l % S        (4 * S <= 32 lanes active; 28 of 32 for the default 7x7 window)
+// and loops over the S columns j of its row.  Everything that depends on (ant, row) -- cos/sin of the frame, the
+// shifted position, st*Y and ct*Y of RL_api.py:110-111, the anthill, the record base, the row's mask bits -- lives in
+// registers for the whole row; the column offset X = off[j] is a kernel-parameter constant after unrolling, so a
+// sample costs two f64 multiplies, four adds and two conversions for its cell (bit-identical to the reference's
+// ct*X - st*Y, st*X + ct*Y: every product is rounded separately, -fmad=false), one 128-bit record load (compact
+// records; two for f64 records), a branch-free decode and C shared-memory stores.  All record loads of a row are in
+// flight before the first is decoded.  Exploration counts are per-lane adds, summed over the S rows in the epilogue.
+// The staged (4 x S*S x C) f32 tile leaves with one TMA bulk store, as before.
+#pragma once
+
+namespace ants {
+
+constexpr int kRowsThreads = 128;
+constexpr int kRowsGroup = 4;
+
+struct RowPrep {                 // 64 bytes per ant, shared memory (phase A -> phase B)
+    double ct, st;               // cos / sin(theta + pi/2)
+    double xf, yf;               // position shifted forward by perception_fwd_delta
+    unsigned long long rocks;    // candidate rocks whose disc can reach the window
+    int e, hx, hy, hr2;          // environment; anthill centre and radius^2
+    int pad[2];
+};
+
+// one conditional add or subtract wraps a sample coordinate onto the torus (np.mod on ints, RL_api.py:118-119) when
+// the window reaches less than one map size past the border: of v, v + n, v - n the one in [0, n) is the smallest as
+// an unsigned number
+__device__ __forceinline__ int wrap1(int v, int n) {
+    return (int)min(min((unsigned)v, (unsigned)(v + n)), (unsigned)(v - n));
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2 (2^-22 relative); arguments here are in [-15, 0]
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// value of a pheromone field that is neither zero nor a live boxed deposit outside walls (rare): kept out of line
+__device__ __noinline__ float phero_obs_slow(const Params &p, const uint8_t *rp, int k, uint32_t now, uint32_t now_abs) {
+    const double inv_max = 1.0 / p.phero_max_val;
+    return (float)(phero_value(p, rp, k, now, now_abs) * inv_max);
+}
+
+// exact rock test of one sample cell against the candidate rocks (RL_api.py:132-135, strict <)
+__device__ __noinline__ float rock_channel(const Params &p, int e, unsigned long long rm, int ix, int iy) {
+    const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+    const double *rr = p.rock_rad + (int64_t)e * p.R;
+    while (rm) {
+        const int r = __ffsll((long long)rm) - 1;
+        rm &= rm - 1;
+        const double ddx = (double)ix - rc[2 * r], ddy = (double)iy - rc[2 * r + 1];
+        if (sqrt(ddx * ddx + ddy * ddy) < rr[r]) return 1.f;
+    }
+    return 0.f;
+}
+
+template <int LAYOUT, bool REC16, int S>
+#ifndef ANTS_ROWS_OCC
+#define ANTS_ROWS_OCC 5
+#endif
+#ifndef ANTS_ROWS_UNR
+#define ANTS_ROWS_UNR 7
+#endif
+__global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
+k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
+                double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
+                uint32_t now, uint32_t now_abs, int dbg) {
+    static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
+    static_assert(kRowsGroup * S <= 32, "a chunk's rows must fit one warp");
+    constexpr int S2 = S * S, C = (LAYOUT == 2) ? 7 : 6, SC = S2 * C;
+    constexpr int G = kRowsGroup, ROWS = G * S, TILE = G * SC;       // TILE * 4 bytes is a multiple of 16
+    constexpr int NW = kRowsThreads / 32;
+    constexpr int UNR = REC16 ? (S < ANTS_ROWS_UNR ? S : ANTS_ROWS_UNR) : (S + 1) / 2;                      // record loads in flight per lane
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s_obs = reinterpret_cast<float *>(smem_raw);               // [NW][TILE]
+    RowPrep *prep = reinterpret_cast<RowPrep *>(s_obs + NW * TILE);   // [threads]
+    uint8_t *s_rowcnt = reinterpret_cast<uint8_t *>(prep + kRowsThreads);   // [threads][S]
+
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kRowsThreads;
+    const bool explore_on = p.explore_on != 0;
+
+    // ---- phase A (thread per ant): frame, reward terms that do not need the exploration count, small outputs
+    double r_other = 0.0, r_mult = 1.0;
+    {
+        const int64_t i = base + tid;
+        if (i < p.EN) {
+            const int e = (int)(i / p.N);
+            const double x = p.x[i], y = p.y[i], th = p.theta[i], hold = p.holding[i];
+            double s0, c0, st, ct;
+            sincos(th, &s0, &c0);
+            sincos(th + 3.141592653589793 * 0.5, &st, &ct);                    // RL_api.py:101,107-108
+            RowPrep q;
+            q.ct = ct; q.st = st;
+            q.xf = x; q.yf = y;
+            if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // :103-104
+            q.e = e;
+            const int32_t *hl = p.hill + 4 * e;
+            q.hx = hl[0]; q.hy = hl[1]; q.hr2 = hl[3];
+            const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
+            const double d = hold - hprev;
+            if (p.reward_kind == 0) {                                          // All_Rewards, reward_custom.py:79-106
+                const double r_food = d < 0.0 ? 0.0 : d;
+                const double r_hill = d < 0.0 ? 1.0 : 0.0;
+                const double ddx = x - (double)q.hx, ddy = y - (double)q.hy;
+                const double nd = sqrt(ddx * ddx + ddy * ddy);
+                const double heading = (p.rw_prev_dist[i] > nd && hold > 0.0) ? 0.1 : 0.0;
+                p.rw_prev_dist[i] = nd;
+                r_other = r_food * p.f_food + r_hill * p.f_anthill + heading * p.f_heading;
+                r_mult = (hold == 0.0) ? p.f_explore : p.f_explore_hold;
+                p.rw_holding_prev[i] = hold;
+            } else if (p.reward_kind == 2) {                                   // Food_Reward, :37-40
+                r_other = d < 0.0 ? 10.0 : d;
+                p.rw_holding_prev[i] = hold;
+            }
+            unsigned long long rm = 0ull;
+            if (LAYOUT == 2) {
+                // grid candidates, narrowed to the rocks whose disc can reach the window: a sample lies within
+                // radius*DELTA*sqrt(2) + 0.5 (rounding) of (xf, yf) on the torus
+                rm = rock_candidates(p, e, q.xf, q.yf);
+                if (rm) {
+                    const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+                    const double *rr = p.rock_rad + (int64_t)e * p.R;
+                    const double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.0;
+                    unsigned long long keep = 0ull, it = rm;
+                    while (it) {
+                        const int r = __ffsll((long long)it) - 1;
+                        it &= it - 1;
+                        double dx = fabs(q.xf - rc[2 * r]), dy = fabs(q.yf - rc[2 * r + 1]);
+                        dx = fmin(dx, fabs((double)p.W - dx));
+                        dy = fmin(dy, fabs((double)p.H - dy));
+                        const double L = rr[r] + reach;
+                        if (dx < L && dy < L) keep |= 1ull << r;
+                    }
+                    rm = keep;
+                }
+            }
+            q.rocks = rm;
+            {   // can the window touch the anthill disc?  (torus distance, same reach as for the rocks)
+                const double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.0 + (double)hl[2];
+                double dx = fabs(q.xf - (double)q.hx), dy = fabs(q.yf - (double)q.hy);
+                dx = fmin(dx, fabs((double)p.W - dx));
+                dy = fmin(dy, fabs((double)p.H - dy));
+                q.pad[0] = (rm != 0ull || (dx < reach && dy < reach)) ? 1 : 0;
+                q.pad[1] = 0;
+            }
+            prep[tid] = q;
+            agent_state[2 * i] = (float)hold;                                  // RL_api.py:160-162
+            agent_state[2 * i + 1] = (float)p.seed[i];
+            if (state_out != nullptr) {                                        // RL_api.py:155-158
+                float *so = state_out + i * (2 + p.P);
+                so[0] = (float)p.mandibles[i];
+                so[1] = (float)hold;
+                for (int k = 0; k < p.P; ++k) so[2 + k] = p.act[(int64_t)k * p.EN + i] > 0.0 ? 1.f : 0.f;
+            }
+        }
+    }
+    __syncwarp();        // a warp only reads the prep records of its own 32 ants
+
+    // ---- phase B: lane = (ant of the chunk, window row), loop over the row's columns
+    const int warp = tid >> 5, lane = tid & 31;
+    const int la = lane / S, li = lane - la * S;
+    const bool lane_on = lane < ROWS;
+    const double offY = p.off_c[lane_on ? li : 0];
+    uint32_t mrow = p.mask_rows[lane_on ? li : 0];
+    const int W = p.W, H = p.H;
+    const int nby64 = p.nby << 6;
+    const uint32_t tab_len = (uint32_t)p.tab_len;
+    const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
+    const bool any_plain = !p.lazy || *p.plain_flag != 0u;          // plain (non-boxed) pheromone values may exist
+    // boxed deposit b = box | t: (box | now) - b = now - t = age; zero and plain values give an "age" >= 2^22
+    const uint32_t nowb = REC16 ? box32(now_abs) : (now_abs & kBoxMask);
+    const uint32_t ogs = obs_gen << 8;
+    float *wobs = s_obs + warp * TILE;
+    // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
+    uint32_t orow_s = (uint32_t)__cvta_generic_to_shared(wobs + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
+    asm volatile("" : "+r"(orow_s), "+r"(mrow));                    // keep them in registers (no rematerialisation)
+    // masked samples read -1 in every channel (RL_api.py:147-148) and their tile slots are never written again
+    if (lane_on) {
+#pragma unroll
+        for (int j = 0; j < S; ++j)
+            if (!((mrow >> j) & 1u))
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + c) * 4)), "f"(-1.f) : "memory");
+    }
+
+    for (int g = 0; g < 32; g += G) {
+        const int64_t i0 = base + warp * 32 + g;
+        if (i0 >= p.EN) break;
+        const int n_in = (p.EN - i0 < G) ? (int)(p.EN - i0) : G;
+        // the previous chunk's bulk store must have finished reading the staging tile
+        if (lane == 0) bulk_store_wait_read();
+        __syncwarp();
+        if (lane_on && la < n_in) {
+            const RowPrep &q = prep[warp * 32 + g + la];
+            const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
+            const int e = q.e;
+            const uint32_t special = (uint32_t)q.pad[0];               // 1 = the window may touch the anthill or a rock
+            const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << (REC16 ? 4 : 5));
+            const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
+            int cnt = 0;
+#pragma unroll
+            for (int j0 = 0; j0 < S; j0 += UNR) {
+                uint4 lo[UNR], hi[UNR];
+                uint32_t cell[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = j0 + u;
+                    if (j < S) {
+                        // sample cell, RL_api.py:110-119: round_half_even(rot(theta + pi/2) * offset + xy_f) mod (W, H)
+                        const double X = p.off_c[j];
+                        const double rx = ct * X - stY;
+                        const double ry = st * X + ctY;
+                        int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
+                        ix = wrap1(ix, W); iy = wrap1(iy, H);
+                        // cidx(): 8 x 8 blocks of 64 records
+                        cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
+                        const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
+                        lo[u] = *reinterpret_cast<const uint4 *>(rp);
+                        if (!REC16) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = j0 + u;
+                    if (j < S) {
+                        uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << (REC16 ? 4 : 5));
+                        bool wl, occupied, fresh, seen_now;
+                        uint32_t age0, age1;
+                        float v5;                      // food as the f32 observation shows it
+                        if (REC16) {
+                            const uint32_t pk = lo[u].w;
+                            occupied = (pk & 0xFFu) == occ_gen;
+                            wl = (pk & 0x8000u) != 0;
+                            fresh = (pk & 0x7F00u) == 0u;
+                            seen_now = (pk & 0x7F00u) == ogs;
+                            v5 = __uint_as_float(lo[u].z);
+                            age0 = nowb - lo[u].x; age1 = nowb - lo[u].y;
+                            if (explore_on && fresh && !(dbg & 2)) rp[13] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
+                        } else {
+                            occupied = (hi[u].z >> 16) == occ_gen;
+                            wl = (hi[u].w & 0xFFu) != 0;
+                            fresh = (hi[u].z & 0xFFFFu) == 0u;
+                            seen_now = (hi[u].z & 0xFFFFu) == obs_gen;
+                            v5 = (float)__hiloint2double((int)hi[u].y, (int)hi[u].x);
+                            // f64 fields: boxed <=> the high word carries the NaN box; the deposit step is the low word
+                            const bool bx0 = p.lazy && (lo[u].y & 0xFFF80000u) == 0x7FF80000u;
+                            const bool bx1 = p.lazy && (lo[u].w & 0xFFF80000u) == 0x7FF80000u;
+                            age0 = bx0 ? ((nowb - lo[u].x) & kBoxMask) : 0xFFFFFFFFu;
+                            age1 = bx1 ? ((nowb - lo[u].z) & kBoxMask) : 0xFFFFFFFFu;
+                            if (explore_on && fresh && !(dbg & 2)) *reinterpret_cast<uint16_t *>(rp + 24) = (uint16_t)obs_gen;
+                        }
+                        if (explore_on) cnt += (fresh || seen_now) ? 1 : 0;    // gather-before-scatter, Q7
+                        if ((mrow >> j) & 1u) {
+                            // pheromone channels, RL_api.py:124-125.  A saturated deposit of age k shows
+                            // (float)(max_val * keep^k / max_val) = keep^k (the reference's per-step rounding moves it by
+                            // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
+                            // cut is the exact table length; inside a wall only a deposit of this very update shows.
+                            const uint32_t lim = wl ? 1u : tab_len;
+                            float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
+                            float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                            if (any_plain) {           // plain values (bool activations, imports, eager modes): out of line
+                                const bool pl0 = REC16 ? (lo[u].x != 0u && !is_boxed32(lo[u].x))
+                                                       : ((lo[u].x | lo[u].y) != 0u && age0 == 0xFFFFFFFFu);
+                                const bool pl1 = REC16 ? (lo[u].y != 0u && !is_boxed32(lo[u].y))
+                                                       : ((lo[u].z | lo[u].w) != 0u && age1 == 0xFFFFFFFFu);
+                                if (pl0) v1 = phero_obs_slow(p, rp, 0, now, now_abs);
+                                if (pl1) v2 = phero_obs_slow(p, rp, 1, now, now_abs);
+                            }
+                            float v3 = 0.f, v6 = 0.f;
+                            if (special) {             // anthill (:130-131, anthill.py:31-33) and rocks (:132-135)
+                                const double X = p.off_c[j];               // same arithmetic as above, from the
+                                const double rx = q.ct * X - q.st * offY;  // shared-memory frame (rare path)
+                                const double ry = q.st * X + q.ct * offY;
+                                int ix = __double2int_rn(rx + q.xf), iy = __double2int_rn(ry + q.yf);
+                                ix = wrap1(ix, W); iy = wrap1(iy, H);
+                                const int hdx = q.hx - ix, hdy = q.hy - iy;
+                                v3 = (hdx * hdx + hdy * hdy <= q.hr2) ? 1.f : 0.f;
+                                if (LAYOUT == 2 && q.rocks) v6 = rock_channel(p, e, q.rocks, ix, iy);
+                            }
+                            const float v0 = occupied ? 1.f : 0.f;                               // :136-142
+                            const float v4 = wl ? 1.f : 0.f;                                     // :128-129
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 0) * 4)), "f"(v0) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 1) * 4)), "f"(v1) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 2) * 4)), "f"(v2) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 3) * 4)), "f"(v3) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 4) * 4)), "f"(v4) : "memory");
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 5) * 4)), "f"(v5) : "memory");
+                            if (LAYOUT == 2)
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 6) * 4)), "f"(v6) : "memory");
+                        }
+                    }
+                }
+            }
+            s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
+        }
+        // flush the staged (n_in x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
+        float *dst = obs + i0 * SC;
+        const uint32_t bytes = (uint32_t)(n_in * SC * 4);
+        if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(dbg & 1)) bulk_store_s2g(dst, wobs, bytes);
+        } else {
+            __syncwarp();
+            for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+
+    // ---- phase C: reward epilogue, thread per ant (this warp's own ants)
+    {
+        const int64_t i = base + tid;
+        if (i < p.EN) {
+            int count = 0;
+            if (explore_on) {
+#pragma unroll
+                for (int k = 0; k < S; ++k) count += s_rowcnt[tid * S + k];
+            }
+            double reward;
+            if (p.reward_kind == 1) {
+                reward = (double)count / 10.0;                                 // reward_custom.py:19
+            } else if (p.reward_kind == 0) {
+                reward = 0.0;
+                if (explore_on) reward += ((double)count / 10.0) * r_mult;     // :89-94
+                reward += r_other;                                             // :106
+            } else {
+                reward = r_other;
+            }
+            p.rewards[i] = reward;
+            if (reward_out != nullptr) reward_out[i] = reward;
+            if (is_step) {                                                     // ants.py:119-121 (Q16)
+                int rs = p.reward_state[i];
+                rs += ((reward - p.reward_threshold) > 0.0) ? 255 : 0;
+                p.reward_state[i] = (uint8_t)(rs > 255 ? 255 : rs);
+            }
+        }
+    }
+    if (lane == 0) bulk_store_wait_read();   // smem must stay valid until the last bulk store has read it
+}
+
+}  // namespace ants
