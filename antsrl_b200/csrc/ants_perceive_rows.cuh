@@ -22,12 +22,14 @@ namespace ants {
 constexpr int kRowsThreads = 128;
 constexpr int kRowsGroup = 4;
 
-struct RowPrep {                 // 64 bytes per ant, shared memory (phase A -> phase B)
+struct RowPrep {                 // 96 bytes per ant, shared memory (phase A -> phase B)
     double ct, st;               // cos / sin(theta + pi/2)
     double xf, yf;               // position shifted forward by perception_fwd_delta
-    unsigned long long rocks;    // candidate rocks whose disc can reach the window
+    unsigned long long rocks;    // further candidate rocks (beyond the first) whose disc can reach the window
     int e, hx, hy, hr2;          // environment; anthill centre and radius^2
-    int pad[2];
+    int flags, pad;              // 1 = the window may touch the anthill, 2 = a rock may reach it, 4 = more than one
+    double rcx, rcy, rrad;       // the first candidate rock
+    double pad2;
 };
 
 // one conditional add or subtract wraps a sample coordinate onto the torus (np.mod on ints, RL_api.py:118-119) when
@@ -142,14 +144,23 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     rm = keep;
                 }
             }
-            q.rocks = rm;
             {   // can the window touch the anthill disc?  (torus distance, same reach as for the rocks)
                 const double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.0 + (double)hl[2];
                 double dx = fabs(q.xf - (double)q.hx), dy = fabs(q.yf - (double)q.hy);
                 dx = fmin(dx, fabs((double)p.W - dx));
                 dy = fmin(dy, fabs((double)p.H - dy));
-                q.pad[0] = (rm != 0ull || (dx < reach && dy < reach)) ? 1 : 0;
-                q.pad[1] = 0;
+                q.flags = (dx < reach && dy < reach) ? 1 : 0;
+                q.pad = 0; q.pad2 = 0.0;
+                q.rcx = q.rcy = 0.0; q.rrad = -1.0;
+                if (rm) {
+                    const int r = __ffsll((long long)rm) - 1;
+                    rm &= rm - 1;
+                    q.rcx = p.rock_c[((int64_t)e * p.R + r) * 2];
+                    q.rcy = p.rock_c[((int64_t)e * p.R + r) * 2 + 1];
+                    q.rrad = p.rock_rad[(int64_t)e * p.R + r];
+                    q.flags |= rm ? 6 : 2;
+                }
+                q.rocks = rm;
             }
             prep[tid] = q;
             agent_state[2 * i] = (float)hold;                                  // RL_api.py:160-162
@@ -196,16 +207,22 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         const int64_t i0 = base + warp * 32 + g;
         if (i0 >= p.EN) break;
         const int n_in = (p.EN - i0 < G) ? (int)(p.EN - i0) : G;
-        // the previous chunk's bulk store must have finished reading the staging tile
-        if (lane == 0) bulk_store_wait_read();
-        __syncwarp();
+        // the previous chunk's bulk store must have finished reading the staging tile before it is written again:
+        // with a single batch of loads (compact records) that wait sits behind the loads, where it costs nothing
+        constexpr bool kLateWait = (UNR >= S);
+        const uint32_t amask = (n_in * S >= 32) ? 0xffffffffu : ((1u << (n_in * S)) - 1u);   // the lanes with a row
+        if (!kLateWait) {
+            if (lane == 0) bulk_store_wait_read();
+            __syncwarp();
+        }
         if (lane_on && la < n_in) {
             const RowPrep &q = prep[warp * 32 + g + la];
             const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
             const int e = q.e;
-            const uint32_t special = (uint32_t)q.pad[0];               // 1 = the window may touch the anthill or a rock
             const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << (REC16 ? 4 : 5));
             const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
+            const int flags = q.flags;
+            uint32_t hbits = 0u;                                       // bit j: anthill, bit 8 + j: rock, at column j
             int cnt = 0;
 #pragma unroll
             for (int j0 = 0; j0 < S; j0 += UNR) {
@@ -221,12 +238,31 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         const double ry = st * X + ctY;
                         int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
                         ix = wrap1(ix, W); iy = wrap1(iy, H);
+                        if (flags) {                   // few ants are near the anthill or a rock
+                            if (flags & 1) {           // anthill.py:31-33 on integers (RL_api.py:130-131)
+                                const int hdx = q.hx - ix, hdy = q.hy - iy;
+                                hbits |= (hdx * hdx + hdy * hdy <= q.hr2 ? 1u : 0u) << j;
+                            }
+                            if (LAYOUT == 2 && (flags & 2)) {          // RL_api.py:132-135, strict <
+                                // sqrt(d2) < r decided on the squares unless d2 is within 1e-12 of r^2
+                                const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
+                                const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
+                                bool hit = d2 < r2 * 0.999999999999;
+                                if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
+                                if (!hit && (flags & 4)) hit = rock_channel(p, e, q.rocks, ix, iy) != 0.f;
+                                hbits |= (hit ? 1u : 0u) << (8 + j);
+                            }
+                        }
                         // cidx(): 8 x 8 blocks of 64 records
                         cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
                         const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
                         lo[u] = *reinterpret_cast<const uint4 *>(rp);
                         if (!REC16) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
                     }
+                }
+                if (kLateWait) {
+                    if (lane == 0) bulk_store_wait_read();
+                    __syncwarp(amask);
                 }
 #pragma unroll
                 for (int u = 0; u < UNR; ++u) {
@@ -275,17 +311,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                                 if (pl0) v1 = phero_obs_slow(p, rp, 0, now, now_abs);
                                 if (pl1) v2 = phero_obs_slow(p, rp, 1, now, now_abs);
                             }
-                            float v3 = 0.f, v6 = 0.f;
-                            if (special) {             // anthill (:130-131, anthill.py:31-33) and rocks (:132-135)
-                                const double X = p.off_c[j];               // same arithmetic as above, from the
-                                const double rx = q.ct * X - q.st * offY;  // shared-memory frame (rare path)
-                                const double ry = q.st * X + q.ct * offY;
-                                int ix = __double2int_rn(rx + q.xf), iy = __double2int_rn(ry + q.yf);
-                                ix = wrap1(ix, W); iy = wrap1(iy, H);
-                                const int hdx = q.hx - ix, hdy = q.hy - iy;
-                                v3 = (hdx * hdx + hdy * hdy <= q.hr2) ? 1.f : 0.f;
-                                if (LAYOUT == 2 && q.rocks) v6 = rock_channel(p, e, q.rocks, ix, iy);
-                            }
+                            const float v3 = ((hbits >> j) & 1u) ? 1.f : 0.f;
+                            const float v6 = ((hbits >> (8 + j)) & 1u) ? 1.f : 0.f;
                             const float v0 = occupied ? 1.f : 0.f;                               // :136-142
                             const float v4 = wl ? 1.f : 0.f;                                     // :128-129
                             asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 0) * 4)), "f"(v0) : "memory");
