@@ -295,7 +295,7 @@ int do_update(AntsBatch *b, const double *d_noise) {
     if (p.R > 0) {
         {
             LaunchScope ls(b, F_ROCKS);
-            ants::k_rocks_pushed<<<p.E, 256, 0, b->stream>>>(p);
+            ants::k_rocks_pushed<<<(unsigned)cdiv((int64_t)p.E * p.R, 8), 256, 0, b->stream>>>(p);
         }
         TRY(check_launch("k_rocks_pushed"));
         {
@@ -513,6 +513,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.rock_c, (int64_t)p.E * p.R * 2)); A(dev_alloc(b, &p.rock_rad, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.rock_w, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.rock_grid, (int64_t)p.E * p.grid_w * p.grid_h));
+    A(dev_alloc(b, &p.rock_touch, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.food_delta, EN, false));
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
     A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));

@@ -68,6 +68,7 @@ struct Params {
     double *hill_food;                     // [E]
     double *rock_c, *rock_rad, *rock_w;    // [E][R][2], [E][R], [E][R]
     unsigned long long *rock_grid;         // [E][grid_w][grid_h] bitmask of rocks near each 16x16 block
+    uint32_t *rock_touch;                  // [E][R] bit c: an ant of ant-chunk c touches the rock this update
     const double *samp_off;                // [S] = (k - r) * DELTA  (RL_api.py:92-93)
     const uint8_t *mask;                   // [S2]
     double off_c[16];                      // the same offsets in the kernel-parameter constant bank
@@ -89,6 +90,15 @@ __device__ __forceinline__ double pymod(double a, double b) {      // np.mod on 
         r = copysign(0.0, b);
     }
     return r;
+}
+// the same value for any a; straight-line for -b < a < 2b (b > 0), which is every call of the step loop: positions
+// move by at most a few cells per step and headings by less than a turn.  fmod is exact, so a - b (Sterbenz) and the
+// single rounding of a + b are what npy_remainder produces.
+__device__ __forceinline__ double pymod_near(double a, double b) {
+    if (a >= 0.0 && a < b) return a + 0.0;              // (-0.0 -> +0.0 like copysign(0, b))
+    if (a >= b && a < b + b) return a - b;
+    if (a < 0.0 && a > -b) return a + b;
+    return pymod(a, b);
 }
 __device__ __forceinline__ int imod(int a, int n) {                // np.mod on ints
     int r = a % n;
@@ -267,10 +277,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 // Candidate rocks of a point: every rock whose (radius + reach) box overlaps the point's grid cell was OR-ed
 // into that cell by rock_grid_mark, so one 8-byte load replaces a loop over all rocks.
 __device__ __forceinline__ unsigned long long rock_candidates(const Params &p, int e, double x, double y) {
-    int gx = cell_of(pymod(x, (double)p.W), p.W) >> kGridShift;
-    int gy = cell_of(pymod(y, (double)p.H), p.H) >> kGridShift;
+    int gx = cell_of(pymod_near(x, (double)p.W), p.W) >> kGridShift;
+    int gy = cell_of(pymod_near(y, (double)p.H), p.H) >> kGridShift;
     return p.rock_grid[((int64_t)e * p.grid_w + gx) * p.grid_h + gy];
 }
+template <bool SET = true>
 __device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad) {
     const double L = rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
     const double step = (double)(1 << kGridShift);
@@ -283,7 +294,7 @@ __device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, do
         for (double oy = -L;; oy += step) {
             if (oy > L) oy = L;
             int gy = cell_of(pymod(cy + oy, (double)p.H), p.H) >> kGridShift;
-            atomicOr(g + gx * p.grid_h + gy, bit);
+            if (SET) atomicOr(g + gx * p.grid_h + gy, bit); else atomicAnd(g + gx * p.grid_h + gy, ~bit);
             if (oy >= L) break;
         }
         if (ox >= L) break;
@@ -334,13 +345,13 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
         p.act[i] = (v == 1) ? act_on : 0.0;
         p.act[p.EN + i] = (v != 0 && v != 1) ? act_on : 0.0;
     }
-    if (rot != nullptr) th = pymod(th + (double)rot[i] * p.max_rot_speed, 6.283185307179586);   // ants.py:62-67
+    if (rot != nullptr) th = pymod_near(th + (double)rot[i] * p.max_rot_speed, 6.283185307179586);   // ants.py:62-67
     double fwd = (1.0 * p.max_speed) * (1.0 - hold * p.csr);                    // RL_api.py:194
     if (fwd < 0.0) fwd *= p.bsr;                                                // RL_api.py:195
     double s, c;
     sincos(th, &s, &c);
-    x = pymod(x + c * fwd, (double)p.W);                                        // ants.py:69-80
-    y = pymod(y + s * fwd, (double)p.H);
+    x = pymod_near(x + c * fwd, (double)p.W);                                   // ants.py:69-80
+    y = pymod_near(y + s * fwd, (double)p.H);
     p.x[i] = x; p.y[i] = y; p.theta[i] = th;
     uint8_t *orec = rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H)));
     st_occ(p, orec, occ_gen);
@@ -727,6 +738,23 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
         th += u - 0.5;                                                         // not re-wrapped (Q3)
         p.x[i] = x; p.y[i] = y; p.theta[i] = th;
     }
+    if (p.R > 0) {
+        // CircleObstacles.update, first half (circle_obstacles.py:35-37): which rocks does this ant push?  The rocks
+        // registered near it in the rock grid (current centres) are tested exactly; a hit sets the bit of the ant's
+        // chunk in rock_touch[e][rock] for k_rocks_pushed.
+        unsigned long long rm = rock_candidates(p, e, x, y);
+        if (rm) {
+            const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+            const double *rr = p.rock_rad + (int64_t)e * p.R;
+            const int G = ((p.N + 31) / 32 + 31) / 32 * 32;  // ants per chunk: a multiple of 32, at most 32 chunks
+            while (rm) {
+                int r = __ffsll((long long)rm) - 1;
+                rm &= rm - 1;
+                double vx = rc[2 * r] - x, vy = rc[2 * r + 1] - y;
+                if (!(sqrt(vx * vx + vy * vy) > rr[r])) atomicOr(p.rock_touch + (int64_t)e * p.R + r, 1u << (a / G));
+            }
+        }
+    }
     if (finish) {
         p.prev_x[i] = x; p.prev_y[i] = y; p.prev_theta[i] = th;
         atomicMax(p.owner + (int64_t)e * p.plane + cidx(p, cell_of(x, p.W), cell_of(y, p.H)), owner_stamp | (uint32_t)a);
@@ -734,76 +762,57 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
     }
 }
 
-// CircleObstacles.update, first half (circle_obstacles.py:35-40): ants push rocks.  One block per env.
-//   phase 1 (thread per ant): every ant looks up the rocks registered near it in the rock grid (built from the
-//            current centres) and, for each rock it really touches, sets the bit of its ant-chunk in touch[rock].
-//   phase 2 (warp per rock): the warp walks only the touched chunks, in ant order, adding the pushes with an
-//            ordered ballot loop -- the same summation order as np.sum(axis=0); untouched ants contribute exact 0.
-//   phase 3: the rock grid is rebuilt from the new centres.
+// CircleObstacles.update, first half (circle_obstacles.py:35-40): ants push rocks.  One warp per (env, rock); a rock
+// no ant touches (rock_touch == 0, set by k_collide) costs one load.  For a touched rock the warp walks only the
+// touched ant-chunks, in ant order, adding the pushes with an ordered ballot loop -- the same summation order as
+// np.sum(axis=0); untouched ants contribute exact 0.  Then the rock's entries in the rock grid move with it.
 __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
-    __shared__ uint32_t s_touch[64];                     // ANTS_MAX_ROCKS
-    const int e = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (pair >= (int64_t)p.E * p.R) return;
+    uint32_t tm = p.rock_touch[pair];
+    if (tm == 0u) return;
+    const int e = (int)(pair / p.R), r = (int)(pair - (int64_t)e * p.R);
     const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
     double *rc = p.rock_c + (int64_t)e * p.R * 2;
-    const double *rr = p.rock_rad + (int64_t)e * p.R;
-    const int G = ((p.N + 31) / 32 + 31) / 32 * 32;      // ants per chunk: a multiple of 32, at most 32 chunks
-    if (threadIdx.x < 64) s_touch[threadIdx.x] = 0u;
-    __syncthreads();
-    for (int a = threadIdx.x; a < p.N; a += blockDim.x) {
-        const double x = xs[a], y = ys[a];
-        unsigned long long rm = rock_candidates(p, e, x, y);
-        while (rm) {
-            int r = __ffsll((long long)rm) - 1;
-            rm &= rm - 1;
-            double vx = rc[2 * r] - x, vy = rc[2 * r + 1] - y;
-            if (!(sqrt(vx * vx + vy * vy) > rr[r])) atomicOr(&s_touch[r], 1u << (a / G));
-        }
-    }
-    __syncthreads();
-    for (int r = warp; r < p.R; r += nwarp) {
-        const double cx = rc[2 * r], cy = rc[2 * r + 1], rad = rr[r];
-        double sx = 0.0, sy = 0.0;
-        uint32_t tm = s_touch[r];
-        while (tm) {
-            const int g = __ffs(tm) - 1;
-            tm &= tm - 1;
-            const int a_end = min((g + 1) * G, p.N);
-            for (int a0 = g * G; a0 < a_end; a0 += 32) {
-                int a = a0 + lane;
-                double px = 0.0, py = 0.0;
-                bool hit = false;
-                if (a < a_end) {
-                    double vx = cx - xs[a], vy = cy - ys[a];
-                    double d = sqrt(vx * vx + vy * vy);
-                    if (!(d > rad)) {
-                        double fac = 1.0 - rad / (d + 0.001);
-                        px = vx * fac; py = vy * fac; hit = true;
-                    }
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    int l = __ffs(m) - 1;
-                    m &= m - 1;
-                    sx += __shfl_sync(0xffffffffu, px, l);
-                    sy += __shfl_sync(0xffffffffu, py, l);
+    const int G = ((p.N + 31) / 32 + 31) / 32 * 32;
+    const double cx = rc[2 * r], cy = rc[2 * r + 1], rad = p.rock_rad[pair];
+    double sx = 0.0, sy = 0.0;
+    while (tm) {
+        const int g = __ffs(tm) - 1;
+        tm &= tm - 1;
+        const int a_end = min((g + 1) * G, p.N);
+        for (int a0 = g * G; a0 < a_end; a0 += 32) {
+            int a = a0 + lane;
+            double px = 0.0, py = 0.0;
+            bool hit = false;
+            if (a < a_end) {
+                double vx = cx - xs[a], vy = cy - ys[a];
+                double d = sqrt(vx * vx + vy * vy);
+                if (!(d > rad)) {
+                    double fac = 1.0 - rad / (d + 0.001);
+                    px = vx * fac; py = vy * fac; hit = true;
                 }
             }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            double wt = p.rock_w[(int64_t)e * p.R + r];
-            rc[2 * r] = cx - sx / wt;
-            rc[2 * r + 1] = cy - sy / wt;
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                int l = __ffs(m) - 1;
+                m &= m - 1;
+                sx += __shfl_sync(0xffffffffu, px, l);
+                sy += __shfl_sync(0xffffffffu, py, l);
+            }
         }
     }
-    __syncthreads();
-    {   // rebuild the rock grid from the new centres
-        const int gcells = p.grid_w * p.grid_h;
-        unsigned long long *g = p.rock_grid + (int64_t)e * gcells;
-        for (int k = threadIdx.x; k < gcells; k += blockDim.x) g[k] = 0ull;
-        __syncthreads();
-        for (int r = threadIdx.x; r < p.R; r += blockDim.x) rock_grid_mark(p, e, r, rc[2 * r], rc[2 * r + 1], rr[r]);
+    if (lane == 0) {
+        const double wt = p.rock_w[pair];
+        const double nx = cx - sx / wt, ny = cy - sy / wt;
+        rc[2 * r] = nx;
+        rc[2 * r + 1] = ny;
+        p.rock_touch[pair] = 0u;
+        if (nx != cx || ny != cy) {                    // the grid entries follow the rock
+            rock_grid_mark<false>(p, e, r, cx, cy, rad);
+            rock_grid_mark<true>(p, e, r, nx, ny, rad);
+        }
     }
 }
 
@@ -831,8 +840,8 @@ __global__ void __launch_bounds__(256) k_rocks_push_ants(Params p, uint32_t owne
             sx += vx * fac; sy += vy * fac;
         }
     }
-    x = pymod(x + sx, (double)p.W);                                            // translate_ants -> warp_xy
-    y = pymod(y + sy, (double)p.H);
+    x = pymod_near(x + sx, (double)p.W);                                       // translate_ants -> warp_xy
+    y = pymod_near(y + sy, (double)p.H);
     p.x[i] = x; p.y[i] = y;
     p.prev_x[i] = x; p.prev_y[i] = y; p.prev_theta[i] = p.theta[i];
     atomicMax(p.owner + (int64_t)e * p.plane + cidx(p, cell_of(x, p.W), cell_of(y, p.H)), owner_stamp | (uint32_t)a);
