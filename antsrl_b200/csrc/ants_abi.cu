@@ -209,8 +209,7 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
 #define ANTS_ROWS(L, R16)                                                                                   \
     ants::k_perceive_rows<L, R16, 7><<<rblocks, ants::kRowsThreads, b->rows_smem, b->stream>>>(             \
         p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias,                            \
-        b->lazy_now, b->lazy_abs, dbg)
-            static int dbg = getenv("ANTS_DBG") ? atoi(getenv("ANTS_DBG")) : 0;
+        b->lazy_now, b->lazy_abs)
             if (p.rec16) { if (layout == 2) ANTS_ROWS(2, true); else ANTS_ROWS(1, true); }
             else { if (layout == 2) ANTS_ROWS(2, false); else ANTS_ROWS(1, false); }
 #undef ANTS_ROWS

@@ -44,6 +44,23 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2 (2^-22 rela
     return y;
 }
 
+// 16-byte record load; ANTS_LD_L2_128 asks L2 to fetch the whole 128-byte line (one x-row of an 8x8 block) on a miss
+__device__ __forceinline__ uint4 ld_record16(const uint8_t *rp) {
+#ifdef ANTS_LD_L2_128
+    uint4 v;
+    asm volatile("ld.global.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rp));
+    return v;
+#elif defined(ANTS_LD_L2_64)
+    uint4 v;
+    asm volatile("ld.global.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rp));
+    return v;
+#elif defined(ANTS_LD_NC)
+    return __ldg(reinterpret_cast<const uint4 *>(rp));
+#else
+    return *reinterpret_cast<const uint4 *>(rp);
+#endif
+}
+
 // value of a pheromone field that is neither zero nor a live boxed deposit outside walls (rare): kept out of line
 __device__ __noinline__ float phero_obs_slow(const Params &p, const uint8_t *rp, int k, uint32_t now, uint32_t now_abs) {
     const double inv_max = 1.0 / p.phero_max_val;
@@ -73,7 +90,7 @@ template <int LAYOUT, bool REC16, int S>
 __global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
 k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
                 double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
-                uint32_t now, uint32_t now_abs, int dbg) {
+                uint32_t now, uint32_t now_abs) {
     static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
     static_assert(kRowsGroup * S <= 32, "a chunk's rows must fit one warp");
     constexpr int S2 = S * S, C = (LAYOUT == 2) ? 7 : 6, SC = S2 * C;
@@ -256,7 +273,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         // cidx(): 8 x 8 blocks of 64 records
                         cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
                         const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
-                        lo[u] = *reinterpret_cast<const uint4 *>(rp);
+                        lo[u] = ld_record16(rp);
                         if (!REC16) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
                     }
                 }
@@ -280,7 +297,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                             seen_now = (pk & 0x7F00u) == ogs;
                             v5 = __uint_as_float(lo[u].z);
                             age0 = nowb - lo[u].x; age1 = nowb - lo[u].y;
-                            if (explore_on && fresh && !(dbg & 2)) rp[13] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
+                            if (explore_on && fresh) rp[13] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
                         } else {
                             occupied = (hi[u].z >> 16) == occ_gen;
                             wl = (hi[u].w & 0xFFu) != 0;
@@ -292,7 +309,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                             const bool bx1 = p.lazy && (lo[u].w & 0xFFF80000u) == 0x7FF80000u;
                             age0 = bx0 ? ((nowb - lo[u].x) & kBoxMask) : 0xFFFFFFFFu;
                             age1 = bx1 ? ((nowb - lo[u].z) & kBoxMask) : 0xFFFFFFFFu;
-                            if (explore_on && fresh && !(dbg & 2)) *reinterpret_cast<uint16_t *>(rp + 24) = (uint16_t)obs_gen;
+                            if (explore_on && fresh) *reinterpret_cast<uint16_t *>(rp + 24) = (uint16_t)obs_gen;
                         }
                         if (explore_on) cnt += (fresh || seen_now) ? 1 : 0;    // gather-before-scatter, Q7
                         if ((mrow >> j) & 1u) {
@@ -335,7 +352,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0 && !(dbg & 1)) bulk_store_s2g(dst, wobs, bytes);
+            if (lane == 0) bulk_store_s2g(dst, wobs, bytes);
         } else {
             __syncwarp();
             for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
