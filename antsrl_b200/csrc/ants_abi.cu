@@ -58,6 +58,8 @@ struct AntsBatch {
     uint32_t obs_gen = 0, occ_gen = 0, owner_phase = 0;
     int64_t timestep = 1;
     int rw_alias = 1, act_bool = 1, prev_synced = 1, needs_sweep = 1;
+    int wall_flags_valid = 0;       // wall_hit[] was written by the step that precedes this update
+    int absorb_par = 0;             // which absorb counter the steps append under
     uint32_t lazy_now = 0;          // updates since the last fold of plain values (lazy evaporation), small counter
     uint32_t lazy_abs = 0;          // updates since creation / the last unboxing fold (22 bits)
     AntsStats stats;
@@ -267,10 +269,11 @@ int do_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs,
     TRY(check_launch("k_step_move"));
     {
         LaunchScope ls(b, F_FOOD);
-        ants::k_food_commit<<<64, 128, 0, b->stream>>>(p, phase << 16);
+        ants::k_food_commit<<<64, 128, 0, b->stream>>>(p, phase << 16, b->absorb_par);
     }
     TRY(check_launch("k_food_commit"));
     b->prev_synced = 0;
+    b->wall_flags_valid = 1;
     TRY(launch_perceive(b, d_obs, d_as, nullptr, d_reward, 1));
     if (done) *done = (b->cfg.max_time == b->timestep) ? 1 : 0;   // RL_api.py:200 (Q15)
     b->stats.steps++;
@@ -287,7 +290,10 @@ int do_update(AntsBatch *b, const double *d_noise) {
     //    nothing the objects in between read.
     {
         LaunchScope ls(b, F_COLLIDE);
-        ants::k_collide<<<blocks, 256, 0, b->stream>>>(p, d_noise, step_id, phase << 16, p.R > 0 ? 0 : 1);
+        ants::k_collide<<<blocks, 256, 0, b->stream>>>(p, d_noise, step_id, phase << 16, p.R > 0 ? 0 : 1,
+                                                       b->wall_flags_valid, b->absorb_par);
+        b->absorb_par ^= 1;
+        b->wall_flags_valid = 0;
     }
     TRY(check_launch("k_collide"));
     // 3. CircleObstacles (order 0)
@@ -350,17 +356,14 @@ int do_update(AntsBatch *b, const double *d_noise) {
         }
         TRY(check_launch("k_deposit_commit"));
     }
-    // 7. Anthill (order 1000)
+    // 7. Anthill (order 1000): the queued cells were absorbed by the first blocks of k_collide; after an import one
+    //    sweep over the disc takes whatever the generator put there (Q10)
     if (b->needs_sweep) {
         LaunchScope ls(b, F_ABSORB);
         ants::k_absorb_sweep<<<p.E, 256, 0, b->stream>>>(p);
         b->needs_sweep = 0;
-        CK(cudaMemsetAsync(p.absorb_count, 0, sizeof(uint32_t), b->stream));
-    } else {
-        LaunchScope ls(b, F_ABSORB);
-        ants::k_absorb_list<<<1, 256, 0, b->stream>>>(p);
+        TRY(check_launch("absorb"));
     }
-    TRY(check_launch("absorb"));
     b->prev_synced = 1;
     b->stats.updates++;
     return ANTS_OK;
@@ -515,7 +518,8 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.rock_touch, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.food_delta, EN, false));
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 1));
-    A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 1));
+    A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 2));
+    A(dev_alloc(b, &p.wall_hit, EN));
     A(dev_alloc(b, &p.tile_counter, 1));
     A(dev_alloc(b, &p.plain_flag, 1));
 
@@ -742,7 +746,8 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         TRY(check_launch("k_rock_grid_build"));
     }
     CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(p.absorb_count, 0, sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(p.absorb_count, 0, 2 * sizeof(uint32_t), st));
+    b->wall_flags_valid = 0;
     b->owner_phase = 0;
     b->timestep = s->timestep > 0 ? s->timestep : 1;
     b->rw_alias = s->rw_alias ? 1 : 0;
@@ -939,7 +944,7 @@ int ants_get_stats(AntsBatch *b, AntsStats *out) {
     if (!b || !out) return fail(ANTS_E_ARG, "null argument");
     CK(cudaSetDevice(b->cfg.device));
     CK(cudaMemcpyAsync(b->h_counts, b->p.commit_count, 4, cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaMemcpyAsync(b->h_counts + 1, b->p.absorb_count, 4, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b->h_counts + 1, b->p.absorb_count + b->absorb_par, 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b->h_counts + 2, b->p.tile_counter, 8, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     b->stats.food_commits = b->h_counts[0];

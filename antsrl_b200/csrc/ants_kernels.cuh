@@ -76,7 +76,9 @@ struct Params {
     // scratch
     double *food_delta;                    // [E*N]
     uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food of a cell this step
-    uint32_t *absorb_list, *absorb_count;  // (env, cell) pairs of food lying inside the anthill disc
+    uint32_t *absorb_list, *absorb_count;  // (env, cell) pairs of food lying inside the anthill disc; absorb_count[2]:
+                                           // the step appends under one counter while the update zeroes the other
+    uint8_t *wall_hit;                     // [E*N] 1 = the ant stands in a wall cell after this step's move
     unsigned long long *tile_counter;      // tiles processed by the evaporation kernel
     uint32_t *plain_flag;                  // lazy mode: set once any plain (non-saturated) pheromone value is stored
 };
@@ -354,6 +356,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     y = pymod_near(y + s * fwd, (double)p.H);
     p.x[i] = x; p.y[i] = y; p.theta[i] = th;
     uint8_t *orec = rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H)));
+    p.wall_hit[i] = ld_wall(p, orec) ? 1 : 0;           // read here for Walls.update: k_collide then needs no record
     st_occ(p, orec, occ_gen);
 }
 
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(256) k_occ_stamp(Params p, uint32_t occ_gen) {
 // ------------------------------------------------------------------------------------------------ step, part 2
 // The winners of the food scatter write `old + (dropped - taken)` (ants.py:116); food that now lies inside the
 // anthill disc is queued for Anthill.update (anthill.py:41-46).
-__global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_stamp) {
+__global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_stamp, int par) {
     uint32_t n = *p.commit_count;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         int64_t i = p.commit_list[k];
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_st
         st_food(p, fr, nv);
         nv = ld_food(p, fr);                                                   // as stored (f32 in compact records)
         if (nv != 0.0 && in_hill(p.hill + 4 * e, pcx, pcy)) {
-            uint32_t s = atomicAdd(p.absorb_count, 1u);
+            uint32_t s = atomicAdd(p.absorb_count + par, 1u);
             p.absorb_list[2 * s] = (uint32_t)e;
             p.absorb_list[2 * s + 1] = (uint32_t)pcell;
         }
@@ -726,13 +729,33 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
 // Walls.update for ants (walls.py:24-28) and, when there are no rocks, the ant part of Ants.update
 // (ants.py:124,130) plus the ownership stamp of the pheromone deposit (pheromone.py:39, Q1).
 __global__ void __launch_bounds__(256)
-k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t owner_stamp, int finish) {
+k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t owner_stamp, int finish, int use_flag,
+          int par) {
+    // Anthill.update (anthill.py:41-46) for the cells queued by k_food_commit: nothing else in the update reads the
+    // food field, so the first blocks of this kernel absorb them; the other counter is zeroed for the next step.
+    {
+        const uint32_t n = p.absorb_count[par];
+        const uint32_t nb = gridDim.x < 32u ? gridDim.x : 32u;
+        if (blockIdx.x < nb) {
+            for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += nb * blockDim.x) {
+                uint32_t e = p.absorb_list[2 * k], c = p.absorb_list[2 * k + 1];
+                uint8_t *fr = rec_at(p, (int)e, (int)c);
+                double v;                                                      // qte -= qte * area
+                if (p.rec16) v = (double)__uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(fr + 8), 0u));
+                else v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(fr + p.food_off), 0ull));
+                if (v != 0.0) atomicAdd(p.hill_food + e, v);
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) p.absorb_count[par ^ 1] = 0u;
+    }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
     int a = (int)(i - (int64_t)e * p.N);
     double x = p.x[i], y = p.y[i], th = p.theta[i];
-    if (ld_wall(p, rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H))))) {
+    const bool in_wall = use_flag ? p.wall_hit[i] != 0
+                                  : ld_wall(p, rec_at(p, e, cidx(p, cell_of(x, p.W), cell_of(y, p.H))));
+    if (in_wall) {
         x = p.prev_x[i]; y = p.prev_y[i];
         double u = noise ? noise[i] : philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)a);
         th += u - 0.5;                                                         // not re-wrapped (Q3)
@@ -1031,21 +1054,6 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     }
     if (wrote && p.tile_active != nullptr)
         p.tile_active[((int64_t)e * p.tiles_x + cx / kTile) * p.tiles_y + cy / kTile] = 1;
-}
-
-// Anthill.update (anthill.py:41-46) for the cells queued by k_food_commit.
-__global__ void __launch_bounds__(256) k_absorb_list(Params p) {
-    uint32_t n = *p.absorb_count;
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
-        uint32_t e = p.absorb_list[2 * k], c = p.absorb_list[2 * k + 1];
-        uint8_t *fr = rec_at(p, (int)e, (int)c);
-        double v;                                                              // qte -= qte * area
-        if (p.rec16) v = (double)__uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(fr + 8), 0u));
-        else v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(fr + p.food_off), 0ull));
-        if (v != 0.0) atomicAdd(p.hill_food + e, v);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *p.absorb_count = 0u;
 }
 
 // Anthill.update as a sweep over the disc's bounding box (first update after an import, quirk Q10).
