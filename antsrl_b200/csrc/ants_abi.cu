@@ -164,7 +164,7 @@ int check_launch(const char *what) {
 // every live exploration stamp into "explored long ago" and clears the occupancy stamps.  Called at the start of
 // observe / step, before any stamp of the new generation is written.
 void maybe_fold_generations(AntsBatch *b) {
-    const uint32_t obs_lim = b->p.explored_old - 2u, occ_lim = b->p.rec16 ? 0xFEu : 0xFFFEu;
+    const uint32_t obs_lim = b->p.explored_old - 2u, occ_lim = b->p.rec16 ? 0x7Eu : 0xFFFEu;
     if (b->obs_gen + 1u >= obs_lim || b->occ_gen + 1u >= occ_lim) {
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 16, 256, 0, b->stream>>>(b->p, 1, 1);
@@ -181,7 +181,7 @@ uint32_t next_obs_gen(AntsBatch *b) {
     return ++b->obs_gen;
 }
 uint32_t next_occ_gen(AntsBatch *b) {
-    if (b->occ_gen >= (b->p.rec16 ? 0xFEu : 0xFFFEu)) {
+    if (b->occ_gen >= (b->p.rec16 ? 0x7Eu : 0xFFFEu)) {
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 0, 1);
         b->occ_gen = 0;
@@ -735,6 +735,8 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
             hill4[4 * e + 2] = r; hill4[4 * e + 3] = r < 0 ? -1 : r * r;
         }
         CK(cudaMemcpyAsync(p.hill, hill4.data(), hill4.size() * 4, cudaMemcpyHostToDevice, st));
+        ants::k_hill_mark<<<148 * 8, 256, 0, st>>>(p);
+        TRY(check_launch("k_hill_mark"));
         b->needs_sweep = 1;
     }
     if (s->anthill_food) CK(cudaMemcpyAsync(p.hill_food, s->anthill_food, (size_t)p.E * 8, cudaMemcpyHostToDevice, st));

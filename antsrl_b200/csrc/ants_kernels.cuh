@@ -134,7 +134,9 @@ __device__ __forceinline__ uint8_t *rec_at(const Params &p, int e, int cell) {
 __device__ __forceinline__ double *rec_phero(uint8_t *r, int k) { return reinterpret_cast<double *>(r) + k; }
 __device__ __forceinline__ uint8_t *rec_wall(const Params &p, uint8_t *r) { return r + p.wall_off; }
 // field access for both record formats.  Compact record (lazy mode, P <= 2), 16 bytes = half a sector:
-//   [0] f32 phero0  [4] f32 phero1  [8] f32 food  [12] u8 occ_gen  [13] u8 (wall << 7 | explored_gen)  [14],[15] u8 ts
+//   [0] f32 phero0  [4] f32 phero1  [8] f32 food  [12] u8 (hill << 7 | occ_gen)  [13] u8 (wall << 7 | explored_gen)
+//   [14],[15] u8 ts.  "hill" = the cell lies in the anthill disc (anthill.py:31-33), written by k_hill_mark at import;
+//   f64 records keep it in bit 1 of the wall byte.
 __device__ __forceinline__ double ld_food(const Params &p, const uint8_t *r) {
     return p.rec16 ? (double)*reinterpret_cast<const float *>(r + 8) : *reinterpret_cast<const double *>(r + p.food_off);
 }
@@ -148,16 +150,19 @@ __device__ __forceinline__ void st_phero(const Params &p, uint8_t *r, int k, dou
     if (p.rec16) reinterpret_cast<float *>(r)[k] = (float)v; else reinterpret_cast<double *>(r)[k] = v;
 }
 __device__ __forceinline__ bool ld_wall(const Params &p, const uint8_t *r) {
-    return p.rec16 ? (r[13] >> 7) != 0 : r[p.wall_off] != 0;
+    return p.rec16 ? (r[13] >> 7) != 0 : (r[p.wall_off] & 1) != 0;
 }
 __device__ __forceinline__ void st_wall(const Params &p, uint8_t *r, bool w) {
-    if (p.rec16) r[13] = (uint8_t)((r[13] & 0x7F) | (w ? 0x80 : 0)); else r[p.wall_off] = w ? 1 : 0;
+    if (p.rec16) r[13] = (uint8_t)((r[13] & 0x7F) | (w ? 0x80 : 0)); else r[p.wall_off] = (uint8_t)((r[p.wall_off] & 2) | (w ? 1 : 0));
 }
 __device__ __forceinline__ void st_occ(const Params &p, uint8_t *r, uint32_t gen) {
-    if (p.rec16) r[12] = (uint8_t)gen; else reinterpret_cast<uint16_t *>(r + p.meta_off)[1] = (uint16_t)gen;
+    if (p.rec16) r[12] = (uint8_t)((r[12] & 0x80u) | (gen & 0x7Fu)); else reinterpret_cast<uint16_t *>(r + p.meta_off)[1] = (uint16_t)gen;
 }
 __device__ __forceinline__ uint32_t ld_occ(const Params &p, const uint8_t *r) {
-    return p.rec16 ? r[12] : reinterpret_cast<const uint16_t *>(r + p.meta_off)[1];
+    return p.rec16 ? (r[12] & 0x7Fu) : reinterpret_cast<const uint16_t *>(r + p.meta_off)[1];
+}
+__device__ __forceinline__ void st_hill(const Params &p, uint8_t *r, bool h) {
+    if (p.rec16) r[12] = (uint8_t)((r[12] & 0x7Fu) | (h ? 0x80u : 0u)); else r[p.wall_off] = (uint8_t)((r[p.wall_off] & 1) | (h ? 2 : 0));
 }
 __device__ __forceinline__ uint32_t ld_explored(const Params &p, const uint8_t *r) {
     return p.rec16 ? (r[13] & 0x7Fu) : reinterpret_cast<const uint16_t *>(r + p.meta_off)[0];
@@ -227,7 +232,7 @@ __device__ __forceinline__ double phero_value(const Params &p, const uint8_t *r,
     const unsigned long long b = reinterpret_cast<const unsigned long long *>(r)[k];
     if (!p.lazy) return __longlong_as_double((long long)b);
     if (b == 0ull) return 0.0;
-    const bool wl = r[p.wall_off] != 0;
+    const bool wl = (r[p.wall_off] & 1) != 0;
     if (is_boxed64(b)) return boxed_value(p, (now_abs - (uint32_t)b) & kBoxMask, wl);
     return plain_value(p, __longlong_as_double((long long)b), rec_ts(p, r, k), now, wl);
 }
@@ -557,7 +562,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 } else {                       // generic f64 record: gather the fields into the same register shape
                     const double fdv = *reinterpret_cast<const double *>(rp[u] + food_off);
                     const uint32_t mtv = *reinterpret_cast<const uint32_t *>(rp[u] + meta_off);
-                    const uint32_t wlv = *(rp[u] + wall_off);
+                    const uint32_t wlv = *(rp[u] + wall_off) & 1u;
                     hi[u] = make_uint4((uint32_t)__double2loint(fdv), (uint32_t)__double2hiint(fdv), mtv, wlv);
                     lo[u] = make_uint4(0u, 0u, 0u, 0u);
                 }
@@ -574,10 +579,10 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 float fdf;                     // food as the f32 observation shows it
                 if (REC16) {
                     const uint32_t pk = lo[u].w;
-                    occ = pk & 0xFFu; eg = (pk >> 8) & 0x7Fu; wl = ((pk >> 15) & 1u) != 0;
+                    occ = pk & 0x7Fu; eg = (pk >> 8) & 0x7Fu; wl = ((pk >> 15) & 1u) != 0;
                     fdf = __uint_as_float(lo[u].z);
                 } else {
-                    occ = hi[u].z >> 16; eg = hi[u].z & 0xFFFFu; wl = (hi[u].w & 0xFFu) != 0;
+                    occ = hi[u].z >> 16; eg = hi[u].z & 0xFFFFu; wl = (hi[u].w & 1u) != 0;
                     fdf = (float)__hiloint2double((int)hi[u].y, (int)hi[u].x);
                 }
                 if (explore_on) {
@@ -880,7 +885,7 @@ __device__ __forceinline__ bool evaporate_record(const Params &p, uint8_t *r, do
     if (p.P == 2) {
         double2 v = *reinterpret_cast<double2 *>(r);
         if (v.x == 0.0 && v.y == 0.0) return false;
-        const bool wl = *rec_wall(p, r) != 0;
+        const bool wl = (*rec_wall(p, r) & 1) != 0;
         double a = wl ? 0.0 : v.x * c, b = wl ? 0.0 : v.y * c;
         a = a < 0.01 ? 0.0 : a;
         b = b < 0.01 ? 0.0 : b;
@@ -888,7 +893,7 @@ __device__ __forceinline__ bool evaporate_record(const Params &p, uint8_t *r, do
         *reinterpret_cast<double2 *>(r) = make_double2(a, b);
         any = (a != 0.0) || (b != 0.0);
     } else {
-        const bool wl = *rec_wall(p, r) != 0;
+        const bool wl = (*rec_wall(p, r) & 1) != 0;
         for (int k = 0; k < p.P; ++k) {
             double v = *rec_phero(r, k);
             if (v == 0.0) continue;
@@ -957,7 +962,7 @@ __global__ void __launch_bounds__(256) k_evaporate_tiles(Params p, const uint32_
                 const int by = by0 + ((pass >> 1) & 1);
                 rp[pass] = rec_at(p, e, ((bx * p.nby + by) << 6) + (pass & 1) * 32 + lane);
                 v[pass] = *reinterpret_cast<const double2 *>(rp[pass]);
-                wl[pass] = rp[pass][p.wall_off];
+                wl[pass] = rp[pass][p.wall_off] & 1;
             }
 #pragma unroll
             for (int pass = 0; pass < 8; ++pass) {
@@ -997,7 +1002,7 @@ __global__ void __launch_bounds__(256) k_diffuse_stencil(Params p, int nbx, int 
         double v = 0.0;
         if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
             uint8_t *r = rec_at(p, e, cidx(p, gx, gy));
-            v = *rec_wall(p, r) ? 0.0 : *rec_phero(r, k);
+            v = (*rec_wall(p, r) & 1) ? 0.0 : *rec_phero(r, k);
         }
         tile[lx][ly] = v;
     }
@@ -1139,6 +1144,17 @@ __global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what) {
         int x = (int)(ex - e * p.W);
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
         dense[j] = what == 0 ? (ld_wall(p, r) ? 1 : 0) : (ld_explored(p, r) ? 1 : 0);
+    }
+}
+// the anthill disc as a bit of every cell record (anthill.py:31-33), after the anthill was imported
+__global__ void k_hill_mark(Params p) {
+    const int64_t n = (int64_t)p.E * p.W * p.H;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t ex = j / p.H;
+        int y = (int)(j - ex * p.H);
+        int64_t e = ex / p.W;
+        int x = (int)(ex - e * p.W);
+        st_hill(p, rec_at(p, (int)e, cidx(p, x, y)), in_hill(p.hill + 4 * e, x, y));
     }
 }
 // generation counters are 16 bit: before one wraps, fold every live stamp into the "long ago" value

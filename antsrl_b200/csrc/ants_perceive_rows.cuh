@@ -27,7 +27,7 @@ struct RowPrep {                 // 96 bytes per ant, shared memory (phase A -> 
     double xf, yf;               // position shifted forward by perception_fwd_delta
     unsigned long long rocks;    // further candidate rocks (beyond the first) whose disc can reach the window
     int e, hx, hy, hr2;          // environment; anthill centre and radius^2
-    int flags, pad;              // 1 = the window may touch the anthill, 2 = a rock may reach it, 4 = more than one
+    int flags, pad;              // 2 = a rock may reach the window, 4 = more than one
     double rcx, rcy, rrad;       // the first candidate rock
     double pad2;
 };
@@ -161,12 +161,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     rm = keep;
                 }
             }
-            {   // can the window touch the anthill disc?  (torus distance, same reach as for the rocks)
-                const double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.0 + (double)hl[2];
-                double dx = fabs(q.xf - (double)q.hx), dy = fabs(q.yf - (double)q.hy);
-                dx = fmin(dx, fabs((double)p.W - dx));
-                dy = fmin(dy, fabs((double)p.H - dy));
-                q.flags = (dx < reach && dy < reach) ? 1 : 0;
+            {
+                q.flags = 0;
                 q.pad = 0; q.pad2 = 0.0;
                 q.rcx = q.rcy = 0.0; q.rrad = -1.0;
                 if (rm) {
@@ -239,7 +235,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << (REC16 ? 4 : 5));
             const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
             const int flags = q.flags;
-            uint32_t hbits = 0u;                                       // bit j: anthill, bit 8 + j: rock, at column j
+            uint32_t rbits = 0u;                                       // bit j: a rock covers the sample at column j
             int cnt = 0;
 #pragma unroll
             for (int j0 = 0; j0 < S; j0 += UNR) {
@@ -255,26 +251,28 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         const double ry = st * X + ctY;
                         int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
                         ix = wrap1(ix, W); iy = wrap1(iy, H);
-                        if (flags) {                   // few ants are near the anthill or a rock
-                            if (flags & 1) {           // anthill.py:31-33 on integers (RL_api.py:130-131)
-                                const int hdx = q.hx - ix, hdy = q.hy - iy;
-                                hbits |= (hdx * hdx + hdy * hdy <= q.hr2 ? 1u : 0u) << j;
-                            }
-                            if (LAYOUT == 2 && (flags & 2)) {          // RL_api.py:132-135, strict <
-                                // sqrt(d2) < r decided on the squares unless d2 is within 1e-12 of r^2
-                                const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
-                                const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
-                                bool hit = d2 < r2 * 0.999999999999;
-                                if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
-                                if (!hit && (flags & 4)) hit = rock_channel(p, e, q.rocks, ix, iy) != 0.f;
-                                hbits |= (hit ? 1u : 0u) << (8 + j);
-                            }
-                        }
                         // cidx(): 8 x 8 blocks of 64 records
                         cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
                         const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
                         lo[u] = ld_record16(rp);
                         if (!REC16) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
+                    }
+                }
+                if (LAYOUT == 2 && flags) {            // a rock may reach this ant's window (few ants): RL_api.py:132-135
+#pragma unroll 1
+                    for (int j = j0; j < S && j < j0 + UNR; ++j) {
+                        const double X = p.off_c[j];                           // the same arithmetic as above
+                        const double rx = ct * X - stY;
+                        const double ry = st * X + ctY;
+                        int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
+                        ix = wrap1(ix, W); iy = wrap1(iy, H);
+                        // strict sqrt(d2) < r, decided on the squares unless d2 is within 1e-12 of r^2
+                        const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
+                        const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
+                        bool hit = d2 < r2 * 0.999999999999;
+                        if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
+                        if (!hit && (flags & 4)) hit = rock_channel(p, e, q.rocks, ix, iy) != 0.f;
+                        rbits |= (hit ? 1u : 0u) << j;
                     }
                 }
                 if (kLateWait) {
@@ -286,12 +284,13 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     const int j = j0 + u;
                     if (j < S) {
                         uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << (REC16 ? 4 : 5));
-                        bool wl, occupied, fresh, seen_now;
+                        bool wl, occupied, fresh, seen_now, hill;
                         uint32_t age0, age1;
                         float v5;                      // food as the f32 observation shows it
                         if (REC16) {
                             const uint32_t pk = lo[u].w;
-                            occupied = (pk & 0xFFu) == occ_gen;
+                            occupied = (pk & 0x7Fu) == occ_gen;
+                            hill = (pk & 0x80u) != 0;
                             wl = (pk & 0x8000u) != 0;
                             fresh = (pk & 0x7F00u) == 0u;
                             seen_now = (pk & 0x7F00u) == ogs;
@@ -300,7 +299,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                             if (explore_on && fresh) rp[13] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
                         } else {
                             occupied = (hi[u].z >> 16) == occ_gen;
-                            wl = (hi[u].w & 0xFFu) != 0;
+                            wl = (hi[u].w & 1u) != 0;
+                            hill = (hi[u].w & 2u) != 0;
                             fresh = (hi[u].z & 0xFFFFu) == 0u;
                             seen_now = (hi[u].z & 0xFFFFu) == obs_gen;
                             v5 = (float)__hiloint2double((int)hi[u].y, (int)hi[u].x);
@@ -312,35 +312,48 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                             if (explore_on && fresh) *reinterpret_cast<uint16_t *>(rp + 24) = (uint16_t)obs_gen;
                         }
                         if (explore_on) cnt += (fresh || seen_now) ? 1 : 0;    // gather-before-scatter, Q7
-                        if ((mrow >> j) & 1u) {
-                            // pheromone channels, RL_api.py:124-125.  A saturated deposit of age k shows
-                            // (float)(max_val * keep^k / max_val) = keep^k (the reference's per-step rounding moves it by
-                            // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
-                            // cut is the exact table length; inside a wall only a deposit of this very update shows.
-                            const uint32_t lim = wl ? 1u : tab_len;
-                            float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
-                            float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
-                            if (any_plain) {           // plain values (bool activations, imports, eager modes): out of line
-                                const bool pl0 = REC16 ? (lo[u].x != 0u && !is_boxed32(lo[u].x))
-                                                       : ((lo[u].x | lo[u].y) != 0u && age0 == 0xFFFFFFFFu);
-                                const bool pl1 = REC16 ? (lo[u].y != 0u && !is_boxed32(lo[u].y))
-                                                       : ((lo[u].z | lo[u].w) != 0u && age1 == 0xFFFFFFFFu);
-                                if (pl0) v1 = phero_obs_slow(p, rp, 0, now, now_abs);
-                                if (pl1) v2 = phero_obs_slow(p, rp, 1, now, now_abs);
-                            }
-                            const float v3 = ((hbits >> j) & 1u) ? 1.f : 0.f;
-                            const float v6 = ((hbits >> (8 + j)) & 1u) ? 1.f : 0.f;
-                            const float v0 = occupied ? 1.f : 0.f;                               // :136-142
-                            const float v4 = wl ? 1.f : 0.f;                                     // :128-129
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 0) * 4)), "f"(v0) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 1) * 4)), "f"(v1) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 2) * 4)), "f"(v2) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 3) * 4)), "f"(v3) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 4) * 4)), "f"(v4) : "memory");
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 5) * 4)), "f"(v5) : "memory");
-                            if (LAYOUT == 2)
-                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + 6) * 4)), "f"(v6) : "memory");
-                        }
+                        // pheromone channels, RL_api.py:124-125.  A saturated deposit of age k shows
+                        // (float)(max_val * keep^k / max_val) = keep^k (the reference's per-step rounding moves it by
+                        // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
+                        // cut is the exact table length; inside a wall only a deposit of this very update shows.
+                        const uint32_t lim = wl ? 1u : tab_len;
+                        const float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
+                        const float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                        const float v0 = occupied ? 1.f : 0.f;                                   // :136-142
+                        const float v3 = hill ? 1.f : 0.f;                                       // :130-131 (disc bit of the record)
+                        const float v4 = wl ? 1.f : 0.f;                                         // :128-129
+                        const float v6 = ((rbits >> j) & 1u) ? 1.f : 0.f;                        // :132-135
+                        const uint32_t vis = (mrow >> j) & 1u;     // masked slots keep the -1 written once above
+                        const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
+                        if (LAYOUT == 2)
+                            asm volatile("{\n .reg .pred pv;\n setp.ne.u32 pv, %0, 0;\n"
+                                         " @pv st.shared.f32 [%1], %2;\n @pv st.shared.f32 [%1+4], %3;\n"
+                                         " @pv st.shared.f32 [%1+8], %4;\n @pv st.shared.f32 [%1+12], %5;\n"
+                                         " @pv st.shared.f32 [%1+16], %6;\n @pv st.shared.f32 [%1+20], %7;\n"
+                                         " @pv st.shared.f32 [%1+24], %8;\n}"
+                                         ::"r"(vis), "r"(oaddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6) : "memory");
+                        else
+                            asm volatile("{\n .reg .pred pv;\n setp.ne.u32 pv, %0, 0;\n"
+                                         " @pv st.shared.f32 [%1], %2;\n @pv st.shared.f32 [%1+4], %3;\n"
+                                         " @pv st.shared.f32 [%1+8], %4;\n @pv st.shared.f32 [%1+12], %5;\n"
+                                         " @pv st.shared.f32 [%1+16], %6;\n @pv st.shared.f32 [%1+20], %7;\n}"
+                                         ::"r"(vis), "r"(oaddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5) : "memory");
+                    }
+                }
+                if (any_plain) {   // plain pheromone values (bool activations, imports, eager modes) may exist: patch them in
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int j = j0 + u;
+                        if (j >= S || !((mrow >> j) & 1u)) continue;
+                        const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
+                        const uint4 r4 = *reinterpret_cast<const uint4 *>(rp);
+                        const bool pl0 = REC16 ? (r4.x != 0u && !is_boxed32(r4.x))
+                                               : ((r4.x | r4.y) != 0u && !(p.lazy && (r4.y & 0xFFF80000u) == 0x7FF80000u));
+                        const bool pl1 = REC16 ? (r4.y != 0u && !is_boxed32(r4.y))
+                                               : ((r4.z | r4.w) != 0u && !(p.lazy && (r4.w & 0xFFF80000u) == 0x7FF80000u));
+                        const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
+                        if (pl0) asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 0, now, now_abs)) : "memory");
+                        if (pl1) asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 1, now, now_abs)) : "memory");
                     }
                 }
             }
@@ -352,7 +365,9 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             fence_proxy_async_smem();
             __syncwarp();
+#ifndef ANTS_DBG_NOSTORE
             if (lane == 0) bulk_store_s2g(dst, wobs, bytes);
+#endif
         } else {
             __syncwarp();
             for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
