@@ -288,23 +288,43 @@ __device__ __forceinline__ unsigned long long rock_candidates(const Params &p, i
     int gy = cell_of(pymod_near(y, (double)p.H), p.H) >> kGridShift;
     return p.rock_grid[((int64_t)e * p.grid_w + gx) * p.grid_h + gy];
 }
-template <bool SET = true>
-__device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad) {
-    const double L = rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
+// reach of a rock in the grid: radius + the farthest a perception sample can lie from the (shifted) ant position
+__device__ __forceinline__ double rock_reach(const Params &p, double rad) {
+    return rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
+}
+// k-th sample offset of the box [-L, L] walked in grid steps, the far edge included: -L, -L + 16, ..., L
+__device__ __forceinline__ bool rock_box_offset(double L, int k, double *o) {
     const double step = (double)(1 << kGridShift);
-    unsigned long long *g = p.rock_grid + (int64_t)e * p.grid_w * p.grid_h;
+    const double v = -L + (double)k * step;
+    if (k > 0 && v - step >= L) return false;          // the previous sample already was the far edge
+    *o = v > L ? L : v;
+    return true;
+}
+__device__ __forceinline__ void rock_grid_touch(const Params &p, int e, int r, double x, double y, bool set) {
+    const int gx = cell_of(pymod_near(x, (double)p.W), p.W) >> kGridShift;
+    const int gy = cell_of(pymod_near(y, (double)p.H), p.H) >> kGridShift;
+    unsigned long long *g = p.rock_grid + ((int64_t)e * p.grid_w + gx) * p.grid_h + gy;
     const unsigned long long bit = 1ull << r;
-    // sample the box [c - L, c + L] every grid step (and at its far edge): hits every grid cell it overlaps
-    for (double ox = -L;; ox += step) {
-        if (ox > L) ox = L;
-        int gx = cell_of(pymod(cx + ox, (double)p.W), p.W) >> kGridShift;
-        for (double oy = -L;; oy += step) {
-            if (oy > L) oy = L;
-            int gy = cell_of(pymod(cy + oy, (double)p.H), p.H) >> kGridShift;
-            if (SET) atomicOr(g + gx * p.grid_h + gy, bit); else atomicAnd(g + gx * p.grid_h + gy, ~bit);
-            if (oy >= L) break;
-        }
-        if (ox >= L) break;
+    if (set) atomicOr(g, bit); else atomicAnd(g, ~bit);
+}
+// every grid cell the box [c - L, c + L] overlaps gets (or loses) the rock's bit; one thread
+__device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad, bool set = true) {
+    const double L = rock_reach(p, rad);
+    double ox, oy;
+    for (int i = 0; rock_box_offset(L, i, &ox); ++i)
+        for (int j = 0; rock_box_offset(L, j, &oy); ++j) rock_grid_touch(p, e, r, cx + ox, cy + oy, set);
+}
+// the same by a whole warp: lane = (i, j) of the box samples (boxes of up to 5 x 5 samples, else lane 0 alone)
+__device__ __forceinline__ void rock_grid_mark_warp(const Params &p, int e, int r, double cx, double cy, double rad, bool set, int lane) {
+    const double L = rock_reach(p, rad);
+    double o;
+    if (rock_box_offset(L, 5, &o)) {                   // more than 5 samples per axis: serial fallback
+        if (lane == 0) rock_grid_mark(p, e, r, cx, cy, rad, set);
+        return;
+    }
+    if (lane < 25) {
+        double ox, oy;
+        if (rock_box_offset(L, lane / 5, &ox) && rock_box_offset(L, lane % 5, &oy)) rock_grid_touch(p, e, r, cx + ox, cy + oy, set);
     }
 }
 
@@ -831,16 +851,18 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
             }
         }
     }
+    // every lane holds the same sums
+    const double wt = p.rock_w[pair];
+    const double nx = cx - sx / wt, ny = cy - sy / wt;
     if (lane == 0) {
-        const double wt = p.rock_w[pair];
-        const double nx = cx - sx / wt, ny = cy - sy / wt;
         rc[2 * r] = nx;
         rc[2 * r + 1] = ny;
         p.rock_touch[pair] = 0u;
-        if (nx != cx || ny != cy) {                    // the grid entries follow the rock
-            rock_grid_mark<false>(p, e, r, cx, cy, rad);
-            rock_grid_mark<true>(p, e, r, nx, ny, rad);
-        }
+    }
+    if (nx != cx || ny != cy) {                        // the grid entries follow the rock
+        rock_grid_mark_warp(p, e, r, cx, cy, rad, false, lane);
+        __syncwarp();                                  // orders the clears before the sets (the boxes overlap)
+        rock_grid_mark_warp(p, e, r, nx, ny, rad, true, lane);
     }
 }
 
