@@ -310,3 +310,105 @@ def test_random_configurations(case):
     kw = _random_config(rng)
     mode, record = [("dense", "f64"), ("tiles", "f64"), ("lazy", "f64"), ("lazy", "compact")][case % 4]
     run_parity(_variants(kw, 2), evap_mode=mode, record=record)
+
+
+def _cmp_outputs(gpu, refs, what):
+    obs, ast, rew = [g.cpu().numpy() for g in gpu]
+    assert_close(obs, np.stack([r[0] for r in refs]), what + ": obs")
+    assert_close(ast, np.stack([r[1] for r in refs]), what + ": agent_state")
+    assert_close(rew, np.stack([r[2] for r in refs]), what + ": reward")
+
+
+@pytest.mark.parametrize("record", ["compact", "f64"])
+@pytest.mark.parametrize("n_rocks", [0, 5])
+def test_irregular_call_order(record, n_rocks):
+    """observe / step / update in an order main.py never uses (update before the first step, two steps in a row, two
+    updates in a row, a stand-alone observation in between): the per-call bookkeeping the kernels share across calls
+    (wall flags written by the move, the double-buffered absorb counter, deposit ownership phases, generation stamps)
+    must not depend on strict step/update alternation."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from parity_util import compare_state
+    from oracle.antsrl_oracle import OracleEnv
+    scen = [make_scenario(seed=900 + e, w=56, h=48, n_ants=40, n_rocks=n_rocks, steps=16, n_walls=6, n_food=8)
+            for e in range(3)]
+    cfg = scen[0][0]
+    oracles = [OracleEnv(c, i) for c, i, _ in scen]
+    b = BatchedAnts(cfg, 3, evap_mode="lazy", record=record)
+    b.import_state(stack_init(cfg, [i for _, i, _ in scen]))
+    order = "ousussuuosuosusuuussu"
+    t = 0
+    for k, op in enumerate(order):
+        what = "call %d (%s)" % (k, op)
+        if op == "o":
+            refs = []
+            for o in oracles:
+                p_, a_, _ = o.observation()
+                refs.append((p_, a_, o.s["rewards"].copy()))
+            obs, ast, st, rew = b.observe()
+            _cmp_outputs((obs, ast, rew), refs, what)
+        elif op == "s":
+            rot = np.stack([s[2]["rot"][t] for s in scen]).astype(np.int8)
+            ph = np.stack([s[2]["ph"][t] for s in scen]).astype(np.int8)
+            refs = []
+            for e, o in enumerate(oracles):
+                p_, a_, r_, _ = o.step(rot[e].astype(np.int64), ph[e].astype(np.int64))
+                refs.append((p_, a_, r_.copy()))
+            obs, ast, rew, _ = b.step(torch.from_numpy(rot).cuda(), torch.from_numpy(ph).cuda())
+            _cmp_outputs((obs, ast, rew), refs, what)
+        else:
+            noise = np.stack([s[2]["noise"][t] for s in scen])
+            for e, o in enumerate(oracles):
+                o.update(noise[e])
+            b.update(torch.from_numpy(noise).cuda())
+            t += 1
+        compare_state(b.export_state(), oracles, what, cfg)
+    b.close()
+
+
+def test_reimport_moves_anthill_and_walls():
+    """A handle is reused for a new episode (main.py:66-79 generates a new map per episode): the second import moves
+    the anthill (the disc bit of the cell records), the walls and the rocks; nothing of the first map may survive."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from parity_util import compare_state
+    from oracle.antsrl_oracle import OracleEnv
+    b = None
+    for episode, seed0 in enumerate((950, 960)):
+        scen = [make_scenario(seed=seed0 + e, w=64, h=64, n_ants=48, n_rocks=4, steps=10, n_walls=5) for e in range(2)]
+        cfg = scen[0][0]
+        if b is None:
+            b = BatchedAnts(cfg, 2, evap_mode="lazy", record="compact")
+        oracles = [OracleEnv(c, i) for c, i, _ in scen]
+        # a COMPLETE state (import leaves missing members untouched): the oracle's own initial state
+        b.import_state(stack_init(cfg, [dict(o.s) for o in oracles]))
+        refs = []
+        for o in oracles:
+            p_, a_, _ = o.observation()
+            refs.append((p_, a_, o.s["rewards"].copy()))
+        obs, ast, st, rew = b.observe()
+        _cmp_outputs((obs, ast, rew), refs, "episode %d observation" % episode)
+        for t in range(10):
+            rot = np.stack([s[2]["rot"][t] for s in scen]).astype(np.int8)
+            ph = np.stack([s[2]["ph"][t] for s in scen]).astype(np.int8)
+            refs = []
+            for e, o in enumerate(oracles):
+                p_, a_, r_, _ = o.step(rot[e].astype(np.int64), ph[e].astype(np.int64))
+                refs.append((p_, a_, r_.copy()))
+            obs, ast, rew, _ = b.step(torch.from_numpy(rot).cuda(), torch.from_numpy(ph).cuda())
+            _cmp_outputs((obs, ast, rew), refs, "episode %d step %d" % (episode, t))
+            noise = np.stack([s[2]["noise"][t] for s in scen])
+            for e, o in enumerate(oracles):
+                o.update(noise[e])
+            b.update(torch.from_numpy(noise).cuda())
+            compare_state(b.export_state(), oracles, "episode %d update %d" % (episode, t), cfg)
+    b.close()
+
+
+def test_crowded_rocks_default_channels():
+    """Many rocks on a small map: most ants have several candidate rocks (the multi-rock path of the row-per-lane
+    perception kernel), rocks get pushed every step (incremental rock-grid update) and push ants across the seam."""
+    kw = dict(seed=970, w=40, h=40, n_ants=64, n_rocks=14, steps=40, n_walls=2, n_food=5)
+    for record, mode in (("compact", "lazy"), ("f64", "dense")):
+        rep = run_parity(_variants(kw, 3), evap_mode=mode, record=record)
+        assert rep["state_checks"] == kw["steps"]
