@@ -607,8 +607,17 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         const int C = p.C;
         b->perceive_rows = (b->perceive_layout != 0 && p.S == 7 && !b->perceive_slow_wrap &&
                             !getenv("ANTS_PERCEIVE_GENERIC")) ? 1 : 0;
-        b->rows_smem = (ants::kRowsThreads / 32) * ants::kRowsGroup * p.S2 * C * 4 +
+        b->rows_smem = (ants::kRowsThreads / 32) * ants::kRowsTiles * ants::kRowsGroup * p.S2 * C * 4 +
                        ants::kRowsThreads * (int)sizeof(ants::RowPrep) + ants::kRowsThreads * p.S;
+    }
+    if (b->perceive_rows && b->rows_smem > 48 * 1024) {
+        const void *fns[4] = {(const void *)ants::k_perceive_rows<1, false, 7>, (const void *)ants::k_perceive_rows<2, false, 7>,
+                              (const void *)ants::k_perceive_rows<1, true, 7>, (const void *)ants::k_perceive_rows<2, true, 7>};
+        for (int k = 0; k < 4; ++k)
+            if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, b->rows_smem) != cudaSuccess) {
+                ants_destroy(b);
+                return fail(ANTS_E_CUDA, "k_perceive_rows needs %d B of shared memory", b->rows_smem);
+            }
     }
     if (b->perceive_smem > 48 * 1024) {
         cudaError_t e = cudaSuccess;

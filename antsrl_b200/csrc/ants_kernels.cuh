@@ -274,8 +274,9 @@ __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uin
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
-__device__ __forceinline__ void bulk_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+template <int PENDING = 0>
+__device__ __forceinline__ void bulk_store_wait_read() {   // until at most PENDING bulk stores still read shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(PENDING) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");

@@ -21,6 +21,10 @@ namespace ants {
 
 constexpr int kRowsThreads = 128;
 constexpr int kRowsGroup = 4;
+#ifndef ANTS_ROWS_TILES
+#define ANTS_ROWS_TILES 1
+#endif
+constexpr int kRowsTiles = ANTS_ROWS_TILES;   // staging tiles per warp (2 = the bulk store of chunk g drains while g + 1 is staged)
 
 struct RowPrep {                 // 96 bytes per ant, shared memory (phase A -> phase B)
     double ct, st;               // cos / sin(theta + pi/2)
@@ -99,7 +103,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     constexpr int UNR = REC16 ? (S < ANTS_ROWS_UNR ? S : ANTS_ROWS_UNR) : (S + 1) / 2;                      // record loads in flight per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_obs = reinterpret_cast<float *>(smem_raw);               // [NW][TILE]
-    RowPrep *prep = reinterpret_cast<RowPrep *>(s_obs + NW * TILE);   // [threads]
+    RowPrep *prep = reinterpret_cast<RowPrep *>(s_obs + NW * kRowsTiles * TILE);   // [threads]
     uint8_t *s_rowcnt = reinterpret_cast<uint8_t *>(prep + kRowsThreads);   // [threads][S]
 
     const int tid = threadIdx.x;
@@ -202,10 +206,10 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     // boxed deposit b = box | t: (box | now) - b = now - t = age; zero and plain values give an "age" >= 2^22
     const uint32_t nowb = REC16 ? box32(now_abs) : (now_abs & kBoxMask);
     const uint32_t ogs = obs_gen << 8;
-    float *wobs = s_obs + warp * TILE;
+    float *wobs0 = s_obs + warp * kRowsTiles * TILE;
     // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
-    uint32_t orow_s = (uint32_t)__cvta_generic_to_shared(wobs + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
-    asm volatile("" : "+r"(orow_s), "+r"(mrow));                    // keep them in registers (no rematerialisation)
+    uint32_t orow_s0 = (uint32_t)__cvta_generic_to_shared(wobs0 + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
+    asm volatile("" : "+r"(orow_s0), "+r"(mrow));                    // keep them in registers (no rematerialisation)
     // masked samples read -1 in every channel (RL_api.py:147-148) and their tile slots are never written again
     if (lane_on) {
 #pragma unroll
@@ -213,19 +217,24 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             if (!((mrow >> j) & 1u))
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + c) * 4)), "f"(-1.f) : "memory");
+#pragma unroll
+                    for (int t = 0; t < kRowsTiles; ++t)
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s0 + (uint32_t)((t * TILE + j * C + c) * 4)), "f"(-1.f) : "memory");
     }
 
     for (int g = 0; g < 32; g += G) {
         const int64_t i0 = base + warp * 32 + g;
         if (i0 >= p.EN) break;
         const int n_in = (p.EN - i0 < G) ? (int)(p.EN - i0) : G;
+        const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
+        float *wobs = wobs0 + tsel * TILE;
+        const uint32_t orow_s = orow_s0 + (uint32_t)(tsel * TILE * 4);
         // the previous chunk's bulk store must have finished reading the staging tile before it is written again:
         // with a single batch of loads (compact records) that wait sits behind the loads, where it costs nothing
         constexpr bool kLateWait = (UNR >= S);
         const uint32_t amask = (n_in * S >= 32) ? 0xffffffffu : ((1u << (n_in * S)) - 1u);   // the lanes with a row
         if (!kLateWait) {
-            if (lane == 0) bulk_store_wait_read();
+            if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
             __syncwarp();
         }
         if (lane_on && la < n_in) {
@@ -276,7 +285,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     }
                 }
                 if (kLateWait) {
-                    if (lane == 0) bulk_store_wait_read();
+                    if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
                     __syncwarp(amask);
                 }
 #pragma unroll
