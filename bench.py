@@ -380,7 +380,7 @@ def run_ours(args):
             "active_tile_fraction": (st["active_tiles"] / st["total_tiles"]) if st["total_tiles"] else None,
             "setup_s": t_setup,
         }
-        print(json.dumps(line))
+        emit(line)
     batch.close()
     if world > 1:
         dist.destroy_process_group()
@@ -403,10 +403,28 @@ def run_reference(args):
                        "ants_per_env": wl["n_ants"], "map": [wl["w"], wl["h"]]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "ant-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
+    # Libraries print on fd 1 (NCCL's version banner comes from C, whatever NCCL_DEBUG says): everything but the
+    # final JSON line is sent to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

@@ -19,7 +19,7 @@ if os.path.exists(lc):
         if len(r) > mv:
             try: d[r[kn].split('(')[0].replace('void ', '')].append(float(r[mv].replace(',', '')))
             except ValueError: pass
-    step_k = {k: v for k, v in d.items() if not k.startswith(("k_pack", "k_unpack", "k_rock_grid_build", "k_tiles_from", "k_occ_stamp", "k_absorb_sweep", "k_meta"))}
+    step_k = {k: v for k, v in d.items() if not k.startswith(("k_pack", "k_unpack", "k_rock_grid_build", "k_tiles_from", "k_occ_stamp", "k_absorb_sweep", "k_meta", "k_hill_mark"))}
     tot = sum(sum(v) for v in step_k.values())
     lines += ["## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares)", "",
               "| kernel | launches | avg us | share of step kernels |", "|---|---|---|---|"]
