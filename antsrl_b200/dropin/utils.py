@@ -1,12 +1,11 @@
-"""Mirror of the reference's top-level ``utils`` module (utils.py:5-33): only ``AX`` is on the step path."""
+"""Mirror of the reference's top-level ``utils`` module (utils.py:5-33): only ``AX`` is on the step path;
+``perlin_noise_generator`` restates the absent third-party ``noise.pnoise2`` (antsrl_b200/perlin.py)."""
 import numpy as np
 
 AX = np.newaxis
 
 
-def perlin_noise_generator(w, h, offset_x, offset_y, scale=22.0, octaves=2, persistence=0.5, lacunarity=2.0):
-    raise NotImplementedError("perlin_noise_generator needs the third-party `noise` package (utils.py:12), which "
-                              "is not available; SURVEY.md section 8(f) row 1")
+from antsrl_b200.perlin import perlin_noise_generator   # noqa: E402,F401  (utils.py:7-18; restated, parity unpinned)
 
 
 def plot_training(reward, loss):   # utils.py:20-33 (plotting, out of scope; kept so `from utils import *` works)

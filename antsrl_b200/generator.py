@@ -55,17 +55,7 @@ class CirclesGenerator:
         return gen
 
 
-class PerlinGenerator:
-    """map_generators.py:9-25 needs the third-party C extension `noise` (caseman/noise, unpinned, absent here):
-    SURVEY.md section 8(f) row 1, not built this round."""
-
-    def __init__(self, scale=22.0, density=0.05, octaves=2, persistence=0.5, lacunarity=2.0):
-        self.scale, self.density, self.octaves = scale, density, octaves
-        self.persistence, self.lacunarity = persistence, lacunarity
-
-    def generate(self, w, h):
-        raise NotImplementedError("PerlinGenerator depends on the `noise` package (utils.py:12); use "
-                                  "CirclesGenerator or any object with generate(w, h) for walls")
+from .perlin import PerlinGenerator   # noqa: E402,F401  (map_generators.py:9-25; parity unpinned, see perlin.py)
 
 
 def generate_state(w, h, n_ants, n_pheromones, n_rocks, food_generator, walls_generator, seed=None, max_hold=5,

@@ -76,10 +76,11 @@ def test_api_surface_matches_reference():
         assert env.timestep == 1 and env.max_time == 100 and api.ants.phero_activation.dtype == bool
         api.ants.activate_all_pheromones(np.ones((50, 2)) * 10)
         assert api.ants.phero_activation.dtype == float
-        try:
-            PerlinGenerator().generate(8, 8); raise SystemExit('Perlin should be unavailable')
-        except NotImplementedError:
-            pass
+        import random
+        random.seed(3)
+        walls = PerlinGenerator().generate(40, 24)      # restated pnoise2 (parity unpinned): shape / dtype / determinism
+        random.seed(3)
+        assert walls.shape == (40, 24) and walls.dtype == bool and np.array_equal(walls, PerlinGenerator().generate(40, 24))
         print('surface ok')
     """ % os.path.join(GOLDEN, "gen_200_s1000.npz"))
     assert "surface ok" in out
