@@ -75,7 +75,8 @@ struct Params {
     uint32_t mask_rows[16];                // bit j of entry i = mask[i][j] (all ones without a mask)
     // scratch
     double *food_delta;                    // [E*N]
-    uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food of a cell this step
+    uint32_t *commit_list, *commit_count;  // ants whose mandible action changes the food of a cell this step;
+                                           // commit_count[2]: a step appends under one counter, k_food_commit zeroes the other
     uint32_t *absorb_list, *absorb_count;  // (env, cell) pairs of food lying inside the anthill disc; absorb_count[2]:
                                            // the step appends under one counter while the update zeroes the other
     uint8_t *wall_hit;                     // [E*N] 1 = the ant stands in a wall cell after this step's move
@@ -267,6 +268,14 @@ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t env, ui
     return (a * 67108864.0 + b) / 9007199254740992.0;
 }
 
+// Programmatic dependent launch (the step kernels are launched with programmatic stream serialisation): a kernel lets
+// the next one in the stream be scheduled while its own last blocks still run, and waits for its predecessor's memory
+// before it touches anything.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_begin() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // shared -> global bulk copy through the async proxy (TMA 1-D bulk store, SASS UBLKCP)
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
@@ -335,7 +344,8 @@ __device__ __forceinline__ void rock_grid_mark_warp(const Params &p, int e, int 
 // plus the occupancy stamp consumed by the "ants" perception channel (RL_api.py:136-142).
 __global__ void __launch_bounds__(256)
 k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__ ph, uint32_t owner_stamp,
-            uint32_t occ_gen, int all_stamp, double act_on) {
+            uint32_t occ_gen, int all_stamp, double act_on, int cpar) {
+    pdl_begin();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
@@ -362,7 +372,7 @@ k_step_move(Params p, const int8_t *__restrict__ rot, const int8_t *__restrict__
     // a cell that holds no food and is outside the hill cannot change it and need not compete.
     if (all_stamp || f > 0.0 || hill) atomicMax(p.owner + (int64_t)e * p.plane + pcell, owner_stamp | (uint32_t)a);
     if (delta != 0.0) {
-        uint32_t slot = atomicAdd(p.commit_count, 1u);
+        uint32_t slot = atomicAdd(p.commit_count + cpar, 1u);
         p.commit_list[slot] = (uint32_t)i;
         p.food_delta[i] = delta;
     }
@@ -398,8 +408,10 @@ __global__ void __launch_bounds__(256) k_occ_stamp(Params p, uint32_t occ_gen) {
 // ------------------------------------------------------------------------------------------------ step, part 2
 // The winners of the food scatter write `old + (dropped - taken)` (ants.py:116); food that now lies inside the
 // anthill disc is queued for Anthill.update (anthill.py:41-46).
-__global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_stamp, int par) {
-    uint32_t n = *p.commit_count;
+__global__ void __launch_bounds__(128) k_food_commit(Params p, uint32_t owner_stamp, int par, int cpar) {
+    pdl_begin();
+    uint32_t n = p.commit_count[cpar];
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.commit_count[cpar ^ 1] = 0u;    // for the next step
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         int64_t i = p.commit_list[k];
         int e = (int)(i / p.N);
@@ -459,6 +471,7 @@ __global__ void __launch_bounds__(kPerceiveThreads, 6)
 k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
            double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
            int group, uint32_t s2_magic, int slow_wrap, uint32_t now, uint32_t now_abs) {
+    pdl_begin();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int S = p.S, S2 = p.S2, C = p.C;
     const int SC = S2 * C;
@@ -757,6 +770,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
 __global__ void __launch_bounds__(256)
 k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t owner_stamp, int finish, int use_flag,
           int par) {
+    pdl_begin();
     // Anthill.update (anthill.py:41-46) for the cells queued by k_food_commit: nothing else in the update reads the
     // food field, so the first blocks of this kernel absorb them; the other counter is zeroed for the next step.
     {
@@ -816,6 +830,7 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
 // touched ant-chunks, in ant order, adding the pushes with an ordered ballot loop -- the same summation order as
 // np.sum(axis=0); untouched ants contribute exact 0.  Then the rock's entries in the rock grid move with it.
 __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
+    pdl_begin();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (pair >= (int64_t)p.E * p.R) return;
@@ -869,6 +884,7 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
 
 // CircleObstacles.update, second half (circle_obstacles.py:53-58) + the ant part of Ants.update.
 __global__ void __launch_bounds__(256) k_rocks_push_ants(Params p, uint32_t owner_stamp) {
+    pdl_begin();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);
@@ -1063,6 +1079,7 @@ __global__ void __launch_bounds__(256) k_diffuse_commit(Params p) {
 // Ants.emit_pheromones -> Pheromone.add_pheromones (ants.py:98-100, pheromone.py:36-41): the owner of each cell
 // adds its activation and clamps to max_val.
 __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner_stamp, uint32_t now, uint32_t now_abs) {
+    pdl_begin();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.EN) return;
     int e = (int)(i / p.N);

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
 k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
                 double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
                 uint32_t now, uint32_t now_abs) {
+    pdl_begin();
     static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
     static_assert(kRowsGroup * S <= 32, "a chunk's rows must fit one warp");
     constexpr int S2 = S * S, C = (LAYOUT == 2) ? 7 : 6, SC = S2 * C;
