@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "ants_import_state", "ants_export_state", "ants_activate_all_pheromones", "ants_observe", "ants_step",
     "ants_update", "ants_rollout", "ants_host_alloc", "ants_host_free", "ants_observe_host", "ants_step_host",
     "ants_update_host", "ants_get_stats", "ants_set_profiling", "ants_get_kernel_ms", "ants_reset_kernel_ms",
+    "ants_sample_actions",
 ]
 
 
@@ -93,6 +94,7 @@ def load_library(path=None):
     lib.ants_step.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(i32)]
     lib.ants_update.argtypes = [vp, vp]
     lib.ants_rollout.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.ants_sample_actions.argtypes = [vp, C.c_uint64, i32, i32, vp, vp]
     lib.ants_host_alloc.argtypes = [C.c_uint64]
     lib.ants_host_alloc.restype = vp
     lib.ants_host_free.argtypes = [vp]

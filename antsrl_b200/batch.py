@@ -265,6 +265,19 @@ class BatchedAnts:
                                               self._ptr(o["obs"]), self._ptr(o["agent_state"]), self._ptr(o["reward"])))
         return o["obs"], o["agent_state"], o["reward"]
 
+    def sample_actions(self, seed, n_rotations=3, n_pheromones=3):
+        """The agents' exploration branch (collect_agent.py:172-177) drawn on the device: int8 CUDA tensors
+        rotation in {-(n//2) .. n - 1 - n//2} and pheromone in {0 .. n_pheromones-1}, shape (E, N)."""
+        import torch
+        if not hasattr(self, "_act_buf"):
+            shape = (self.E, self.N)
+            self._act_buf = (torch.empty(shape, dtype=torch.int8, device=self.device),
+                             torch.empty(shape, dtype=torch.int8, device=self.device))
+        rot, ph = self._act_buf
+        check(self.lib, self.lib.ants_sample_actions(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(n_rotations),
+                                                     int(n_pheromones), self._ptr(rot), self._ptr(ph)))
+        return rot, ph
+
     # ------------------------------------------------------------------ host-buffer path (numpy in / numpy out)
     def pinned(self, name, shape, dtype):
         """A page-locked numpy array owned by this object (ants_host_alloc)."""

@@ -923,6 +923,19 @@ int ants_rollout(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape
     return ANTS_OK;
 }
 
+int ants_sample_actions(AntsBatch *b, uint64_t seed, int32_t n_rotations, int32_t n_pheromones, int8_t *d_rot,
+                        int8_t *d_ph) {
+    if (!b) return fail(ANTS_E_ARG, "null handle");
+    if (n_rotations < 1 || n_rotations > 127 || n_pheromones < 1 || n_pheromones > 127)
+        return fail(ANTS_E_ARG, "ants_sample_actions: action counts must be in 1..127");
+    CK(cudaSetDevice(b->cfg.device));
+    const Params &p = b->p;
+    ants::k_sample_actions<<<(unsigned)cdiv(p.EN, 256), 256, 0, b->stream>>>(p, seed, (uint32_t)b->timestep, n_rotations,
+                                                                             n_pheromones, d_rot, d_ph);
+    b->stats.kernel_launches++;
+    return check_launch("k_sample_actions");
+}
+
 void *ants_host_alloc(uint64_t bytes) {
     void *ptr = nullptr;
     if (cudaHostAlloc(&ptr, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

@@ -276,6 +276,29 @@ __device__ __forceinline__ void pdl_begin() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// The exploration branch of the reference's agents (collect_agent.py:172-177): rotation = randint(0, n_rot) -
+// n_rot // 2, pheromone = randint(0, n_ph), per ant, drawn on the device so that neither observations nor actions cross
+// PCIe.  Philox4x32-10 with counter (ant, step, env, 1) -- word 3 separates the stream from the collision noise --
+// and key (seed_lo, seed_hi); value = (r * n) >> 32.  Mirrored by oracle.philox_actions.
+__global__ void __launch_bounds__(256)
+k_sample_actions(Params p, uint64_t seed, uint32_t step, int n_rot, int n_ph, int8_t *__restrict__ rot, int8_t *__restrict__ ph) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.EN) return;
+    const int e = (int)(i / p.N);
+    uint32_t c0 = (uint32_t)(i - (int64_t)e * p.N), c1 = step, c2 = (uint32_t)(p.env_id_base + e), c3 = 1u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    if (rot) rot[i] = (int8_t)((int)__umulhi(c0, (uint32_t)n_rot) - n_rot / 2);
+    if (ph) ph[i] = (int8_t)__umulhi(c1, (uint32_t)n_ph);
+}
+
 // shared -> global bulk copy through the async proxy (TMA 1-D bulk store, SASS UBLKCP)
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),

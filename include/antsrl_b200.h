@@ -161,6 +161,13 @@ int ants_update(AntsBatch *b, const double *d_noise);
 int ants_rollout(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape, int32_t n_steps,
                  float *d_obs, float *d_agent_state, double *d_reward);
 
+/* The exploration branch of the reference's agents (agents/collect_agent.py:172-177: rotation = randint(0,
+ * n_rotations) - n_rotations // 2, pheromone = randint(0, n_pheromones) per ant) drawn on the device into DEVICE
+ * int8 [E][N] buffers (either may be NULL), so a random-agent episode needs no host round trip.  Philox4x32-10
+ * keyed by (seed, env_id_base + e, timestep, ant): the draws do not depend on how envs are sharded. */
+int ants_sample_actions(AntsBatch *b, uint64_t seed, int32_t n_rotations, int32_t n_pheromones, int8_t *d_rot,
+                        int8_t *d_ph);
+
 /* Host-buffer variants (the reference-facing path: numpy in, numpy out).  Buffers obtained from
  * ants_host_alloc are pinned and are copied to/from directly; other host memory is staged. */
 void *ants_host_alloc(uint64_t bytes);

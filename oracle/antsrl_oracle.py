@@ -100,6 +100,31 @@ def philox_uniform(seed, env_id, step, n_ants):
     return (a * 67108864.0 + b) / 9007199254740992.0
 
 
+def philox_actions(seed, env_id, step, n_ants, n_rot=3, n_ph=3):
+    """Mirror of the CUDA path's on-device action sampler (ants_sample_actions; the agents' exploration branch,
+    collect_agent.py:172-177): Philox4x32-10, counter (ant, step, env_id, 1), value = (r * n) >> 32."""
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    W0, W1 = 0x9E3779B9, 0xBB67AE85
+    c0 = np.arange(n_ants, dtype=np.uint64)
+    c1 = np.full(n_ants, step & 0xFFFFFFFF, dtype=np.uint64)
+    c2 = np.full(n_ants, env_id & 0xFFFFFFFF, dtype=np.uint64)
+    c3 = np.ones(n_ants, dtype=np.uint64)
+    k0 = seed & 0xFFFFFFFF
+    k1 = (seed >> 32) & 0xFFFFFFFF
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c0
+        p1 = M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)), lo1, (hi0 ^ c3 ^ np.uint64(k1)), lo0
+        k0 = (k0 + W0) & 0xFFFFFFFF
+        k1 = (k1 + W1) & 0xFFFFFFFF
+    rot = ((c0 * np.uint64(n_rot)) >> np.uint64(32)).astype(np.int64) - n_rot // 2
+    ph = ((c1 * np.uint64(n_ph)) >> np.uint64(32)).astype(np.int64)
+    return rot, ph
+
+
 class OracleEnv:
     """One environment.  ``cfg`` from :func:`make_config`, ``state`` in the shared schema."""
 

@@ -412,3 +412,76 @@ def test_crowded_rocks_default_channels():
     for record, mode in (("compact", "lazy"), ("f64", "dense")):
         rep = run_parity(_variants(kw, 3), evap_mode=mode, record=record)
         assert rep["state_checks"] == kw["steps"]
+
+
+def test_device_action_sampler_matches_oracle_and_sharding():
+    """ants_sample_actions: the agents' exploration branch drawn on the device (Philox keyed by global env id, step,
+    ant) equals the oracle's mirror, covers the action ranges uniformly and does not depend on the sharding."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from oracle.antsrl_oracle import philox_actions
+    scen = [make_scenario(seed=990 + e, w=32, h=32, n_ants=96, steps=4) for e in range(4)]
+    cfg = scen[0][0]
+    whole = BatchedAnts(cfg, 4, evap_mode="lazy", record="compact", env_id_base=10)
+    whole.import_state(stack_init(cfg, [i for _, i, _ in scen]))
+    halves = [BatchedAnts(cfg, 2, evap_mode="lazy", record="compact", env_id_base=10 + 2 * k) for k in range(2)]
+    for k in range(2):
+        halves[k].import_state(stack_init(cfg, [i for _, i, _ in scen[2 * k:2 * k + 2]]))
+    whole.observe()
+    counts = np.zeros((3, 3))
+    for t in range(1, 6):
+        rot, ph = whole.sample_actions(seed=77)
+        rot_h = torch.cat([h.sample_actions(seed=77)[0] for h in halves]).cpu().numpy()
+        rot, ph = rot.cpu().numpy(), ph.cpu().numpy()
+        assert np.array_equal(rot, rot_h)
+        for e in range(4):
+            r_ref, p_ref = philox_actions(77, 10 + e, t, 96)
+            assert np.array_equal(rot[e], r_ref) and np.array_equal(ph[e], p_ref)
+        assert rot.min() == -1 and rot.max() == 1 and ph.min() == 0 and ph.max() == 2
+        for a in range(3):
+            for b_ in range(3):
+                counts[a, b_] += ((rot == a - 1) & (ph == b_)).sum()
+        whole.step(torch.from_numpy(rot.astype(np.int8)).cuda(), torch.from_numpy(ph.astype(np.int8)).cuda())
+        whole.update(None)
+        for h in halves:        # advance the timestep of the halves too (their own random walk)
+            r, p = h.sample_actions(seed=77)
+            h.step(r, p); h.update(None)
+    assert np.abs(counts / counts.sum() - 1 / 9).max() < 0.03
+    # five actions: rotation in {-2..2}
+    rot5, _ = whole.sample_actions(seed=3, n_rotations=5, n_pheromones=2)
+    assert int(rot5.min()) == -2 and int(rot5.max()) == 2
+    whole.close()
+    for h in halves:
+        h.close()
+
+
+def test_device_replay_memory_ring_buffer():
+    """DeviceReplayMemory (agents/replay_memory.py on device tensors): rolling write with wrap-around, the actions
+    layout (rotation, pheromone), sampling without replacement -- fed by a random-agent loop that never leaves HBM."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from antsrl_b200.replay import DeviceReplayMemory
+    scen = [make_scenario(seed=995 + e, w=32, h=32, n_ants=10, steps=4) for e in range(2)]
+    cfg = scen[0][0]
+    b = BatchedAnts(cfg, 2, evap_mode="lazy", record="compact")
+    b.import_state(stack_init(cfg, [i for _, i, _ in scen]))
+    mem = DeviceReplayMemory(50, (7, 7, 6), (2,), 2)
+    obs, ast, _, _ = b.observe()
+    obs, ast = obs.clone(), ast.clone()
+    log = []
+    for t in range(4):                                   # 4 x 20 entries into 50 slots: wraps once
+        rot, ph = b.sample_actions(seed=5)
+        new_obs, new_ast, rew, done = b.step(rot, ph)
+        mem.extend(obs, ast, (rot, ph), rew, new_obs, new_ast, done)
+        log.append((obs.reshape(20, 7, 7, 6).clone(), rot.reshape(-1).clone(), rew.reshape(-1).clone()))
+        b.update(None)
+        obs, ast = new_obs.clone(), new_ast.clone()
+    assert len(mem) == 50 and mem.head == 30
+    # slots 0..29 hold entries 50..79 (steps 2 (second half) and 3), slots 30..49 hold entries 30..49 (step 1 tail, step 2 head)
+    allobs = torch.cat([l[0] for l in log]); allrot = torch.cat([l[1] for l in log]); allrew = torch.cat([l[2] for l in log])
+    assert torch.equal(mem.states[:30], allobs[50:80]) and torch.equal(mem.states[30:], allobs[30:50])
+    assert torch.equal(mem.actions[:30, 0], allrot[50:80].float())
+    assert torch.allclose(mem.rewards[30:], allrew[30:50].float())
+    s = mem.random_access(16)
+    assert s[0].shape == (16, 7, 7, 6) and s[2].shape == (16, 2) and s[0].is_cuda
+    b.close()
