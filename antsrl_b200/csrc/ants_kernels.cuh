@@ -301,8 +301,12 @@ k_sample_actions(Params p, uint64_t seed, uint32_t step, int n_rot, int n_ph, in
 
 // shared -> global bulk copy through the async proxy (TMA 1-D bulk store, SASS UBLKCP)
 __device__ __forceinline__ void bulk_store_s2g(void *gdst, const void *ssrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst),
-                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+    // the observations are written once and never read by the step loop: evict-first keeps them from displacing
+    // cell records in L2 (measured: -1 % on the perception kernel)
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(pol)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
 }
