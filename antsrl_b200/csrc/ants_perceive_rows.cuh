@@ -48,22 +48,9 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2 (2^-22 rela
     return y;
 }
 
-// 16-byte record load; ANTS_LD_L2_128 asks L2 to fetch the whole 128-byte line (one x-row of an 8x8 block) on a miss
-__device__ __forceinline__ uint4 ld_record16(const uint8_t *rp) {
-#ifdef ANTS_LD_L2_128
-    uint4 v;
-    asm volatile("ld.global.L2::128B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rp));
-    return v;
-#elif defined(ANTS_LD_L2_64)
-    uint4 v;
-    asm volatile("ld.global.L2::64B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rp));
-    return v;
-#elif defined(ANTS_LD_NC)
-    return __ldg(reinterpret_cast<const uint4 *>(rp));
-#else
-    return *reinterpret_cast<const uint4 *>(rp);
-#endif
-}
+// 16-byte record load.  (Measured alternatives, all slower on the cfg4 shard: ld.global.L2::128B / L2::64B prefetch
+// sizes and the non-coherent path, 0.35 ms against 0.29 ms.)
+__device__ __forceinline__ uint4 ld_record16(const uint8_t *rp) { return *reinterpret_cast<const uint4 *>(rp); }
 
 // value of a pheromone field that is neither zero nor a live boxed deposit outside walls (rare): kept out of line
 __device__ __noinline__ float phero_obs_slow(const Params &p, const uint8_t *rp, int k, uint32_t now, uint32_t now_abs) {
@@ -375,9 +362,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
             fence_proxy_async_smem();
             __syncwarp();
-#ifndef ANTS_DBG_NOSTORE
             if (lane == 0) bulk_store_s2g(dst, wobs, bytes);
-#endif
         } else {
             __syncwarp();
             for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
