@@ -62,6 +62,8 @@ struct AntsBatch {
     int absorb_par = 0;             // which absorb counter the steps append under
     int commit_par = 0;             // which commit counter this step appends under
     int use_pdl = 0;                // programmatic dependent launch of the step kernels (large batches)
+    CUtensorMap plane_map;          // diffusion mode: {H, W, 2 * E * P} f64 over both pheromone planes, box 68 x 66 x 1
+    int plane_src = 0;              // which half of the plane allocation is current
     uint32_t lazy_now = 0;          // updates since the last fold of plain values (lazy evaporation), small counter
     uint32_t lazy_abs = 0;          // updates since creation / the last unboxing fold (22 bits)
     AntsStats stats;
@@ -354,13 +356,12 @@ int do_update(AntsBatch *b, const double *d_noise) {
             int nbx = (int)cdiv(p.W, ants::kStX), nby = (int)cdiv(p.H, ants::kStY);
             {
                 LaunchScope ls(b, F_EVAP);
-                ants::k_diffuse_stencil<<<(unsigned)((int64_t)nbx * nby * p.E * p.P), 256, 0, b->stream>>>(p, nbx, nby);
+                ants::k_diffuse_tma<<<(unsigned)((int64_t)nbx * nby * p.E * p.P), 256, 0, b->stream>>>(
+                    p, b->plane_map, b->plane_src * p.E * p.P, nbx, nby);
             }
-            TRY(check_launch("k_diffuse_stencil"));
-            {
-                LaunchScope ls(b, F_EVAP);
-                ants::k_diffuse_commit<<<148 * 8, 256, 0, b->stream>>>(p);
-            }
+            TRY(check_launch("k_diffuse_tma"));
+            std::swap(p.phero_pl, p.phero_alt);            // the stencil's output is the field from now on
+            b->plane_src ^= 1;
             b->stats.active_tiles = b->stats.total_tiles;
         } else if (b->cfg.evap_mode == ANTS_EVAP_ACTIVE_TILES) {
             CK(cudaMemsetAsync(p.tile_counter, 0, sizeof(unsigned long long), b->stream));
@@ -531,7 +532,11 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.mandibles, EN)); A(dev_alloc(b, &p.reward_state, EN));
     A(dev_alloc(b, &p.rw_holding_prev, EN)); A(dev_alloc(b, &p.rw_prev_dist, EN)); A(dev_alloc(b, &p.rewards, EN));
     A(dev_alloc(b, &p.cells, cells << p.rec_shift));
-    if (cfg->diffuse_factor != 0.0) A(dev_alloc(b, &p.phero_alt, cells * (p.P > 0 ? p.P : 1)));
+    p.diffuse = (cfg->diffuse_factor != 0.0 && p.P > 0) ? 1 : 0;
+    if (p.diffuse) {
+        A(dev_alloc(b, &p.phero_pl, 2 * cells * p.P));
+        p.phero_alt = p.phero_pl ? p.phero_pl + cells * p.P : nullptr;
+    }
     A(dev_alloc(b, &p.owner, cells));
     if (cfg->evap_mode == ANTS_EVAP_ACTIVE_TILES && cfg->diffuse_factor == 0.0)
     {
@@ -557,6 +562,30 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     uint8_t *d_mask = nullptr;
     A(dev_alloc(b, &d_off, p.S)); A(dev_alloc(b, &d_mask, p.S2));
     if (rc != ANTS_OK) { ants_destroy(b); return rc; }
+    if (p.diffuse) {
+        // tensor map over both planes: extents are the TRUE map size, so the TMA unit zero-fills the convolution's
+        // border (pheromone.py:44 boundary='fill'); the pitch is the padded row
+        typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            ants_destroy(b);
+            return fail(ANTS_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        }
+        const cuuint64_t dims[3] = {(cuuint64_t)p.H, (cuuint64_t)p.W, (cuuint64_t)(2 * (int64_t)p.E * p.P)};
+        const cuuint64_t strides[2] = {(cuuint64_t)p.Hp * 8, (cuuint64_t)p.plane * 8};
+        const cuuint32_t box[3] = {(cuuint32_t)(ants::kStY + 2 + ants::kStPadY), (cuuint32_t)(ants::kStX + 2), 1u};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        CUresult cr = ((EncodeFn)fn)(&b->plane_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)p.phero_pl, dims, strides,
+                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            ants_destroy(b);
+            return fail(ANTS_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        }
+    }
     {
         std::vector<double> off(p.S);
         std::vector<uint8_t> mk(p.S2, 1);
@@ -629,6 +658,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         for (int c = 0; ok && c < 6; ++c) ok = p.ch_kind[c] == std6[c];
         ok = ok && p.ch_arg[1] == 0 && p.ch_arg[2] == 1;
         if (ok && p.C == 7) ok = p.ch_kind[6] == ANTS_CH_ROCKS;
+        if (p.diffuse) ok = false;                     // the field lives in planes: generic channel code reads them
         b->perceive_layout = ok ? (p.C == 7 ? 2 : 1) : 0;
     }
     {   // the row-per-lane kernel serves the default channel lists with a 7x7 (default) or 5x5 window
@@ -758,6 +788,10 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         CK(cudaMemcpyAsync(d_tmp, s->walls, ncell, cudaMemcpyHostToDevice, st));
         ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 0);      // Walls.__init__: astype(bool)
         TRY(check_launch("k_pack_u8"));
+    }
+    if (p.diffuse && (s->walls || s->phero)) {         // the planes carry the wall bit in their sign
+        ants::k_plane_walls<<<148 * 8, 256, 0, st>>>(p);
+        TRY(check_launch("k_plane_walls"));
     }
     if (s->explored) {
         CK(cudaMemcpyAsync(d_tmp, s->explored, ncell, cudaMemcpyHostToDevice, st));

@@ -16,6 +16,7 @@
 // All position / angle / sample-coordinate arithmetic is f64 in the reference's operation order (compiled with
 // -fmad=false) so that truncated / rounded cell indices agree with numpy.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -62,7 +63,11 @@ struct Params {
     // map
     uint8_t *cells;                        // [E][W][Hp] records
     uint32_t *owner;                       // [E][W][Hp]
-    double *phero_alt;                     // [E][P][W][Hp] scratch of the diffusion stencil (DIFFUSE_FACTOR != 0)
+    // DIFFUSE_FACTOR != 0: the pheromone field lives in two row-major f64 planes [E][P][Wp][Hp] (ping-pong: the 3x3
+    // stencil reads `phero_pl` through TMA and writes `phero_alt`, then the host swaps them); the sign bit of a plane
+    // value is the cell's wall bit (walls.py:30 zeroes the stencil's inputs in wall cells), its magnitude the value
+    double *phero_pl, *phero_alt;
+    int32_t diffuse;
     uint8_t *tile_active;                  // [E][tiles_x][tiles_y]
     int32_t *hill;                         // [E][4] = x, y, r, r*r
     double *hill_food;                     // [E]
@@ -250,6 +255,12 @@ __device__ __forceinline__ void phero_store(const Params &p, uint8_t *r, int k, 
         if (v != 0.0 && *p.plain_flag == 0u) *p.plain_flag = 1u;
     }
 }
+
+// diffusion mode: plane accessors
+__device__ __forceinline__ double *plane_at(const Params &p, int e, int k, int x, int y) {
+    return p.phero_pl + ((int64_t)e * p.P + k) * p.plane + (int64_t)x * p.Hp + y;
+}
+__device__ __forceinline__ double plane_value(const Params &p, int e, int k, int x, int y) { return fabs(*plane_at(p, e, k, x, y)); }
 
 // Philox4x32-10, counter (ant, step, env, 0), key (seed_lo, seed_hi) -> one double in [0,1) built like
 // numpy's random_sample: ((a >> 5) * 2^26 + (b >> 6)) / 2^53.  Mirrored by oracle.philox_uniform.
@@ -725,7 +736,8 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                         double v;
                         switch (p.ch_kind[c]) {
                             case 0: v = (occ == occ_gen) ? 1.0 : 0.0; break;
-                            case 1: v = phero_value(p, rp[u], p.ch_arg[c], now, now_abs) * inv_max; break;
+                            case 1: v = (p.diffuse ? plane_value(p, q.e, p.ch_arg[c], ix, iy)
+                                                   : phero_value(p, rp[u], p.ch_arg[c], now, now_abs)) * inv_max; break;
                             case 2: v = hill ? 1.0 : 0.0; break;
                             case 3: v = wl ? 1.0 : 0.0; break;
                             case 4: v = (double)fdf; break;
@@ -1052,54 +1064,100 @@ __global__ void __launch_bounds__(256) k_evaporate_tiles(Params p, const uint32_
     }
 }
 
-// Diffusion stencil for DIFFUSE_FACTOR != 0 (pheromone.py:44, 3x3 zero-filled convolution) with the wall
-// zeroing of walls.py:30 applied to the inputs, threshold and clamp; reads the records, writes `phero_alt`
-// (k_diffuse_commit copies it back).  Tile of 32 x 32 outputs per block, halo staged in shared memory.
-constexpr int kStX = 32, kStY = 32;
-__global__ void __launch_bounds__(256) k_diffuse_stencil(Params p, int nbx, int nby) {
-    __shared__ double tile[kStX + 2][kStY + 2 + 1];
+// Diffusion stencil for DIFFUSE_FACTOR != 0 (pheromone.py:43-45: 3x3 convolution, boundary='fill', fillvalue=0, then
+// the < 0.01 cut) with the wall zeroing of walls.py:30 applied to its inputs and the whole-plane clamp of
+// pheromone.py:41.  One block = 64 x 64 outputs of one pheromone plane of one environment.  The (66 x 66) input tile
+// with its halo arrives by ONE TMA tiled load (cp.async.bulk.tensor.3d, SASS UTMALDG) from the tensor map over the
+// planes: the map's extents are the true (H, W), so everything outside the map -- the convolution's zero fill -- is
+// filled with zeros by the TMA unit, also for negative coordinates; no bounds logic in the kernel.  Wall cells carry
+// their flag in the sign bit: fmax(v, 0) is the zeroed input.  Output goes to the other plane, coalesced.
+// (The innermost start coordinate of a tiled load must be 16-byte aligned -- an odd f64 coordinate is an illegal
+// instruction, scripts/microbench/tma_probe.cu -- so the box starts two columns left of the tile: 66 x 68.)
+// tile shape (measured on 1024 envs x 256^2, 2 pheromones, ms per update): 32x32 0.488, 16x64 0.474, 8x128 0.468,
+// 64x32 0.407, 128x32 0.360, 64x64 0.354 (= 0.96 of the measured HBM copy peak)
+#ifndef ANTS_ST_X
+#define ANTS_ST_X 64
+#define ANTS_ST_Y 64
+#endif
+constexpr int kStX = ANTS_ST_X, kStY = ANTS_ST_Y, kStPadY = 2;
+// Arithmetic: a warp owns 32 columns and a few consecutive output rows; a thread slides down its column
+// keeping per input row the three clipped values (left, centre, right), their sum and the sum of the two sides, so an
+// output costs 3 shared-memory loads and ~10 f64 operations instead of 9 and 27:
+//     out = ring * (rowsum[x-1] + sides[x] + rowsum[x+1]) + centre_tap * v[x][y]
+// (pheromone.py:7-9: the ring taps are all DIFFUSE_FACTOR (1 - EVAP), the centre is (1 - 8 DIFFUSE_FACTOR)(1 - EVAP);
+// the summation order differs from scipy's, inside the 1e-5 bar, golden scenario `diffuse`).
+__global__ void __launch_bounds__(256)
+k_diffuse_tma(Params p, const __grid_constant__ CUtensorMap tmap, int src_z0, int nbx, int nby) {
+    __shared__ __align__(128) double tile[kStX + 2][kStY + 2 + kStPadY];
+    __shared__ __align__(8) unsigned long long bar;
     const int64_t ep = blockIdx.x / (nbx * nby);
     const int brem = (int)(blockIdx.x - ep * (nbx * nby));
-    const int e = (int)(ep / p.P), k = (int)(ep - (int64_t)e * p.P);
     const int x0 = (brem / nby) * kStX, y0 = (brem % nby) * kStY;
-    for (int t = threadIdx.x; t < (kStX + 2) * (kStY + 2); t += blockDim.x) {
-        int lx = t / (kStY + 2), ly = t - lx * (kStY + 2);
-        int gx = x0 + lx - 1, gy = y0 + ly - 1;
-        double v = 0.0;
-        if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H) {
-            uint8_t *r = rec_at(p, e, cidx(p, gx, gy));
-            v = (*rec_wall(p, r) & 1) ? 0.0 : *rec_phero(r, k);
-        }
-        tile[lx][ly] = v;
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(&bar);
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        constexpr uint32_t bytes = (kStX + 2) * (kStY + 2 + kStPadY) * sizeof(double);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(tile_s), "l"(&tmap), "r"(y0 - kStPadY), "r"(x0 - 1), "r"(src_z0 + (int)ep), "r"(bar_s) : "memory");
+    }
+    if (threadIdx.x == 0) {   // one thread polls the barrier (phase 0); the block barrier hands the tile to the others
+        uint32_t done = 0;    // (all 256 threads polling cost 3/4 of the kernel's issue slots in ncu)
+        while (!done)
+            asm volatile("{\n .reg .pred q;\n mbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n selp.u32 %0, 1, 0, q;\n}"
+                         : "=r"(done) : "r"(bar_s) : "memory");
     }
     __syncthreads();
     const double fc = p.filt_center, fr = p.filt_ring, mx = p.phero_max_val;
     const bool clamp = p.has_max_val && p.N > 0;
-    double *dst = p.phero_alt + ep * p.plane;
-    for (int t = threadIdx.x; t < kStX * kStY; t += blockDim.x) {
-        int lx = t / kStY, ly = t - lx * kStY;
-        int gx = x0 + lx, gy = y0 + ly;
-        if (gx >= p.W || gy >= p.H) continue;
-        double acc = 0.0;
+    constexpr int CG = kStY / 32;                      // column groups of 32 lanes
+    constexpr int RPW = kStX * CG / 8;                 // output rows per warp (8 warps)
+    const int warp = threadIdx.x >> 5, ly = (threadIdx.x & 31) + 32 * (warp % CG);
+    const int gy = y0 + ly;
+    const int lx0 = (warp / CG) * RPW;                 // first output row of this warp (tile row lx0 + 1)
+    double *dst = p.phero_alt + ep * p.plane + gy;
+    // tile column of (gy - 1): ly + kStPadY - 1
+    const int c = ly + kStPadY - 1;
+    double rs[RPW + 2], sd[RPW + 2], ce[RPW + 2];      // row sums, side sums, centres (raw centre keeps the wall sign)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
+    for (int r = 0; r < RPW + 2; ++r) {
+        const double a = fmax(tile[lx0 + r][c], 0.0), raw = tile[lx0 + r][c + 1], b2 = fmax(tile[lx0 + r][c + 2], 0.0);
+        const double m = fmax(raw, 0.0);
+        sd[r] = a + b2;
+        rs[r] = sd[r] + m;
+        ce[r] = raw;
+    }
+    if (gy < p.H) {
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
-                acc += tile[lx + dx][ly + dy] * ((dx == 1 && dy == 1) ? fc : fr);
-        acc = acc < 0.01 ? 0.0 : acc;
-        if (clamp) acc = fmin(acc, mx);
-        dst[(int64_t)gx * p.Hp + gy] = acc;
+        for (int r = 0; r < RPW; ++r) {
+            const int gx = x0 + lx0 + r;
+            if (gx >= p.W) break;
+            double acc = (rs[r] + sd[r + 1] + rs[r + 2]) * fr + fmax(ce[r + 1], 0.0) * fc;
+            acc = acc < 0.01 ? 0.0 : acc;
+            if (clamp) acc = fmin(acc, mx);
+            dst[(int64_t)gx * p.Hp] = signbit(ce[r + 1]) ? -acc : acc;
+        }
     }
 }
-__global__ void __launch_bounds__(256) k_diffuse_commit(Params p) {
+// after an import: the sign bit of every plane value = the wall bit of its cell record
+__global__ void k_plane_walls(Params p) {
     const int64_t n = (int64_t)p.E * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
-        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        for (int k = 0; k < p.P; ++k) *rec_phero(r, k) = p.phero_alt[(e * p.P + k) * p.plane + (int64_t)x * p.Hp + y];
+        const bool wall = ld_wall(p, rec_at(p, (int)e, cidx(p, x, y)));
+        for (int k = 0; k < p.P; ++k) {
+            double *pv = plane_at(p, (int)e, k, x, y);
+            const double a = fabs(*pv);
+            *pv = wall ? -a : a;
+        }
     }
 }
 
@@ -1114,6 +1172,18 @@ __global__ void __launch_bounds__(256) k_deposit_commit(Params p, uint32_t owner
     int cx = cell_of(p.x[i], p.W), cy = cell_of(p.y[i], p.H);
     int cell = cidx(p, cx, cy);
     if (p.owner[(int64_t)e * p.plane + cell] != (owner_stamp | (uint32_t)a)) return;
+    if (p.diffuse) {                                                           // planes: magnitude = value, sign = wall
+        for (int k = 0; k < p.P; ++k) {
+            const double av = p.act[(int64_t)k * p.EN + i];
+            if (av == 0.0) continue;
+            double *pv = plane_at(p, e, k, cx, cy);
+            const double old = *pv;
+            double v = fabs(old) + av;
+            if (p.has_max_val) v = fmin(v, p.phero_max_val);
+            *pv = signbit(old) ? -v : v;
+        }
+        return;
+    }
     uint8_t *r = rec_at(p, e, cell);
     bool wrote = false;
     for (int k = 0; k < p.P; ++k) {
@@ -1168,7 +1238,9 @@ __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int plane
         int x = (int)(ex - e * p.W);
         double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        if (phero_k >= 0) {
+        if (phero_k >= 0 && p.diffuse) {
+            *plane_at(p, (int)e, phero_k, x, y) = v;                           // (k_plane_walls sets the sign afterwards)
+        } else if (phero_k >= 0) {
             if (p.lazy && p.has_max_val) v = fmin(v, p.phero_max_val);         // pheromone.py:41 (applied at import)
             phero_store(p, r, phero_k, v, now, now_abs);
         } else {
@@ -1185,7 +1257,8 @@ __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_pe
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        double v = phero_k >= 0 ? phero_value(p, r, phero_k, now, now_abs) : ld_food(p, r);
+        double v = phero_k >= 0 ? (p.diffuse ? plane_value(p, (int)e, phero_k, x, y) : phero_value(p, r, phero_k, now, now_abs))
+                                : ld_food(p, r);
         dense[((e * planes_per_env + k) * p.W + x) * p.H + y] = v;
     }
 }
