@@ -1,18 +1,22 @@
 // ants_kernels.cuh -- sm_100a device code of the AntsRL step loop (one batch of E independent environments).
 //
 // Design.  Ant-centric flat kernels over all E*N ants; the map of every environment is ONE array
-// of cell records (array of structures), sized so that a cell is exactly one 32-byte DRAM sector for the
-// reference's two pheromones:
-//     record (P <= 2: 32 B, P <= 4: 64 B) = { f64 phero[P]; f64 food; u32 meta; u8 wall; pad }
-//     meta = (occ_gen << 16) | explored_gen
-// A perception sample therefore costs one sector and two 128-bit loads instead of five scattered plane reads.
+// of cell records (array of structures) stored in 8 x 8-cell blocks, in one of two formats:
+//     F64      (P <= 2: 32 B = one DRAM sector, P <= 4: 64 B)  { f64 phero[P]; f64 food; u32 meta; u8 wall|hill<<1; ts }
+//              meta = (occ_gen << 16) | explored_gen
+//     COMPACT  16 B = half a sector, the whole cell in one 128-bit load (lazy field, P <= 2)
+//              { f32 phero0; f32 phero1; f32 food; u8 hill<<7|occ_gen; u8 wall<<7|explored_gen; u8 ts0; u8 ts1 }
+// so a perception sample costs one load instead of five scattered plane reads.  (With DIFFUSE_FACTOR != 0 the
+// pheromone field lives in two row-major f64 planes instead, for the TMA-tiled stencil: k_diffuse_tma.)
 // The reference's "last writer wins" fancy-index scatters (quirk Q1: ants.py:116, pheromone.py:39,
 // RL_api.py:141) and its gather-before-scatter exploration reward (Q7: reward_custom.py:89-93) are resolved
 // without per-environment barriers through generation stamps:
 //   owner[e][x][y] : u32 = (phase << 16) | ant   written with atomicMax -> the highest ant index of the current
 //                    scatter phase owns the cell (food pickup/drop, pheromone deposit)
-//   meta.occ_gen == current step                  => an ant stands on the cell ("ants" perception channel)
-//   meta.explored_gen == 0 or == this observation => the cell was unexplored before this observation
+//   occ_gen == current step                       => an ant stands on the cell ("ants" perception channel)
+//   explored_gen == 0 or == this observation      => the cell was unexplored before this observation
+// The dominant kernel for the generator's channel lists is in ants_perceive_rows.cuh; k_perceive below is the
+// general one (any perceived_objects list, any radius, tiny maps).
 // All position / angle / sample-coordinate arithmetic is f64 in the reference's operation order (compiled with
 // -fmad=false) so that truncated / rounded cell indices agree with numpy.
 #pragma once
