@@ -877,13 +877,15 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t pair = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     if (pair >= (int64_t)p.E * p.R) return;
-    uint32_t tm = p.rock_touch[pair];
-    if (tm == 0u) return;
+    // the rock's data is requested together with its touch word: one memory round trip instead of three for a touched
+    // rock (the arrays are small and L2-resident; an untouched rock wastes 40 bytes of L2 traffic)
     const int e = (int)(pair / p.R), r = (int)(pair - (int64_t)e * p.R);
-    const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
     double *rc = p.rock_c + (int64_t)e * p.R * 2;
+    uint32_t tm = p.rock_touch[pair];
+    const double cx = rc[2 * r], cy = rc[2 * r + 1], rad = p.rock_rad[pair], wt = p.rock_w[pair];
+    if (tm == 0u) return;
+    const double *xs = p.x + (int64_t)e * p.N, *ys = p.y + (int64_t)e * p.N;
     const int G = ((p.N + 31) / 32 + 31) / 32 * 32;
-    const double cx = rc[2 * r], cy = rc[2 * r + 1], rad = p.rock_rad[pair];
     double sx = 0.0, sy = 0.0;
     while (tm) {
         const int g = __ffs(tm) - 1;
@@ -911,7 +913,6 @@ __global__ void __launch_bounds__(256) k_rocks_pushed(Params p) {
         }
     }
     // every lane holds the same sums
-    const double wt = p.rock_w[pair];
     const double nx = cx - sx / wt, ny = cy - sy / wt;
     if (lane == 0) {
         rc[2 * r] = nx;
