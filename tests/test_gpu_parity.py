@@ -490,3 +490,12 @@ def test_device_replay_memory_ring_buffer():
     s = mem.random_access(16)
     assert s[0].shape == (16, 7, 7, 6) and s[2].shape == (16, 2) and s[0].is_cuda
     b.close()
+
+
+@pytest.mark.parametrize("record", ["compact", "f64"])
+def test_long_run_crosses_generation_folds(record):
+    """300 steps against the oracle: the 7-bit occupancy / exploration generation counters of the compact records fold
+    twice (every ~125 steps), the double-buffered commit / absorb counters alternate 300 times."""
+    kw = dict(seed=41, w=64, h=56, n_ants=48, n_rocks=3, steps=300, n_walls=5, n_food=8)
+    rep = run_parity(_variants(kw, 2), evap_mode="lazy", record=record, state_every=25)
+    assert rep["steps"] == 300
