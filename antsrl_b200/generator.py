@@ -133,9 +133,13 @@ class BatchedEnvironmentGenerator:
                                self.walls_generator, seed=self.seed_base + first_env + e) for e in range(n_envs)]
 
     def generate(self, n_envs, device=0, first_env=0, float_activation=True, **batch_kw):
-        batch_kw.setdefault("evap_mode", "lazy")
-        """-> BatchedAnts holding envs [first_env, first_env + n_envs) (global ids, for sharding)."""
+        """-> BatchedAnts holding envs [first_env, first_env + n_envs) (global ids, for sharding).  Defaults to the
+        fast field representation the configuration allows: lazy decay and, for one or two pheromones without
+        diffusion, the compact 16-byte cell records."""
         from .batch import BatchedAnts
+        batch_kw.setdefault("evap_mode", "lazy")
+        if self.cfg.get("diffuse_factor", 0.0) == 0.0 and 1 <= self.n_pheromones <= 2 and batch_kw["evap_mode"] == "lazy":
+            batch_kw.setdefault("record", "compact")
         states = self.generate_states(n_envs, first_env)
         batch = BatchedAnts(self.cfg, n_envs, device=device, env_id_base=first_env, **batch_kw)
         batch.import_state(stack_states(states, self.cfg["reward_kind"]))
