@@ -658,7 +658,6 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         for (int c = 0; ok && c < 6; ++c) ok = p.ch_kind[c] == std6[c];
         ok = ok && p.ch_arg[1] == 0 && p.ch_arg[2] == 1;
         if (ok && p.C == 7) ok = p.ch_kind[6] == ANTS_CH_ROCKS;
-        if (p.diffuse) ok = false;                     // the field lives in planes: generic channel code reads them
         b->perceive_layout = ok ? (p.C == 7 ? 2 : 1) : 0;
     }
     {   // the row-per-lane kernel serves the default channel lists with a 7x7 (default) or 5x5 window

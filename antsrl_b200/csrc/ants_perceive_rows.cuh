@@ -190,7 +190,10 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const int nby64 = p.nby << 6;
     const uint32_t tab_len = (uint32_t)p.tab_len;
     const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
-    const bool any_plain = !p.lazy || *p.plain_flag != 0u;          // plain (non-boxed) pheromone values may exist
+    const bool eager = !REC16 && !p.lazy;                           // f64 fields hold plain current values (no decay on read)
+    const bool eager_planes = eager && p.diffuse != 0;              // ... in the diffusion planes (sign bit = wall)
+    const double inv_max = 1.0 / p.phero_max_val;
+    const bool any_plain = !eager && *p.plain_flag != 0u;           // lazy field: plain (non-boxed) values may exist
     // boxed deposit b = box | t: (box | now) - b = now - t = age; zero and plain values give an "age" >= 2^22
     const uint32_t nowb = REC16 ? box32(now_abs) : (now_abs & kBoxMask);
     const uint32_t ogs = obs_gen << 8;
@@ -230,6 +233,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
             const int e = q.e;
             const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << (REC16 ? 4 : 5));
+            const double *plane0 = eager_planes ? p.phero_pl + (int64_t)e * 2 * p.plane : nullptr;   // [e][k = 0, 1]
             const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
             const int flags = q.flags;
             uint32_t rbits = 0u;                                       // bit j: a rock covers the sample at column j
@@ -251,7 +255,14 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         // cidx(): 8 x 8 blocks of 64 records
                         cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
                         const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
-                        lo[u] = ld_record16(rp);
+                        if (!REC16 && eager_planes) {  // diffusion: the two pheromone values come from the row-major planes
+                            const double *pv = plane0 + (int64_t)ix * p.Hp + iy;
+                            const double d0 = pv[0], d1 = pv[p.plane];
+                            lo[u] = make_uint4((uint32_t)__double2loint(d0), (uint32_t)__double2hiint(d0) & 0x7FFFFFFFu,
+                                               (uint32_t)__double2loint(d1), (uint32_t)__double2hiint(d1) & 0x7FFFFFFFu);
+                        } else {
+                            lo[u] = ld_record16(rp);
+                        }
                         if (!REC16) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
                     }
                 }
@@ -314,8 +325,12 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
                         // cut is the exact table length; inside a wall only a deposit of this very update shows.
                         const uint32_t lim = wl ? 1u : tab_len;
-                        const float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
-                        const float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                        float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
+                        float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                        if (!REC16 && eager) {         // eager f64 fields (dense / tiles / diffusion): phero / max_val
+                            v1 = (float)(__hiloint2double((int)lo[u].y, (int)lo[u].x) * inv_max);
+                            v2 = (float)(__hiloint2double((int)lo[u].w, (int)lo[u].z) * inv_max);
+                        }
                         const float v0 = occupied ? 1.f : 0.f;                                   // :136-142
                         const float v3 = hill ? 1.f : 0.f;                                       // :130-131 (disc bit of the record)
                         const float v4 = wl ? 1.f : 0.f;                                         // :128-129
