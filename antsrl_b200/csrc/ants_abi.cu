@@ -468,7 +468,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     p.Wp = (int)(cdiv(cfg->w, 16) * 16);
     p.nby = p.Hp / 8;
     p.EN = (int64_t)p.E * p.N;
-    b->use_pdl = p.EN >= 131072 ? 1 : 0;
+    b->use_pdl = (p.EN >= 131072 || getenv("ANTS_FORCE_PDL")) ? 1 : 0;   // (ANTS_FORCE_PDL: the parity tests under PDL)
     p.plane = (int64_t)p.Wp * p.Hp;
     p.radius = cfg->radius; p.S = 2 * cfg->radius + 1; p.S2 = p.S * p.S; p.C = cfg->n_channels;
     p.has_mask = cfg->has_mask;

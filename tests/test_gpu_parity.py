@@ -499,3 +499,13 @@ def test_long_run_crosses_generation_folds(record):
     kw = dict(seed=41, w=64, h=56, n_ants=48, n_rocks=3, steps=300, n_walls=5, n_food=8)
     rep = run_parity(_variants(kw, 2), evap_mode="lazy", record=record, state_every=25)
     assert rep["steps"] == 300
+
+
+def test_parity_with_programmatic_dependent_launch(monkeypatch):
+    """Large batches launch the step kernels with programmatic stream serialisation (each kernel may be scheduled while
+    its predecessor drains and waits for it with griddepcontrol.wait); the parity batches are small, so force it."""
+    monkeypatch.setenv("ANTS_FORCE_PDL", "1")
+    for name in ("rocks", "crowded", "default_small"):
+        kw = dict(GOLDEN_SCENARIOS)[name]
+        rep = run_parity(_variants(kw, 3), evap_mode="lazy", record="compact")
+        assert rep["state_checks"] == kw["steps"]
