@@ -11,7 +11,7 @@ MAX_PHERO, MAX_CHANNELS, MAX_RADIUS, MAX_SAMPLES, MAX_ROCKS, MAX_ANTS = 4, 16, 7
 CH_ANTS, CH_PHERO, CH_ANTHILL, CH_WALLS, CH_FOOD, CH_ROCKS = range(6)
 REWARD_ALL, REWARD_EXPLORE, REWARD_FOOD = range(3)
 EVAP_DENSE, EVAP_ACTIVE_TILES, EVAP_LAZY = 0, 1, 2
-REC_F64, REC_COMPACT = 0, 1
+REC_F64, REC_COMPACT, REC_COMPACT8 = 0, 1, 2
 
 EXPORTED_SYMBOLS = [
     "ants_abi_version", "ants_last_error", "ants_create", "ants_destroy", "ants_set_stream", "ants_synchronize",

@@ -92,7 +92,7 @@ def build_c_config(cfg, n_envs, device=0, evap_mode="dense", rng_seed=0, env_id_
     c.max_hold = cfg["max_hold"]
     c.rng_seed, c.env_id_base = int(rng_seed), int(env_id_base)
     c.evap_mode = _EVAP_MODES[evap_mode]
-    c.record_format = {"f64": _cabi.REC_F64, "compact": _cabi.REC_COMPACT}[record]
+    c.record_format = {"f64": _cabi.REC_F64, "compact": _cabi.REC_COMPACT, "compact8": _cabi.REC_COMPACT8}[record]
     return c
 
 

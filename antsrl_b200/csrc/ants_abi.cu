@@ -188,7 +188,7 @@ int check_launch(const char *what) {
 // every live exploration stamp into "explored long ago" and clears the occupancy stamps.  Called at the start of
 // observe / step, before any stamp of the new generation is written.
 void maybe_fold_generations(AntsBatch *b) {
-    const uint32_t obs_lim = b->p.explored_old - 2u, occ_lim = b->p.rec16 ? 0x7Eu : 0xFFFEu;
+    const uint32_t obs_lim = b->p.explored_old - 2u, occ_lim = (b->p.rec16 || b->p.rec8) ? 0x7Eu : 0xFFFEu;
     if (b->obs_gen + 1u >= obs_lim || b->occ_gen + 1u >= occ_lim) {
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 16, 256, 0, b->stream>>>(b->p, 1, 1);
@@ -205,7 +205,7 @@ uint32_t next_obs_gen(AntsBatch *b) {
     return ++b->obs_gen;
 }
 uint32_t next_occ_gen(AntsBatch *b) {
-    if (b->occ_gen >= (b->p.rec16 ? 0x7Eu : 0xFFFEu)) {
+    if (b->occ_gen >= ((b->p.rec16 || b->p.rec8) ? 0x7Eu : 0xFFFEu)) {
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 0, 1);
         b->occ_gen = 0;
@@ -238,8 +238,9 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
                 b->rw_alias, b->lazy_now, b->lazy_abs)
 #define ANTS_ROWS_S(SS)                                                                          \
     do {                                                                                         \
-        if (p.rec16) { if (layout == 2) ANTS_ROWS(2, true, SS); else ANTS_ROWS(1, true, SS); }  \
-        else { if (layout == 2) ANTS_ROWS(2, false, SS); else ANTS_ROWS(1, false, SS); }        \
+        if (p.rec8) { if (layout == 2) ANTS_ROWS(2, 2, SS); else ANTS_ROWS(1, 2, SS); }         \
+        else if (p.rec16) { if (layout == 2) ANTS_ROWS(2, 1, SS); else ANTS_ROWS(1, 1, SS); }   \
+        else { if (layout == 2) ANTS_ROWS(2, 0, SS); else ANTS_ROWS(1, 0, SS); }                \
     } while (0)
             if (p.S == 7) ANTS_ROWS_S(7); else ANTS_ROWS_S(5);
 #undef ANTS_ROWS_S
@@ -249,7 +250,9 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
     launch_step(b, ants::k_perceive<L, R16>, (unsigned)blocks, (unsigned)threads, (size_t)b->perceive_smem, \
                 p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step, b->rw_alias, b->perceive_group, \
                 magic, b->perceive_slow_wrap, b->lazy_now, b->lazy_abs)
-        if (p.rec16) {
+        if (p.rec8) {                  // served through the generic channel code (accessor-based decode)
+            ANTS_PERCEIVE(0, false);
+        } else if (p.rec16) {
             if (layout == 1) ANTS_PERCEIVE(1, true);
             else if (layout == 2) ANTS_PERCEIVE(2, true);
             else ANTS_PERCEIVE(0, true);
@@ -342,12 +345,14 @@ int do_update(AntsBatch *b, const double *d_noise) {
     if (p.P > 0) {
         if (p.lazy) {
             // no pass over the field: values are evaluated at read time from their write timestamps
-            const bool unbox = b->lazy_abs >= ants::kBoxMask - 2u;
+            // (8-byte records keep 15 bits of the deposit step: expired deposits are cleared every 16384 updates,
+            //  before an age of tab_len <= 16384 could alias; the step counter itself keeps running)
+            const bool unbox = p.rec8 ? ((b->lazy_abs & 0x3FFFu) == 0x3FFFu) : (b->lazy_abs >= ants::kBoxMask - 2u);
             if (b->lazy_now >= p.ts_mask - 1u || unbox) {     // fold before a counter wraps
                 LaunchScope ls(b, F_EVAP);
                 ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now, b->lazy_abs, unbox ? 1 : 0);
                 b->lazy_now = 0;
-                if (unbox) b->lazy_abs = 0;
+                if (unbox && !p.rec8) b->lazy_abs = 0;
             }
             b->lazy_now += 1;
             b->lazy_abs += 1;
@@ -496,6 +501,12 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
             return fail(ANTS_E_ARG, "compact records need evap_mode LAZY, no diffusion and 1 or 2 pheromones");
         }
         p.rec16 = 1; p.rec_shift = 4; p.ts_mask = 0xFFu; p.explored_old = 0x7Fu;
+    } else if (cfg->record_format == ANTS_REC_COMPACT8) {
+        if (!(cfg->evap_mode == ANTS_EVAP_LAZY && cfg->diffuse_factor == 0.0 && p.P >= 1 && p.P <= 2)) {
+            ants_destroy(b);
+            return fail(ANTS_E_ARG, "compact records need evap_mode LAZY, no diffusion and 1 or 2 pheromones");
+        }
+        p.rec8 = 1; p.rec_shift = 3; p.ts_mask = 0xFFu; p.explored_old = 0x7Fu;
     } else if (cfg->record_format != ANTS_REC_F64) {
         int bad = cfg->record_format;
         ants_destroy(b);
@@ -532,6 +543,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.mandibles, EN)); A(dev_alloc(b, &p.reward_state, EN));
     A(dev_alloc(b, &p.rw_holding_prev, EN)); A(dev_alloc(b, &p.rw_prev_dist, EN)); A(dev_alloc(b, &p.rewards, EN));
     A(dev_alloc(b, &p.cells, cells << p.rec_shift));
+    if (p.rec8) { A(dev_alloc(b, &p.side_val, cells * 3)); A(dev_alloc(b, &p.side_ts, cells * 2)); }
     p.diffuse = (cfg->diffuse_factor != 0.0 && p.P > 0) ? 1 : 0;
     if (p.diffuse) {
         A(dev_alloc(b, &p.phero_pl, 2 * cells * p.P));
@@ -668,11 +680,13 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
                        ants::kRowsThreads * (int)sizeof(ants::RowPrep) + ants::kRowsThreads * p.S;
     }
     if (b->perceive_rows && b->rows_smem > 48 * 1024) {
-        const void *fns[8] = {(const void *)ants::k_perceive_rows<1, false, 7>, (const void *)ants::k_perceive_rows<2, false, 7>,
-                              (const void *)ants::k_perceive_rows<1, true, 7>, (const void *)ants::k_perceive_rows<2, true, 7>,
-                              (const void *)ants::k_perceive_rows<1, false, 5>, (const void *)ants::k_perceive_rows<2, false, 5>,
-                              (const void *)ants::k_perceive_rows<1, true, 5>, (const void *)ants::k_perceive_rows<2, true, 5>};
-        for (int k = 0; k < 8; ++k)
+        const void *fns[12] = {(const void *)ants::k_perceive_rows<1, 0, 7>, (const void *)ants::k_perceive_rows<2, 0, 7>,
+                               (const void *)ants::k_perceive_rows<1, 1, 7>, (const void *)ants::k_perceive_rows<2, 1, 7>,
+                               (const void *)ants::k_perceive_rows<1, 2, 7>, (const void *)ants::k_perceive_rows<2, 2, 7>,
+                               (const void *)ants::k_perceive_rows<1, 0, 5>, (const void *)ants::k_perceive_rows<2, 0, 5>,
+                               (const void *)ants::k_perceive_rows<1, 1, 5>, (const void *)ants::k_perceive_rows<2, 1, 5>,
+                               (const void *)ants::k_perceive_rows<1, 2, 5>, (const void *)ants::k_perceive_rows<2, 2, 5>};
+        for (int k = 0; k < 12; ++k)
             if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, b->rows_smem) != cudaSuccess) {
                 ants_destroy(b);
                 return fail(ANTS_E_CUDA, "k_perceive_rows needs %d B of shared memory", b->rows_smem);

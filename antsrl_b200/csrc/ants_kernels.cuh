@@ -45,6 +45,9 @@ struct Params {
     int32_t tiles_x, tiles_y;              // activity tiles per env
     int32_t rec_shift;                     // log2(record bytes): 4 (compact), 5 or 6
     int32_t rec16;                         // 1 = compact 16-byte record {f32 ph0, f32 ph1, f32 food, u8 occ, u8 wall|explored, u8 ts0, u8 ts1}
+    int32_t rec8;                          // 1 = compact 8-byte record {u16 ph0, u16 ph1, u16 food, u8 hill|occ, u8 wall|explored}
+    float *side_val;                       // rec8: [cells][3] f32 values of escaped fields (plain pheromones, non-integer food)
+    uint8_t *side_ts;                      // rec8: [cells][2] write timestamps of plain pheromone values
     uint32_t ts_mask, explored_old;        // timestamp range (0xFFF / 0xFF); "explored long ago" stamp (0xFFFF / 0x7F)
     int32_t food_off, meta_off, wall_off;  // byte offsets inside a record (phero k at 8k)
     int32_t grid_w, grid_h;                // rock grid dims
@@ -147,10 +150,31 @@ __device__ __forceinline__ uint8_t *rec_wall(const Params &p, uint8_t *r) { retu
 //   [0] f32 phero0  [4] f32 phero1  [8] f32 food  [12] u8 (hill << 7 | occ_gen)  [13] u8 (wall << 7 | explored_gen)
 //   [14],[15] u8 ts.  "hill" = the cell lies in the anthill disc (anthill.py:31-33), written by k_hill_mark at import;
 //   f64 records keep it in bit 1 of the wall byte.
+// Compact 8-byte record (lazy mode, P <= 2), four cells per DRAM sector:
+//   [0] u16 phero0  [2] u16 phero1  [4] u16 food  [6] u8 (hill << 7 | occ_gen)  [7] u8 (wall << 7 | explored_gen)
+//   pheromone code: 0 = nothing, 0x8000 | t = boxed saturated deposit of update t (mod 2^15), 1 = a plain value kept in
+//   side_val / side_ts;  food code: 0 .. 0xFFFE = that many units (what the reference's maps hold), 0xFFFF = a
+//   non-integer amount kept in side_val.  The side arrays are only touched for such escaped fields.
+constexpr uint32_t kBox8 = 0x8000u, kBox8Mask = 0x7FFFu, kFoodEsc = 0xFFFFu;
+__device__ __forceinline__ size_t rec8_index(const Params &p, const uint8_t *r) { return (size_t)(r - p.cells) >> 3; }
 __device__ __forceinline__ double ld_food(const Params &p, const uint8_t *r) {
+    if (p.rec8) {
+        const uint32_t c = *reinterpret_cast<const uint16_t *>(r + 4);
+        return c != kFoodEsc ? (double)c : (double)p.side_val[rec8_index(p, r) * 3 + 2];
+    }
     return p.rec16 ? (double)*reinterpret_cast<const float *>(r + 8) : *reinterpret_cast<const double *>(r + p.food_off);
 }
 __device__ __forceinline__ void st_food(const Params &p, uint8_t *r, double v) {
+    if (p.rec8) {
+        if (v >= 0.0 && v < 65535.0 && v == floor(v)) {
+            *reinterpret_cast<uint16_t *>(r + 4) = (uint16_t)(int)v;
+        } else {
+            *reinterpret_cast<uint16_t *>(r + 4) = (uint16_t)kFoodEsc;
+            p.side_val[rec8_index(p, r) * 3 + 2] = (float)v;
+            if (*p.plain_flag == 0u) *p.plain_flag = 1u;
+        }
+        return;
+    }
     if (p.rec16) *reinterpret_cast<float *>(r + 8) = (float)v; else *reinterpret_cast<double *>(r + p.food_off) = v;
 }
 __device__ __forceinline__ double ld_phero(const Params &p, const uint8_t *r, int k) {
@@ -160,24 +184,31 @@ __device__ __forceinline__ void st_phero(const Params &p, uint8_t *r, int k, dou
     if (p.rec16) reinterpret_cast<float *>(r)[k] = (float)v; else reinterpret_cast<double *>(r)[k] = v;
 }
 __device__ __forceinline__ bool ld_wall(const Params &p, const uint8_t *r) {
+    if (p.rec8) return (r[7] >> 7) != 0;
     return p.rec16 ? (r[13] >> 7) != 0 : (r[p.wall_off] & 1) != 0;
 }
 __device__ __forceinline__ void st_wall(const Params &p, uint8_t *r, bool w) {
+    if (p.rec8) { r[7] = (uint8_t)((r[7] & 0x7F) | (w ? 0x80 : 0)); return; }
     if (p.rec16) r[13] = (uint8_t)((r[13] & 0x7F) | (w ? 0x80 : 0)); else r[p.wall_off] = (uint8_t)((r[p.wall_off] & 2) | (w ? 1 : 0));
 }
 __device__ __forceinline__ void st_occ(const Params &p, uint8_t *r, uint32_t gen) {
+    if (p.rec8) { r[6] = (uint8_t)((r[6] & 0x80u) | (gen & 0x7Fu)); return; }
     if (p.rec16) r[12] = (uint8_t)((r[12] & 0x80u) | (gen & 0x7Fu)); else reinterpret_cast<uint16_t *>(r + p.meta_off)[1] = (uint16_t)gen;
 }
 __device__ __forceinline__ uint32_t ld_occ(const Params &p, const uint8_t *r) {
+    if (p.rec8) return r[6] & 0x7Fu;
     return p.rec16 ? (r[12] & 0x7Fu) : reinterpret_cast<const uint16_t *>(r + p.meta_off)[1];
 }
 __device__ __forceinline__ void st_hill(const Params &p, uint8_t *r, bool h) {
+    if (p.rec8) { r[6] = (uint8_t)((r[6] & 0x7Fu) | (h ? 0x80u : 0u)); return; }
     if (p.rec16) r[12] = (uint8_t)((r[12] & 0x7Fu) | (h ? 0x80u : 0u)); else r[p.wall_off] = (uint8_t)((r[p.wall_off] & 1) | (h ? 2 : 0));
 }
 __device__ __forceinline__ uint32_t ld_explored(const Params &p, const uint8_t *r) {
+    if (p.rec8) return r[7] & 0x7Fu;
     return p.rec16 ? (r[13] & 0x7Fu) : reinterpret_cast<const uint16_t *>(r + p.meta_off)[0];
 }
 __device__ __forceinline__ void st_explored(const Params &p, uint8_t *r, uint32_t gen) {
+    if (p.rec8) { r[7] = (uint8_t)((r[7] & 0x80) | (gen & 0x7F)); return; }
     if (p.rec16) r[13] = (uint8_t)((r[13] & 0x80) | (gen & 0x7F)); else reinterpret_cast<uint16_t *>(r + p.meta_off)[0] = (uint16_t)gen;
 }
 
@@ -200,6 +231,7 @@ __device__ __forceinline__ bool is_boxed64(unsigned long long b) { return (b >> 
 __device__ __forceinline__ unsigned long long box64(uint32_t t) { return 0x7FF8000000000000ull | (t & kBoxMask); }
 
 __device__ __forceinline__ uint32_t rec_ts(const Params &p, const uint8_t *r, int k) {
+    if (p.rec8) return p.side_ts[rec8_index(p, r) * 2 + k];
     if (p.rec16) return r[14 + k];
     if (p.P <= 2) {
         uint32_t w = *reinterpret_cast<const uint32_t *>(r + p.wall_off);      // [wall u8][ts0 12b][ts1 12b]
@@ -208,6 +240,7 @@ __device__ __forceinline__ uint32_t rec_ts(const Params &p, const uint8_t *r, in
     return *reinterpret_cast<const uint16_t *>(r + p.ts_off + 2 * k);
 }
 __device__ __forceinline__ void rec_set_ts(const Params &p, uint8_t *r, int k, uint32_t ts) {
+    if (p.rec8) { p.side_ts[rec8_index(p, r) * 2 + k] = (uint8_t)ts; return; }
     if (p.rec16) { r[14 + k] = (uint8_t)ts; return; }
     if (p.P <= 2) {
         uint32_t *w = reinterpret_cast<uint32_t *>(r + p.wall_off);
@@ -232,6 +265,14 @@ __device__ __forceinline__ double plain_value(const Params &p, double v, uint32_
 }
 // current value of pheromone k of record r (any format; eager modes store plain numbers without decay)
 __device__ __forceinline__ double phero_value(const Params &p, const uint8_t *r, int k, uint32_t now, uint32_t now_abs) {
+    if (p.rec8) {
+        const uint32_t c = reinterpret_cast<const uint16_t *>(r)[k];
+        if (c == 0u) return 0.0;
+        const bool wl = (r[7] >> 7) != 0;
+        if (c & kBox8) return boxed_value(p, (now_abs - c) & kBox8Mask, wl);
+        const size_t ri = rec8_index(p, r);
+        return plain_value(p, (double)p.side_val[ri * 3 + k], p.side_ts[ri * 2 + k], now, wl);
+    }
     if (p.rec16) {
         const uint32_t b = reinterpret_cast<const uint32_t *>(r)[k];
         if (b == 0u) return 0.0;
@@ -248,6 +289,17 @@ __device__ __forceinline__ double phero_value(const Params &p, const uint8_t *r,
 }
 // store a pheromone value that is current at (now, now_abs)
 __device__ __forceinline__ void phero_store(const Params &p, uint8_t *r, int k, double v, uint32_t now, uint32_t now_abs) {
+    if (p.rec8) {
+        uint16_t *c = reinterpret_cast<uint16_t *>(r) + k;
+        if (p.has_max_val && v == p.phero_max_val) { *c = (uint16_t)(kBox8 | (now_abs & kBox8Mask)); return; }
+        if (v == 0.0) { *c = 0; return; }
+        const size_t ri = rec8_index(p, r);
+        *c = 1;
+        p.side_val[ri * 3 + k] = (float)v;
+        p.side_ts[ri * 2 + k] = (uint8_t)now;
+        if (*p.plain_flag == 0u) *p.plain_flag = 1u;
+        return;
+    }
     if (p.lazy && p.has_max_val && v == p.phero_max_val) {
         if (p.rec16) reinterpret_cast<uint32_t *>(r)[k] = box32(now_abs);
         else reinterpret_cast<unsigned long long *>(r)[k] = box64(now_abs);
@@ -635,6 +687,13 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                 } else if (LAYOUT != 0) {      // P == 2: {ph0, ph1} | {food, meta, wall + timestamps}
                     lo[u] = *reinterpret_cast<const uint4 *>(rp[u]);
                     hi[u] = *reinterpret_cast<const uint4 *>(rp[u] + 16);
+                } else if (p.rec8) {           // 8-byte record (this kernel serves it through LAYOUT 0 only)
+                    const uint2 v8 = *reinterpret_cast<const uint2 *>(rp[u]);
+                    const double fdv = (v8.y & 0xFFFFu) != kFoodEsc ? (double)(v8.y & 0xFFFFu) : ld_food(p, rp[u]);
+                    const uint32_t fl = v8.y >> 16;                            // [hill|occ][wall|explored]
+                    hi[u] = make_uint4((uint32_t)__double2loint(fdv), (uint32_t)__double2hiint(fdv),
+                                       ((fl & 0x7Fu) << 16) | ((fl >> 8) & 0x7Fu), (fl >> 15) & 1u);
+                    lo[u] = make_uint4(0u, 0u, 0u, 0u);
                 } else {                       // generic f64 record: gather the fields into the same register shape
                     const double fdv = *reinterpret_cast<const double *>(rp[u] + food_off);
                     const uint32_t mtv = *reinterpret_cast<const uint32_t *>(rp[u] + meta_off);
@@ -665,6 +724,7 @@ k_perceive(Params p, float *__restrict__ obs, float *__restrict__ agent_state, f
                     const bool unexplored = valid && ((eg == 0u) || (eg == obs_gen));     // gather-before-scatter, Q7
                     if (valid && eg == 0u) {
                         if (REC16) const_cast<uint8_t *>(rp[u])[13] = (uint8_t)((wl ? 0x80u : 0u) | obs_gen);
+                        else if (p.rec8) const_cast<uint8_t *>(rp[u])[7] = (uint8_t)((wl ? 0x80u : 0u) | obs_gen);
                         else *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(rp[u]) + meta_off) = (uint16_t)obs_gen;
                     }
                     // the slot's lanes belong to consecutive ants: split the ballot at the ant boundaries (uniform)
@@ -824,7 +884,10 @@ k_collide(Params p, const double *__restrict__ noise, uint32_t step_id, uint32_t
                 uint32_t e = p.absorb_list[2 * k], c = p.absorb_list[2 * k + 1];
                 uint8_t *fr = rec_at(p, (int)e, (int)c);
                 double v;                                                      // qte -= qte * area
-                if (p.rec16) v = (double)__uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(fr + 8), 0u));
+                if (p.rec8) {          // the food code is the low half of the record's second word
+                    const uint32_t c = atomicAnd(reinterpret_cast<unsigned int *>(fr + 4), 0xFFFF0000u) & 0xFFFFu;
+                    v = c != kFoodEsc ? (double)c : (double)p.side_val[rec8_index(p, fr) * 3 + 2];
+                } else if (p.rec16) v = (double)__uint_as_float(atomicExch(reinterpret_cast<unsigned int *>(fr + 8), 0u));
                 else v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(fr + p.food_off), 0ull));
                 if (v != 0.0) atomicAdd(p.hill_food + e, v);
             }
@@ -1320,6 +1383,21 @@ __global__ void k_lazy_fold(Params p, uint32_t now, uint32_t now_abs, int unbox)
         uint8_t *r = p.cells + (j << p.rec_shift);
         for (int k = 0; k < p.P; ++k) {
             bool boxed, zero;
+            if (p.rec8) {
+                // expired boxed deposits are cleared when `unbox` is set (the 15-bit step would alias); plain values
+                // are re-based to timestamp 0 in their side slots
+                const uint32_t c = reinterpret_cast<const uint16_t *>(r)[k];
+                if (c == 0u) continue;
+                if (c & kBox8) {
+                    if (unbox && ((now_abs - c) & kBox8Mask) >= (uint32_t)p.tab_len) reinterpret_cast<uint16_t *>(r)[k] = 0;
+                    continue;
+                }
+                const double v = phero_value(p, r, k, now, now_abs);
+                if (v == 0.0) { reinterpret_cast<uint16_t *>(r)[k] = 0; continue; }
+                p.side_val[rec8_index(p, r) * 3 + k] = (float)v;
+                rec_set_ts(p, r, k, 0u);
+                continue;
+            }
             if (p.rec16) { uint32_t b = reinterpret_cast<const uint32_t *>(r)[k]; boxed = is_boxed32(b); zero = b == 0u; }
             else { unsigned long long b = reinterpret_cast<const unsigned long long *>(r)[k]; boxed = is_boxed64(b); zero = b == 0ull; }
             if (zero || (boxed && !unbox)) { if (!boxed) rec_set_ts(p, r, k, 0u); continue; }

@@ -71,7 +71,7 @@ __device__ __noinline__ float rock_channel(const Params &p, int e, unsigned long
     return 0.f;
 }
 
-template <int LAYOUT, bool REC16, int S>
+template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 16-byte, 2 = compact 8-byte
 #ifndef ANTS_ROWS_OCC
 #define ANTS_ROWS_OCC 5
 #endif
@@ -84,11 +84,13 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 uint32_t now, uint32_t now_abs) {
     pdl_begin();
     static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
+    constexpr bool REC16 = (REC == 1), REC8 = (REC == 2);
+    constexpr int SH = REC8 ? 3 : (REC16 ? 4 : 5);                    // log2(record bytes)
     static_assert(kRowsGroup * S <= 32, "a chunk's rows must fit one warp");
     constexpr int S2 = S * S, C = (LAYOUT == 2) ? 7 : 6, SC = S2 * C;
     constexpr int G = kRowsGroup, ROWS = G * S, TILE = G * SC;       // TILE * 4 bytes is a multiple of 16
     constexpr int NW = kRowsThreads / 32;
-    constexpr int UNR = REC16 ? (S < ANTS_ROWS_UNR ? S : ANTS_ROWS_UNR) : (S + 1) / 2;                      // record loads in flight per lane
+    constexpr int UNR = (REC != 0) ? (S < ANTS_ROWS_UNR ? S : ANTS_ROWS_UNR) : (S + 1) / 2;                      // record loads in flight per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_obs = reinterpret_cast<float *>(smem_raw);               // [NW][TILE]
     RowPrep *prep = reinterpret_cast<RowPrep *>(s_obs + NW * kRowsTiles * TILE);   // [threads]
@@ -190,12 +192,12 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const int nby64 = p.nby << 6;
     const uint32_t tab_len = (uint32_t)p.tab_len;
     const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
-    const bool eager = !REC16 && !p.lazy;                           // f64 fields hold plain current values (no decay on read)
+    const bool eager = (REC == 0) && !p.lazy;                           // f64 fields hold plain current values (no decay on read)
     const bool eager_planes = eager && p.diffuse != 0;              // ... in the diffusion planes (sign bit = wall)
     const double inv_max = 1.0 / p.phero_max_val;
     const bool any_plain = !eager && *p.plain_flag != 0u;           // lazy field: plain (non-boxed) values may exist
     // boxed deposit b = box | t: (box | now) - b = now - t = age; zero and plain values give an "age" >= 2^22
-    const uint32_t nowb = REC16 ? box32(now_abs) : (now_abs & kBoxMask);
+    const uint32_t nowb = REC16 ? box32(now_abs) : (REC8 ? now_abs : (now_abs & kBoxMask));
     const uint32_t ogs = obs_gen << 8;
     float *wobs0 = s_obs + warp * kRowsTiles * TILE;
     // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
@@ -232,7 +234,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             const RowPrep &q = prep[warp * 32 + g + la];
             const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
             const int e = q.e;
-            const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << (REC16 ? 4 : 5));
+            const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
             const double *plane0 = eager_planes ? p.phero_pl + (int64_t)e * 2 * p.plane : nullptr;   // [e][k = 0, 1]
             const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
             const int flags = q.flags;
@@ -254,8 +256,11 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         ix = wrap1(ix, W); iy = wrap1(iy, H);
                         // cidx(): 8 x 8 blocks of 64 records
                         cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
-                        const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
-                        if (!REC16 && eager_planes) {  // diffusion: the two pheromone values come from the row-major planes
+                        const uint8_t *rp = cells + ((size_t)cell[u] << SH);
+                        if (REC8) {                    // the whole cell in one 64-bit load, four cells per sector
+                            const uint2 v8 = *reinterpret_cast<const uint2 *>(rp);
+                            lo[u] = make_uint4(v8.x, v8.y, 0u, 0u);
+                        } else if (REC == 0 && eager_planes) {  // diffusion: the two pheromone values come from the row-major planes
                             const double *pv = plane0 + (int64_t)ix * p.Hp + iy;
                             const double d0 = pv[0], d1 = pv[p.plane];
                             lo[u] = make_uint4((uint32_t)__double2loint(d0), (uint32_t)__double2hiint(d0) & 0x7FFFFFFFu,
@@ -263,7 +268,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         } else {
                             lo[u] = ld_record16(rp);
                         }
-                        if (!REC16) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
+                        if (REC == 0) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
                     }
                 }
                 if (LAYOUT == 2 && flags) {            // a rock may reach this ant's window (few ants): RL_api.py:132-135
@@ -291,11 +296,23 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 for (int u = 0; u < UNR; ++u) {
                     const int j = j0 + u;
                     if (j < S) {
-                        uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << (REC16 ? 4 : 5));
+                        uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << SH);
                         bool wl, occupied, fresh, seen_now, hill;
                         uint32_t age0, age1;
                         float v5;                      // food as the f32 observation shows it
-                        if (REC16) {
+                        if (REC8) {
+                            const uint32_t pk = lo[u].y >> 16;                 // [hill|occ][wall|explored]
+                            const uint32_t c0 = lo[u].x & 0xFFFFu, c1 = lo[u].x >> 16;
+                            occupied = (pk & 0x7Fu) == occ_gen;
+                            hill = (pk & 0x80u) != 0;
+                            wl = (pk & 0x8000u) != 0;
+                            fresh = (pk & 0x7F00u) == 0u;
+                            seen_now = (pk & 0x7F00u) == ogs;
+                            v5 = (float)(lo[u].y & 0xFFFFu);                   // (an escaped amount is patched in below)
+                            age0 = (c0 & kBox8) ? ((nowb - c0) & kBox8Mask) : 0xFFFFFFFFu;
+                            age1 = (c1 & kBox8) ? ((nowb - c1) & kBox8Mask) : 0xFFFFFFFFu;
+                            if (explore_on && fresh) rp[7] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
+                        } else if (REC16) {
                             const uint32_t pk = lo[u].w;
                             occupied = (pk & 0x7Fu) == occ_gen;
                             hill = (pk & 0x80u) != 0;
@@ -327,7 +344,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         const uint32_t lim = wl ? 1u : tab_len;
                         float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
                         float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
-                        if (!REC16 && eager) {         // eager f64 fields (dense / tiles / diffusion): phero / max_val
+                        if (REC == 0 && eager) {       // eager f64 fields (dense / tiles / diffusion): phero / max_val
                             v1 = (float)(__hiloint2double((int)lo[u].y, (int)lo[u].x) * inv_max);
                             v2 = (float)(__hiloint2double((int)lo[u].w, (int)lo[u].z) * inv_max);
                         }
@@ -357,12 +374,20 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     for (int u = 0; u < UNR; ++u) {
                         const int j = j0 + u;
                         if (j >= S || !((mrow >> j) & 1u)) continue;
-                        const uint8_t *rp = cells + ((size_t)cell[u] << (REC16 ? 4 : 5));
-                        const uint4 r4 = *reinterpret_cast<const uint4 *>(rp);
-                        const bool pl0 = REC16 ? (r4.x != 0u && !is_boxed32(r4.x))
-                                               : ((r4.x | r4.y) != 0u && !(p.lazy && (r4.y & 0xFFF80000u) == 0x7FF80000u));
-                        const bool pl1 = REC16 ? (r4.y != 0u && !is_boxed32(r4.y))
-                                               : ((r4.z | r4.w) != 0u && !(p.lazy && (r4.w & 0xFFF80000u) == 0x7FF80000u));
+                        const uint8_t *rp = cells + ((size_t)cell[u] << SH);
+                        bool pl0, pl1;
+                        if (REC8) {
+                            const uint2 r2 = *reinterpret_cast<const uint2 *>(rp);
+                            pl0 = (r2.x & 0xFFFFu) == 1u; pl1 = (r2.x >> 16) == 1u;
+                            if ((r2.y & 0xFFFFu) == kFoodEsc)                  // a non-integer amount of food
+                                asm volatile("st.shared.f32 [%0+20], %1;" ::"r"(orow_s + (uint32_t)(j * C * 4)), "f"((float)ld_food(p, rp)) : "memory");
+                        } else {
+                            const uint4 r4 = *reinterpret_cast<const uint4 *>(rp);
+                            pl0 = REC16 ? (r4.x != 0u && !is_boxed32(r4.x))
+                                        : ((r4.x | r4.y) != 0u && !(p.lazy && (r4.y & 0xFFF80000u) == 0x7FF80000u));
+                            pl1 = REC16 ? (r4.y != 0u && !is_boxed32(r4.y))
+                                        : ((r4.z | r4.w) != 0u && !(p.lazy && (r4.w & 0xFFF80000u) == 0x7FF80000u));
+                        }
                         const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
                         if (pl0) asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 0, now, now_abs)) : "memory");
                         if (pl1) asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 1, now, now_abs)) : "memory");

@@ -57,7 +57,11 @@ enum { ANTS_EVAP_DENSE = 0, ANTS_EVAP_ACTIVE_TILES = 1, ANTS_EVAP_LAZY = 2 };
  *   COMPACT  { f32 phero0; f32 phero1; f32 food; 4 x u8 stamps }        16 B: two cells per DRAM sector.  Needs
  *            ANTS_EVAP_LAZY, P <= 2 and no diffusion.  Saturated (max_val) deposits stay bit-exact through the
  *            decay table; other pheromone values and non-integer food are rounded to f32 (6e-8 relative). */
-enum { ANTS_REC_F64 = 0, ANTS_REC_COMPACT = 1 };
+/*   COMPACT8 { u16 phero0; u16 phero1; u16 food; 2 x u8 stamps }             8 B: four cells per DRAM sector.  Same
+ *            requirements as COMPACT.  A pheromone code is a boxed saturated deposit (15-bit update index, decoded
+ *            through the decay table: bit-exact) or an escape to a side array holding the plain f32 value; food is an
+ *            integer count 0..65534 (what the reference's maps hold) or an escape to the side array. */
+enum { ANTS_REC_F64 = 0, ANTS_REC_COMPACT = 1, ANTS_REC_COMPACT8 = 2 };
 
 typedef struct AntsConfig {
     int32_t abi_version;             /* must be ANTS_ABI_VERSION */

@@ -21,17 +21,17 @@ def _variants(kw, n):
 
 
 @pytest.mark.parametrize("name,kw", GOLDEN_SCENARIOS, ids=[n for n, _ in GOLDEN_SCENARIOS])
-@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy", "lazy_compact"])
+@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy", "lazy_compact", "lazy_compact8"])
 def test_cuda_matches_oracle_every_step(name, kw, evap_mode):
     """3 envs per scenario family (different seeds), device-pointer API, taped collision noise; every evaporation
     mode and both cell-record formats."""
     kw = dict(kw)
     kw["steps"] = min(kw["steps"], 40)
     record = "f64"
-    if evap_mode == "lazy_compact":
+    if evap_mode.startswith("lazy_compact"):
         if kw.get("diffuse_factor", 0.0) != 0.0:
             pytest.skip("compact records exist for the lazy (diffusion-free) field only")
-        evap_mode, record = "lazy", "compact"
+        evap_mode, record = "lazy", evap_mode[5:]
     rep = run_parity(_variants(kw, 3), evap_mode=evap_mode, record=record)
     assert rep["kernel_launches"] > 0
 
@@ -171,15 +171,15 @@ ODD_CONFIGS = [
 
 
 @pytest.mark.parametrize("name,kw", ODD_CONFIGS, ids=[n for n, _ in ODD_CONFIGS])
-@pytest.mark.parametrize("evap_mode", ["dense", "lazy", "lazy_compact"])
+@pytest.mark.parametrize("evap_mode", ["dense", "lazy", "lazy_compact", "lazy_compact8"])
 def test_odd_configurations(name, kw, evap_mode):
     record = "f64"
-    if evap_mode == "lazy_compact":
+    if evap_mode.startswith("lazy_compact"):
         if kw.get("n_phero", 2) not in (1, 2):
             pytest.skip("compact records hold one or two pheromones")
         if kw.get("diffuse_factor", 0.0) != 0.0:
             pytest.skip("compact records are for the lazy field; diffusion keeps the field in f64 planes")
-        evap_mode, record = "lazy", "compact"
+        evap_mode, record = "lazy", evap_mode[5:]
     rep = run_parity(_variants(kw, 3), evap_mode=evap_mode, record=record)
     assert rep["state_checks"] == kw["steps"]
 
@@ -191,9 +191,9 @@ def test_lazy_timestamp_fold():
     from antsrl_b200 import BatchedAnts
     cfg, init, tape = make_scenario(seed=41, w=32, h=32, n_ants=16, steps=8)
     outs = {}
-    for mode in ("tiles", "lazy", "compact"):
-        b = BatchedAnts(cfg, 2, evap_mode="lazy" if mode == "compact" else mode, rng_seed=5,
-                        record="compact" if mode == "compact" else "f64")
+    for mode in ("tiles", "lazy", "compact", "compact8"):
+        b = BatchedAnts(cfg, 2, evap_mode="lazy" if mode.startswith("compact") else mode, rng_seed=5,
+                        record=mode if mode.startswith("compact") else "f64")
         b.import_state(stack_init(cfg, [init, init]))
         b.observe()
         for t in range(4200):
@@ -208,8 +208,9 @@ def test_lazy_timestamp_fold():
     assert np.array_equal(outs["tiles"]["x"], outs["lazy"]["x"])
     assert outs["tiles"]["phero"].max() > 0
     np.testing.assert_allclose(outs["lazy"]["phero"], outs["tiles"]["phero"], rtol=1e-9, atol=0)
-    assert np.array_equal(outs["tiles"]["x"], outs["compact"]["x"])
-    np.testing.assert_allclose(outs["compact"]["phero"], outs["tiles"]["phero"], rtol=1e-5, atol=0)
+    for fmt in ("compact", "compact8"):
+        assert np.array_equal(outs["tiles"]["x"], outs[fmt]["x"])
+        np.testing.assert_allclose(outs[fmt]["phero"], outs["tiles"]["phero"], rtol=1e-5, atol=0)
 
 
 def test_rollout_equals_step_update_loop():
@@ -240,7 +241,7 @@ def test_rollout_equals_step_update_loop():
             assert np.array_equal(v, outs[1][2][k]), k
 
 
-@pytest.mark.parametrize("record", ["compact", "f64"])
+@pytest.mark.parametrize("record", ["compact", "compact8", "f64"])
 def test_full_size_env_matches_oracle(record):
     """BASELINE configs[3] dimensions (1024x1024 map, 1024 ants, 64 rocks, 7x7x7 obs) for two envs generated by the
     drop-in generator (seeds 1000, 1001), 12 steps with Philox collision noise, compared with the oracle."""
@@ -324,7 +325,7 @@ def _cmp_outputs(gpu, refs, what):
     assert_close(rew, np.stack([r[2] for r in refs]), what + ": reward")
 
 
-@pytest.mark.parametrize("record", ["compact", "f64"])
+@pytest.mark.parametrize("record", ["compact", "compact8", "f64"])
 @pytest.mark.parametrize("n_rocks", [0, 5])
 def test_irregular_call_order(record, n_rocks):
     """observe / step / update in an order main.py never uses (update before the first step, two steps in a row, two
@@ -492,7 +493,7 @@ def test_device_replay_memory_ring_buffer():
     b.close()
 
 
-@pytest.mark.parametrize("record", ["compact", "f64"])
+@pytest.mark.parametrize("record", ["compact", "compact8", "f64"])
 def test_long_run_crosses_generation_folds(record):
     """300 steps against the oracle: the 7-bit occupancy / exploration generation counters of the compact records fold
     twice (every ~125 steps), the double-buffered commit / absorb counters alternate 300 times."""
