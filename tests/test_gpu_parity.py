@@ -510,3 +510,34 @@ def test_parity_with_programmatic_dependent_launch(monkeypatch):
         kw = dict(GOLDEN_SCENARIOS)[name]
         rep = run_parity(_variants(kw, 3), evap_mode="lazy", record="compact")
         assert rep["state_checks"] == kw["steps"]
+
+
+def test_compact8_step_counter_wraps():
+    """8-byte records keep 15 bits of a deposit's update index: deposits that have long decayed to zero must not come
+    back when the counter wraps (they are cleared every 16384 updates).  33 000 updates against the eagerly evaporated
+    field, deposits at the start and again after the wrap."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    cfg, init, tape = make_scenario(seed=43, w=32, h=32, n_ants=16, steps=8)
+    outs = {}
+    for mode in ("tiles", "compact8"):
+        b = BatchedAnts(cfg, 1, evap_mode="lazy" if mode == "compact8" else mode, rng_seed=5,
+                        record=mode if mode == "compact8" else "f64")
+        b.import_state(stack_init(cfg, [init]))
+        b.observe()
+        snaps = []
+        for t in range(33000):
+            if t < 30 or 32800 <= t < 32830:
+                k = t % 8
+                b.step(torch.from_numpy(tape["rot"][k][None]).cuda(), torch.from_numpy(tape["ph"][k][None]).cuda())
+            if t == 30:                                  # stop depositing (Ants.update emits whatever is activated)
+                b.activate_all_pheromones(np.zeros((1, 16, 2)))
+            b.update(None)
+            if t in (29, 12000, 32799, 32999):
+                snaps.append(b.export_state(keys=("phero",))["phero"].copy())
+        outs[mode] = snaps
+        b.close()
+    assert outs["tiles"][0].max() > 0 and outs["tiles"][1].max() == 0 and outs["tiles"][2].max() == 0
+    assert outs["tiles"][3].max() > 0
+    for a, c in zip(outs["tiles"], outs["compact8"]):
+        np.testing.assert_allclose(c, a, rtol=1e-5, atol=0)
