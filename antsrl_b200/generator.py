@@ -135,11 +135,11 @@ class BatchedEnvironmentGenerator:
     def generate(self, n_envs, device=0, first_env=0, float_activation=True, **batch_kw):
         """-> BatchedAnts holding envs [first_env, first_env + n_envs) (global ids, for sharding).  Defaults to the
         fast field representation the configuration allows: lazy decay and, for one or two pheromones without
-        diffusion, the compact 16-byte cell records."""
+        diffusion, the compact 8-byte cell records."""
         from .batch import BatchedAnts
         batch_kw.setdefault("evap_mode", "lazy")
         if self.cfg.get("diffuse_factor", 0.0) == 0.0 and 1 <= self.n_pheromones <= 2 and batch_kw["evap_mode"] == "lazy":
-            batch_kw.setdefault("record", "compact")
+            batch_kw.setdefault("record", "compact8")
         states = self.generate_states(n_envs, first_env)
         batch = BatchedAnts(self.cfg, n_envs, device=device, env_id_base=first_env, **batch_kw)
         batch.import_state(stack_states(states, self.cfg["reward_kind"]))

@@ -371,8 +371,10 @@ def run_ours(args):
                        "ants_per_env": N, "map": [wl["w"], wl["h"]], "pheromones": wl["n_phero"], "rocks": wl["n_rocks"],
                        "obs": "7x7x%d f32" % C, "evaporation": st["evap_mode"], "cell_record": record,
                        "precision": "f64 positions / headings / sample coordinates; %s; f32 obs" % (
-                           "16 B cell records (f32 pheromone, bit-exact for saturated deposits via the decay table; f32 food)"
-                           if record == "compact" else "f64 fields"), "l2": "state per GPU (%.1f GB) >> 126 MB L2"
+                           {"compact": "16 B cell records (f32 pheromone, bit-exact for saturated deposits via the decay "
+                                       "table; f32 food)",
+                            "compact8": "8 B cell records (u16 pheromone codes: saturated deposits bit-exact via the "
+                                        "decay table, plain values in f32 side arrays; u16 food counts)"}.get(record, "f64 fields")), "l2": "state per GPU (%.1f GB) >> 126 MB L2"
                        % (st["device_bytes"] / 1e9), "parallelism": "env-sharded x%d, no per-step collective" % world,
                        "noise": "in-kernel Philox", "actions": "uniform random, pre-recorded tape on device"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "kernels": kernels,
@@ -433,8 +435,8 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--evap", default="lazy", choices=["lazy", "tiles", "dense"])
-    ap.add_argument("--record", default="compact", choices=["compact", "f64"],
-                    help="cell record format (compact = 16 B, lazy mode only)")
+    ap.add_argument("--record", default="compact8", choices=["compact8", "compact", "f64"],
+                    help="cell record format (compact8 = 8 B, compact = 16 B: lazy mode only)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")

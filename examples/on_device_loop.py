@@ -51,7 +51,7 @@ def main():
     E, N = a.envs, wl["n_ants"]
     gen = bench.make_generator(wl, a.steps + 10)
     states = bench.generate_states_parallel(wl, a.steps + 10, 0, E)
-    env = BatchedAnts(gen.cfg, E, evap_mode="lazy", record="compact")
+    env = BatchedAnts(gen.cfg, E, evap_mode="lazy", record="compact8")
     env.import_state(stack_states(states, "all"))
     env.activate_all_pheromones(np.ones((E, N, wl["n_phero"])) * 10.0)          # agent.initialize
     C = len(gen.cfg["channels"])
