@@ -316,7 +316,9 @@ def run_ours(args):
     achieved = abytes / (dom_ms_per_launch / 1000.0) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(dom, E * N), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": abytes, "ms_per_launch": dom_ms_per_launch}
+                "algorithmic_bytes_per_launch": abytes, "ms_per_launch": dom_ms_per_launch,
+                "note": "algorithmic bytes = SURVEY.md 8-d (the reference's f64 fields at element granularity, f32 obs); "
+                        "the compact cell records move fewer bytes than that, see traffic (ncu DRAM bytes per launch)"}
     # whole-step view: algorithmic bytes of every family per step / step time
     step_bytes = sum(algorithmic_bytes(f, wl, E, C, st) for f in kernels)
     roofline["step_achieved"] = step_bytes / (ms / K / 1000.0) / 1e9
