@@ -21,19 +21,20 @@ namespace ants {
 
 constexpr int kRowsThreads = 128;
 constexpr int kRowsGroup = 4;
+#ifndef ANTS_ROWS_FLAT
+#define ANTS_ROWS_FLAT 0           // 1 = hand the 32 * S rows of a warp to the lanes without idle lanes (measured slower: 0.279 vs 0.241 ms)
+#endif
 #ifndef ANTS_ROWS_TILES
-#define ANTS_ROWS_TILES 1
+#define ANTS_ROWS_TILES (ANTS_ROWS_FLAT ? 2 : 1)
 #endif
 constexpr int kRowsTiles = ANTS_ROWS_TILES;   // staging tiles per warp (2 = the bulk store of chunk g drains while g + 1 is staged)
 
-struct RowPrep {                 // 96 bytes per ant, shared memory (phase A -> phase B)
+struct RowPrep {                 // 72 bytes per ant, shared memory (phase A -> phase B)
     double ct, st;               // cos / sin(theta + pi/2)
     double xf, yf;               // position shifted forward by perception_fwd_delta
     unsigned long long rocks;    // further candidate rocks (beyond the first) whose disc can reach the window
-    int e, hx, hy, hr2;          // environment; anthill centre and radius^2
-    int flags, pad;              // 2 = a rock may reach the window, 4 = more than one
+    int e, flags;                // environment; 2 = a rock may reach the window, 4 = more than one
     double rcx, rcy, rrad;       // the first candidate rock
-    double pad2;
 };
 
 // one conditional add or subtract wraps a sample coordinate onto the torus (np.mod on ints, RL_api.py:118-119) when
@@ -73,7 +74,7 @@ __device__ __noinline__ float rock_channel(const Params &p, int e, unsigned long
 
 template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 16-byte, 2 = compact 8-byte
 #ifndef ANTS_ROWS_OCC
-#define ANTS_ROWS_OCC 5
+#define ANTS_ROWS_OCC (ANTS_ROWS_FLAT ? 4 : 5)   // resident blocks per SM the register budget allows (shared memory: 4 / 5)
 #endif
 #ifndef ANTS_ROWS_UNR
 #define ANTS_ROWS_UNR 7
@@ -85,6 +86,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     pdl_begin();
     static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
     constexpr bool REC16 = (REC == 1), REC8 = (REC == 2);
+    constexpr bool FLAT = (ANTS_ROWS_FLAT != 0) && S == 7 && REC != 0;
     constexpr int SH = REC8 ? 3 : (REC16 ? 4 : 5);                    // log2(record bytes)
     static_assert(kRowsGroup * S <= 32, "a chunk's rows must fit one warp");
     constexpr int S2 = S * S, C = (LAYOUT == 2) ? 7 : 6, SC = S2 * C;
@@ -116,13 +118,12 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // :103-104
             q.e = e;
             const int32_t *hl = p.hill + 4 * e;
-            q.hx = hl[0]; q.hy = hl[1]; q.hr2 = hl[3];
             const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
             const double d = hold - hprev;
             if (p.reward_kind == 0) {                                          // All_Rewards, reward_custom.py:79-106
                 const double r_food = d < 0.0 ? 0.0 : d;
                 const double r_hill = d < 0.0 ? 1.0 : 0.0;
-                const double ddx = x - (double)q.hx, ddy = y - (double)q.hy;
+                const double ddx = x - (double)hl[0], ddy = y - (double)hl[1];
                 const double nd = sqrt(ddx * ddx + ddy * ddy);
                 const double heading = (p.rw_prev_dist[i] > nd && hold > 0.0) ? 0.1 : 0.0;
                 p.rw_prev_dist[i] = nd;
@@ -157,7 +158,6 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             }
             {
                 q.flags = 0;
-                q.pad = 0; q.pad2 = 0.0;
                 q.rcx = q.rcy = 0.0; q.rrad = -1.0;
                 if (rm) {
                     const int r = __ffsll((long long)rm) - 1;
@@ -182,17 +182,13 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     }
     __syncwarp();        // a warp only reads the prep records of its own 32 ants
 
-    // ---- phase B: lane = (ant of the chunk, window row), loop over the row's columns
+    // ---- phase B: a lane processes one window row of one ant (its S columns); two ways of handing out the rows
     const int warp = tid >> 5, lane = tid & 31;
-    const int la = lane / S, li = lane - la * S;
-    const bool lane_on = lane < ROWS;
-    const double offY = p.off_c[lane_on ? li : 0];
-    uint32_t mrow = p.mask_rows[lane_on ? li : 0];
     const int W = p.W, H = p.H;
     const int nby64 = p.nby << 6;
     const uint32_t tab_len = (uint32_t)p.tab_len;
     const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
-    const bool eager = (REC == 0) && !p.lazy;                           // f64 fields hold plain current values (no decay on read)
+    const bool eager = (REC == 0) && !p.lazy;                       // f64 fields hold plain current values (no decay on read)
     const bool eager_planes = eager && p.diffuse != 0;              // ... in the diffusion planes (sign bit = wall)
     const double inv_max = 1.0 / p.phero_max_val;
     const bool any_plain = !eager && *p.plain_flag != 0u;           // lazy field: plain (non-boxed) values may exist
@@ -200,203 +196,176 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const uint32_t nowb = REC16 ? box32(now_abs) : (REC8 ? now_abs : (now_abs & kBoxMask));
     const uint32_t ogs = obs_gen << 8;
     float *wobs0 = s_obs + warp * kRowsTiles * TILE;
-    // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
-    uint32_t orow_s0 = (uint32_t)__cvta_generic_to_shared(wobs0 + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
-    asm volatile("" : "+r"(orow_s0), "+r"(mrow));                    // keep them in registers (no rematerialisation)
-    // masked samples read -1 in every channel (RL_api.py:147-148) and their tile slots are never written again
-    if (lane_on) {
+    constexpr bool kLateWait = (UNR >= S);
+    // one row: sample cells, record loads, decode, staging-tile stores; returns the row's count of unexplored samples
+    auto row_body = [&](const RowPrep &q, const double offY, const uint32_t mrow, const uint32_t orow_s,
+                        const uint32_t amask) -> int {
+        const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
+        const int e = q.e;
+        const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
+        const double *plane0 = eager_planes ? p.phero_pl + (int64_t)e * 2 * p.plane : nullptr;   // [e][k = 0, 1]
+        const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
+        const int flags = q.flags;
+        uint32_t rbits = 0u;                                       // bit j: a rock covers the sample at column j
+        int cnt = 0;
 #pragma unroll
-        for (int j = 0; j < S; ++j)
-            if (!((mrow >> j) & 1u))
+        for (int j0 = 0; j0 < S; j0 += UNR) {
+            uint4 lo[UNR], hi[UNR];
+            uint32_t cell[UNR];
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-#pragma unroll
-                    for (int t = 0; t < kRowsTiles; ++t)
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s0 + (uint32_t)((t * TILE + j * C + c) * 4)), "f"(-1.f) : "memory");
-    }
-
-    for (int g = 0; g < 32; g += G) {
-        const int64_t i0 = base + warp * 32 + g;
-        if (i0 >= p.EN) break;
-        const int n_in = (p.EN - i0 < G) ? (int)(p.EN - i0) : G;
-        const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
-        float *wobs = wobs0 + tsel * TILE;
-        const uint32_t orow_s = orow_s0 + (uint32_t)(tsel * TILE * 4);
-        // the previous chunk's bulk store must have finished reading the staging tile before it is written again:
-        // with a single batch of loads (compact records) that wait sits behind the loads, where it costs nothing
-        constexpr bool kLateWait = (UNR >= S);
-        const uint32_t amask = (n_in * S >= 32) ? 0xffffffffu : ((1u << (n_in * S)) - 1u);   // the lanes with a row
-        if (!kLateWait) {
-            if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
-            __syncwarp();
-        }
-        if (lane_on && la < n_in) {
-            const RowPrep &q = prep[warp * 32 + g + la];
-            const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
-            const int e = q.e;
-            const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
-            const double *plane0 = eager_planes ? p.phero_pl + (int64_t)e * 2 * p.plane : nullptr;   // [e][k = 0, 1]
-            const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
-            const int flags = q.flags;
-            uint32_t rbits = 0u;                                       // bit j: a rock covers the sample at column j
-            int cnt = 0;
-#pragma unroll
-            for (int j0 = 0; j0 < S; j0 += UNR) {
-                uint4 lo[UNR], hi[UNR];
-                uint32_t cell[UNR];
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int j = j0 + u;
-                    if (j < S) {
-                        // sample cell, RL_api.py:110-119: round_half_even(rot(theta + pi/2) * offset + xy_f) mod (W, H)
-                        const double X = p.off_c[j];
-                        const double rx = ct * X - stY;
-                        const double ry = st * X + ctY;
-                        int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
-                        ix = wrap1(ix, W); iy = wrap1(iy, H);
-                        // cidx(): 8 x 8 blocks of 64 records
-                        cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
-                        const uint8_t *rp = cells + ((size_t)cell[u] << SH);
-                        if (REC8) {                    // the whole cell in one 64-bit load, four cells per sector
-                            const uint2 v8 = *reinterpret_cast<const uint2 *>(rp);
-                            lo[u] = make_uint4(v8.x, v8.y, 0u, 0u);
-                        } else if (REC == 0 && eager_planes) {  // diffusion: the two pheromone values come from the row-major planes
-                            const double *pv = plane0 + (int64_t)ix * p.Hp + iy;
-                            const double d0 = pv[0], d1 = pv[p.plane];
-                            lo[u] = make_uint4((uint32_t)__double2loint(d0), (uint32_t)__double2hiint(d0) & 0x7FFFFFFFu,
-                                               (uint32_t)__double2loint(d1), (uint32_t)__double2hiint(d1) & 0x7FFFFFFFu);
-                        } else {
-                            lo[u] = ld_record16(rp);
-                        }
-                        if (REC == 0) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
+            for (int u = 0; u < UNR; ++u) {
+                const int j = j0 + u;
+                if (j < S) {
+                    // sample cell, RL_api.py:110-119: round_half_even(rot(theta + pi/2) * offset + xy_f) mod (W, H)
+                    const double X = p.off_c[j];
+                    const double rx = ct * X - stY;
+                    const double ry = st * X + ctY;
+                    int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
+                    ix = wrap1(ix, W); iy = wrap1(iy, H);
+                    // cidx(): 8 x 8 blocks of 64 records
+                    cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
+                    const uint8_t *rp = cells + ((size_t)cell[u] << SH);
+                    if (REC8) {                    // the whole cell in one 64-bit load, four cells per sector
+                        const uint2 v8 = *reinterpret_cast<const uint2 *>(rp);
+                        lo[u] = make_uint4(v8.x, v8.y, 0u, 0u);
+                    } else if (REC == 0 && eager_planes) {  // diffusion: the two pheromone values come from the row-major planes
+                        const double *pv = plane0 + (int64_t)ix * p.Hp + iy;
+                        const double d0 = pv[0], d1 = pv[p.plane];
+                        lo[u] = make_uint4((uint32_t)__double2loint(d0), (uint32_t)__double2hiint(d0) & 0x7FFFFFFFu,
+                                           (uint32_t)__double2loint(d1), (uint32_t)__double2hiint(d1) & 0x7FFFFFFFu);
+                    } else {
+                        lo[u] = ld_record16(rp);
                     }
-                }
-                if (LAYOUT == 2 && flags) {            // a rock may reach this ant's window (few ants): RL_api.py:132-135
-#pragma unroll 1
-                    for (int j = j0; j < S && j < j0 + UNR; ++j) {
-                        const double X = p.off_c[j];                           // the same arithmetic as above
-                        const double rx = ct * X - stY;
-                        const double ry = st * X + ctY;
-                        int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
-                        ix = wrap1(ix, W); iy = wrap1(iy, H);
-                        // strict sqrt(d2) < r, decided on the squares unless d2 is within 1e-12 of r^2
-                        const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
-                        const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
-                        bool hit = d2 < r2 * 0.999999999999;
-                        if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
-                        if (!hit && (flags & 4)) hit = rock_channel(p, e, q.rocks, ix, iy) != 0.f;
-                        rbits |= (hit ? 1u : 0u) << j;
-                    }
-                }
-                if (kLateWait) {
-                    if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
-                    __syncwarp(amask);
-                }
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int j = j0 + u;
-                    if (j < S) {
-                        uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << SH);
-                        bool wl, occupied, fresh, seen_now, hill;
-                        uint32_t age0, age1;
-                        float v5;                      // food as the f32 observation shows it
-                        if (REC8) {
-                            const uint32_t pk = lo[u].y >> 16;                 // [hill|occ][wall|explored]
-                            const uint32_t c0 = lo[u].x & 0xFFFFu, c1 = lo[u].x >> 16;
-                            occupied = (pk & 0x7Fu) == occ_gen;
-                            hill = (pk & 0x80u) != 0;
-                            wl = (pk & 0x8000u) != 0;
-                            fresh = (pk & 0x7F00u) == 0u;
-                            seen_now = (pk & 0x7F00u) == ogs;
-                            v5 = (float)(lo[u].y & 0xFFFFu);                   // (an escaped amount is patched in below)
-                            age0 = (c0 & kBox8) ? ((nowb - c0) & kBox8Mask) : 0xFFFFFFFFu;
-                            age1 = (c1 & kBox8) ? ((nowb - c1) & kBox8Mask) : 0xFFFFFFFFu;
-                            if (explore_on && fresh) rp[7] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
-                        } else if (REC16) {
-                            const uint32_t pk = lo[u].w;
-                            occupied = (pk & 0x7Fu) == occ_gen;
-                            hill = (pk & 0x80u) != 0;
-                            wl = (pk & 0x8000u) != 0;
-                            fresh = (pk & 0x7F00u) == 0u;
-                            seen_now = (pk & 0x7F00u) == ogs;
-                            v5 = __uint_as_float(lo[u].z);
-                            age0 = nowb - lo[u].x; age1 = nowb - lo[u].y;
-                            if (explore_on && fresh) rp[13] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
-                        } else {
-                            occupied = (hi[u].z >> 16) == occ_gen;
-                            wl = (hi[u].w & 1u) != 0;
-                            hill = (hi[u].w & 2u) != 0;
-                            fresh = (hi[u].z & 0xFFFFu) == 0u;
-                            seen_now = (hi[u].z & 0xFFFFu) == obs_gen;
-                            v5 = (float)__hiloint2double((int)hi[u].y, (int)hi[u].x);
-                            // f64 fields: boxed <=> the high word carries the NaN box; the deposit step is the low word
-                            const bool bx0 = p.lazy && (lo[u].y & 0xFFF80000u) == 0x7FF80000u;
-                            const bool bx1 = p.lazy && (lo[u].w & 0xFFF80000u) == 0x7FF80000u;
-                            age0 = bx0 ? ((nowb - lo[u].x) & kBoxMask) : 0xFFFFFFFFu;
-                            age1 = bx1 ? ((nowb - lo[u].z) & kBoxMask) : 0xFFFFFFFFu;
-                            if (explore_on && fresh) *reinterpret_cast<uint16_t *>(rp + 24) = (uint16_t)obs_gen;
-                        }
-                        if (explore_on) cnt += (fresh || seen_now) ? 1 : 0;    // gather-before-scatter, Q7
-                        // pheromone channels, RL_api.py:124-125.  A saturated deposit of age k shows
-                        // (float)(max_val * keep^k / max_val) = keep^k (the reference's per-step rounding moves it by
-                        // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
-                        // cut is the exact table length; inside a wall only a deposit of this very update shows.
-                        const uint32_t lim = wl ? 1u : tab_len;
-                        float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
-                        float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
-                        if (REC == 0 && eager) {       // eager f64 fields (dense / tiles / diffusion): phero / max_val
-                            v1 = (float)(__hiloint2double((int)lo[u].y, (int)lo[u].x) * inv_max);
-                            v2 = (float)(__hiloint2double((int)lo[u].w, (int)lo[u].z) * inv_max);
-                        }
-                        const float v0 = occupied ? 1.f : 0.f;                                   // :136-142
-                        const float v3 = hill ? 1.f : 0.f;                                       // :130-131 (disc bit of the record)
-                        const float v4 = wl ? 1.f : 0.f;                                         // :128-129
-                        const float v6 = ((rbits >> j) & 1u) ? 1.f : 0.f;                        // :132-135
-                        const uint32_t vis = (mrow >> j) & 1u;     // masked slots keep the -1 written once above
-                        const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
-                        if (LAYOUT == 2)
-                            asm volatile("{\n .reg .pred pv;\n setp.ne.u32 pv, %0, 0;\n"
-                                         " @pv st.shared.f32 [%1], %2;\n @pv st.shared.f32 [%1+4], %3;\n"
-                                         " @pv st.shared.f32 [%1+8], %4;\n @pv st.shared.f32 [%1+12], %5;\n"
-                                         " @pv st.shared.f32 [%1+16], %6;\n @pv st.shared.f32 [%1+20], %7;\n"
-                                         " @pv st.shared.f32 [%1+24], %8;\n}"
-                                         ::"r"(vis), "r"(oaddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6) : "memory");
-                        else
-                            asm volatile("{\n .reg .pred pv;\n setp.ne.u32 pv, %0, 0;\n"
-                                         " @pv st.shared.f32 [%1], %2;\n @pv st.shared.f32 [%1+4], %3;\n"
-                                         " @pv st.shared.f32 [%1+8], %4;\n @pv st.shared.f32 [%1+12], %5;\n"
-                                         " @pv st.shared.f32 [%1+16], %6;\n @pv st.shared.f32 [%1+20], %7;\n}"
-                                         ::"r"(vis), "r"(oaddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5) : "memory");
-                    }
-                }
-                if (any_plain) {   // plain pheromone values (bool activations, imports, eager modes) may exist: patch them in
-#pragma unroll
-                    for (int u = 0; u < UNR; ++u) {
-                        const int j = j0 + u;
-                        if (j >= S || !((mrow >> j) & 1u)) continue;
-                        const uint8_t *rp = cells + ((size_t)cell[u] << SH);
-                        bool pl0, pl1;
-                        if (REC8) {
-                            const uint2 r2 = *reinterpret_cast<const uint2 *>(rp);
-                            pl0 = (r2.x & 0xFFFFu) == 1u; pl1 = (r2.x >> 16) == 1u;
-                            if ((r2.y & 0xFFFFu) == kFoodEsc)                  // a non-integer amount of food
-                                asm volatile("st.shared.f32 [%0+20], %1;" ::"r"(orow_s + (uint32_t)(j * C * 4)), "f"((float)ld_food(p, rp)) : "memory");
-                        } else {
-                            const uint4 r4 = *reinterpret_cast<const uint4 *>(rp);
-                            pl0 = REC16 ? (r4.x != 0u && !is_boxed32(r4.x))
-                                        : ((r4.x | r4.y) != 0u && !(p.lazy && (r4.y & 0xFFF80000u) == 0x7FF80000u));
-                            pl1 = REC16 ? (r4.y != 0u && !is_boxed32(r4.y))
-                                        : ((r4.z | r4.w) != 0u && !(p.lazy && (r4.w & 0xFFF80000u) == 0x7FF80000u));
-                        }
-                        const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
-                        if (pl0) asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 0, now, now_abs)) : "memory");
-                        if (pl1) asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 1, now, now_abs)) : "memory");
-                    }
+                    if (REC == 0) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
                 }
             }
-            s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
+            if (LAYOUT == 2 && flags) {            // a rock may reach this ant's window (few ants): RL_api.py:132-135
+#pragma unroll 1
+                for (int j = j0; j < S && j < j0 + UNR; ++j) {
+                    const double X = p.off_c[j];                           // the same arithmetic as above
+                    const double rx = ct * X - stY;
+                    const double ry = st * X + ctY;
+                    int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
+                    ix = wrap1(ix, W); iy = wrap1(iy, H);
+                    // strict sqrt(d2) < r, decided on the squares unless d2 is within 1e-12 of r^2
+                    const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
+                    const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
+                    bool hit = d2 < r2 * 0.999999999999;
+                    if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
+                    if (!hit && (flags & 4)) hit = rock_channel(p, e, q.rocks, ix, iy) != 0.f;
+                    rbits |= (hit ? 1u : 0u) << j;
+                }
+            }
+            if (kLateWait) {
+                if (lane == 0) bulk_store_wait_read<FLAT ? 0 : kRowsTiles - 1>();
+                __syncwarp(amask);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int j = j0 + u;
+                if (j < S) {
+                    uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << SH);
+                    bool wl, occupied, fresh, seen_now, hill;
+                    uint32_t age0, age1;
+                    float v5;                      // food as the f32 observation shows it
+                    if (REC8) {
+                        const uint32_t pk = lo[u].y >> 16;                 // [hill|occ][wall|explored]
+                        const uint32_t c0 = lo[u].x & 0xFFFFu, c1 = lo[u].x >> 16;
+                        occupied = (pk & 0x7Fu) == occ_gen;
+                        hill = (pk & 0x80u) != 0;
+                        wl = (pk & 0x8000u) != 0;
+                        fresh = (pk & 0x7F00u) == 0u;
+                        seen_now = (pk & 0x7F00u) == ogs;
+                        v5 = (float)(lo[u].y & 0xFFFFu);                   // (an escaped amount is patched in below)
+                        age0 = (c0 & kBox8) ? ((nowb - c0) & kBox8Mask) : 0xFFFFFFFFu;
+                        age1 = (c1 & kBox8) ? ((nowb - c1) & kBox8Mask) : 0xFFFFFFFFu;
+                        if (explore_on && fresh) rp[7] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
+                    } else if (REC16) {
+                        const uint32_t pk = lo[u].w;
+                        occupied = (pk & 0x7Fu) == occ_gen;
+                        hill = (pk & 0x80u) != 0;
+                        wl = (pk & 0x8000u) != 0;
+                        fresh = (pk & 0x7F00u) == 0u;
+                        seen_now = (pk & 0x7F00u) == ogs;
+                        v5 = __uint_as_float(lo[u].z);
+                        age0 = nowb - lo[u].x; age1 = nowb - lo[u].y;
+                        if (explore_on && fresh) rp[13] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
+                    } else {
+                        occupied = (hi[u].z >> 16) == occ_gen;
+                        wl = (hi[u].w & 1u) != 0;
+                        hill = (hi[u].w & 2u) != 0;
+                        fresh = (hi[u].z & 0xFFFFu) == 0u;
+                        seen_now = (hi[u].z & 0xFFFFu) == obs_gen;
+                        v5 = (float)__hiloint2double((int)hi[u].y, (int)hi[u].x);
+                        // f64 fields: boxed <=> the high word carries the NaN box; the deposit step is the low word
+                        const bool bx0 = p.lazy && (lo[u].y & 0xFFF80000u) == 0x7FF80000u;
+                        const bool bx1 = p.lazy && (lo[u].w & 0xFFF80000u) == 0x7FF80000u;
+                        age0 = bx0 ? ((nowb - lo[u].x) & kBoxMask) : 0xFFFFFFFFu;
+                        age1 = bx1 ? ((nowb - lo[u].z) & kBoxMask) : 0xFFFFFFFFu;
+                        if (explore_on && fresh) *reinterpret_cast<uint16_t *>(rp + 24) = (uint16_t)obs_gen;
+                    }
+                    if (explore_on) cnt += (fresh || seen_now) ? 1 : 0;    // gather-before-scatter, Q7
+                    // pheromone channels, RL_api.py:124-125.  A saturated deposit of age k shows
+                    // (float)(max_val * keep^k / max_val) = keep^k (the reference's per-step rounding moves it by
+                    // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
+                    // cut is the exact table length; inside a wall only a deposit of this very update shows.
+                    const uint32_t lim = wl ? 1u : tab_len;
+                    float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
+                    float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                    if (REC == 0 && eager) {       // eager f64 fields (dense / tiles / diffusion): phero / max_val
+                        v1 = (float)(__hiloint2double((int)lo[u].y, (int)lo[u].x) * inv_max);
+                        v2 = (float)(__hiloint2double((int)lo[u].w, (int)lo[u].z) * inv_max);
+                    }
+                    const float v0 = occupied ? 1.f : 0.f;                                   // :136-142
+                    const float v3 = hill ? 1.f : 0.f;                                       // :130-131 (disc bit of the record)
+                    const float v4 = wl ? 1.f : 0.f;                                         // :128-129
+                    const float v6 = ((rbits >> j) & 1u) ? 1.f : 0.f;                        // :132-135
+                    const uint32_t vis = (mrow >> j) & 1u;     // masked slots keep the -1 written once above
+                    const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
+                    if (LAYOUT == 2)
+                        asm volatile("{\n .reg .pred pv;\n setp.ne.u32 pv, %0, 0;\n"
+                                     " @pv st.shared.f32 [%1], %2;\n @pv st.shared.f32 [%1+4], %3;\n"
+                                     " @pv st.shared.f32 [%1+8], %4;\n @pv st.shared.f32 [%1+12], %5;\n"
+                                     " @pv st.shared.f32 [%1+16], %6;\n @pv st.shared.f32 [%1+20], %7;\n"
+                                     " @pv st.shared.f32 [%1+24], %8;\n}"
+                                     ::"r"(vis), "r"(oaddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5), "f"(v6) : "memory");
+                    else
+                        asm volatile("{\n .reg .pred pv;\n setp.ne.u32 pv, %0, 0;\n"
+                                     " @pv st.shared.f32 [%1], %2;\n @pv st.shared.f32 [%1+4], %3;\n"
+                                     " @pv st.shared.f32 [%1+8], %4;\n @pv st.shared.f32 [%1+12], %5;\n"
+                                     " @pv st.shared.f32 [%1+16], %6;\n @pv st.shared.f32 [%1+20], %7;\n}"
+                                     ::"r"(vis), "r"(oaddr), "f"(v0), "f"(v1), "f"(v2), "f"(v3), "f"(v4), "f"(v5) : "memory");
+                }
+            }
+            if (any_plain) {   // plain pheromone values (bool activations, imports, eager modes) may exist: patch them in
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int j = j0 + u;
+                    if (j >= S || !((mrow >> j) & 1u)) continue;
+                    const uint8_t *rp = cells + ((size_t)cell[u] << SH);
+                    bool pl0, pl1;
+                    if (REC8) {
+                        const uint2 r2 = *reinterpret_cast<const uint2 *>(rp);
+                        pl0 = (r2.x & 0xFFFFu) == 1u; pl1 = (r2.x >> 16) == 1u;
+                        if ((r2.y & 0xFFFFu) == kFoodEsc)                  // a non-integer amount of food
+                            asm volatile("st.shared.f32 [%0+20], %1;" ::"r"(orow_s + (uint32_t)(j * C * 4)), "f"((float)ld_food(p, rp)) : "memory");
+                    } else {
+                        const uint4 r4 = *reinterpret_cast<const uint4 *>(rp);
+                        pl0 = REC16 ? (r4.x != 0u && !is_boxed32(r4.x))
+                                    : ((r4.x | r4.y) != 0u && !(p.lazy && (r4.y & 0xFFF80000u) == 0x7FF80000u));
+                        pl1 = REC16 ? (r4.y != 0u && !is_boxed32(r4.y))
+                                    : ((r4.z | r4.w) != 0u && !(p.lazy && (r4.w & 0xFFF80000u) == 0x7FF80000u));
+                    }
+                    const uint32_t oaddr = orow_s + (uint32_t)(j * C * 4);
+                    if (pl0) asm volatile("st.shared.f32 [%0+4], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 0, now, now_abs)) : "memory");
+                    if (pl1) asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(oaddr), "f"(phero_obs_slow(p, rp, 1, now, now_abs)) : "memory");
+                }
+            }
         }
-        // flush the staged (n_in x S2 x C) f32 tile: one TMA bulk store when 16 B granular, else plain stores
+        return cnt;
+    };
+    // flush n_in ants' staged (S2 x C) f32 observations: one TMA bulk store when 16 B granular, else plain stores
+    auto flush = [&](const float *wobs, int64_t i0, int n_in) {
         float *dst = obs + i0 * SC;
         const uint32_t bytes = (uint32_t)(n_in * SC * 4);
         if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
@@ -407,6 +376,82 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             __syncwarp();
             for (int t = lane; t < n_in * SC; t += 32) dst[t] = wobs[t];
             __syncwarp();
+        }
+    };
+    const int64_t wbase = base + warp * 32;
+    const int n_valid = (p.EN - wbase >= 32) ? 32 : (p.EN > wbase ? (int)(p.EN - wbase) : 0);   // ants of this warp
+    if (FLAT) {
+        // All 32 ants of the warp as 32 * S rows: iteration t hands rows 32t .. 32t+31 to the lanes (no idle lanes:
+        // S iterations instead of 32 / 4 chunks of 4 * S <= 32 rows).  Ant a stages into slot (a / 4) & 1 of two
+        // 4-ant tiles; with S = 7 an iteration touches chunks t and t + 1 only, and chunk t is complete after it.
+        const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(wobs0);
+        for (int rr = lane; rr < 2 * ROWS; rr += 32) {             // masked samples read -1 (RL_api.py:147-148): written once
+            const int slot = rr / ROWS, rem = rr - slot * ROWS, a4 = rem / S, li = rem - a4 * S;
+            const uint32_t m = p.mask_rows[li];
+            const uint32_t o = tiles_s + (uint32_t)((slot * TILE + (a4 * S2 + li * S) * C) * 4);
+            for (int j = 0; j < S; ++j)
+                if (!((m >> j) & 1u))
+                    for (int c = 0; c < C; ++c)
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(o + (uint32_t)((j * C + c) * 4)), "f"(-1.f) : "memory");
+        }
+        __syncwarp();
+        const int chunks_total = (n_valid + G - 1) / G;
+        int flushed = 0;
+        for (int t = 0; t < S; ++t) {
+            const int nrows = n_valid * S - 32 * t;                // rows left for this iteration
+            if (nrows <= 0) break;
+            const int r = 32 * t + lane;
+            const int la = r / S, li = r - la * S;                 // ant of the warp, window row
+            const uint32_t amask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
+            if (lane < nrows) {
+                const uint32_t orow_s = tiles_s + (uint32_t)((((la >> 2) & 1) * TILE + ((la & 3) * S2 + li * S) * C) * 4);
+                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask);
+                s_rowcnt[(warp * 32 + la) * S + li] = (uint8_t)cnt;
+            }
+            const bool last = nrows <= 32;
+            int c_hi = last ? chunks_total : (32 * (t + 1)) / ROWS;
+            if (c_hi > chunks_total) c_hi = chunks_total;
+            for (; flushed < c_hi; ++flushed) {
+                const int left = n_valid - G * flushed;
+                flush(wobs0 + (flushed & 1) * TILE, wbase + G * flushed, left < G ? left : G);
+            }
+        }
+    } else {
+        const int la = lane / S, li = lane - la * S;
+        const bool lane_on = lane < ROWS;
+        const double offY = p.off_c[lane_on ? li : 0];
+        uint32_t mrow = p.mask_rows[lane_on ? li : 0];
+        // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
+        uint32_t orow_s0 = (uint32_t)__cvta_generic_to_shared(wobs0 + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
+        asm volatile("" : "+r"(orow_s0), "+r"(mrow));                // keep them in registers (no rematerialisation)
+        // masked samples read -1 in every channel (RL_api.py:147-148) and their tile slots are never written again
+        if (lane_on) {
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (!((mrow >> j) & 1u))
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int t = 0; t < kRowsTiles; ++t)
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s0 + (uint32_t)((t * TILE + j * C + c) * 4)), "f"(-1.f) : "memory");
+        }
+        for (int g = 0; g < 32; g += G) {
+            const int64_t i0 = wbase + g;
+            if (i0 >= p.EN) break;
+            const int n_in = (p.EN - i0 < G) ? (int)(p.EN - i0) : G;
+            const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
+            float *wobs = wobs0 + tsel * TILE;
+            const uint32_t orow_s = orow_s0 + (uint32_t)(tsel * TILE * 4);
+            const uint32_t amask = (n_in * S >= 32) ? 0xffffffffu : ((1u << (n_in * S)) - 1u);   // the lanes with a row
+            if (!kLateWait) {
+                if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
+                __syncwarp();
+            }
+            if (lane_on && la < n_in) {
+                const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask);
+                s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
+            }
+            flush(wobs, i0, n_in);
         }
     }
     __syncwarp();
