@@ -1368,6 +1368,21 @@ __global__ void k_hill_mark(Params p) {
 // generation counters are 16 bit: before one wraps, fold every live stamp into the "long ago" value
 __global__ void k_meta_renormalize(Params p, int fold_explored, int clear_occ) {
     int64_t n = (int64_t)p.E * p.plane;
+    if (p.rec8) {   // two 8-byte records per 128-bit access; the stamps are the high halves of words 1 and 3
+        uint4 *recs = reinterpret_cast<uint4 *>(p.cells);
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n / 2; j += (int64_t)gridDim.x * blockDim.x) {
+            uint4 v = recs[j];
+            auto fix = [&](uint32_t w) -> uint32_t {
+                uint32_t occ = (w >> 16) & 0xFFu, ex = w >> 24;               // [hill|occ_gen], [wall|explored_gen]
+                if (fold_explored) { const uint32_t g = ex & 0x7Fu; if (g != 0u && g != 0x7Fu) ex |= 0x7Fu; }
+                if (clear_occ) occ &= 0x80u;
+                return (w & 0xFFFFu) | (occ << 16) | (ex << 24);
+            };
+            const uint32_t y = fix(v.y), w = fix(v.w);
+            if (y != v.y || w != v.w) { v.y = y; v.w = w; recs[j] = v; }
+        }
+        return;
+    }
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         uint8_t *r = p.cells + (j << p.rec_shift);
         if (fold_explored) { uint32_t g = ld_explored(p, r); if (g != 0u && g != p.explored_old) st_explored(p, r, p.explored_old); }
