@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "ants_import_state", "ants_export_state", "ants_activate_all_pheromones", "ants_observe", "ants_step",
     "ants_update", "ants_rollout", "ants_host_alloc", "ants_host_free", "ants_observe_host", "ants_step_host",
     "ants_update_host", "ants_get_stats", "ants_set_profiling", "ants_get_kernel_ms", "ants_reset_kernel_ms",
-    "ants_sample_actions",
+    "ants_sample_actions", "ants_export_env_state",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library(path=None):
     lib.ants_synchronize.argtypes = [vp]
     lib.ants_import_state.argtypes = [vp, C.POINTER(AntsHostState)]
     lib.ants_export_state.argtypes = [vp, C.POINTER(AntsHostState)]
+    lib.ants_export_env_state.argtypes = [vp, i32, i32, C.POINTER(AntsHostState)]
     lib.ants_activate_all_pheromones.argtypes = [vp, vp, i32]
     lib.ants_observe.argtypes = [vp, vp, vp, vp, vp]
     lib.ants_step.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(i32)]

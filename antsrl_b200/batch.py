@@ -142,8 +142,8 @@ class BatchedAnts:
             pass
 
     # ------------------------------------------------------------------ state
-    def _shapes(self):
-        E, N, W, H, P, R = self.E, self.N, self.W, self.H, self.P, self.R
+    def _shapes(self, n_envs=None):
+        E, N, W, H, P, R = self.E if n_envs is None else n_envs, self.N, self.W, self.H, self.P, self.R
         sh = {k: (E, N) for k in ("x", "y", "theta", "prev_x", "prev_y", "prev_theta", "holding", "seed",
                                   "rw_holding_prev", "rw_prev_dist", "rewards", "mandibles", "reward_state")}
         sh.update(activation=(E, N, P), phero=(E, P, W, H), food=(E, W, H), walls=(E, W, H), explored=(E, W, H),
@@ -175,8 +175,13 @@ class BatchedAnts:
         hs.act_bool = 1 if state.get("act_bool", True) else 0
         check(self.lib, self.lib.ants_import_state(self._h, C.byref(hs)))
 
-    def export_state(self, keys=None):
-        sh = self._shapes()
+    def export_state(self, keys=None, envs=None):
+        """The state dict of the whole batch, or with ``envs=(env0, n)`` of that window of environments only
+        (arrays then have a leading axis of n) -- what a snapshot of one environment of a large batch needs."""
+        env0, n_envs = (0, self.E) if envs is None else (int(envs[0]), int(envs[1]))
+        if env0 < 0 or n_envs < 1 or env0 + n_envs > self.E:
+            raise ValueError("env window (%d, %d) outside the batch of %d envs" % (env0, n_envs, self.E))
+        sh = self._shapes(n_envs)
         hs = AntsHostState()
         out = {}
         for k in _STATE_F64 + _STATE_U8 + ("anthill_xyr",):
@@ -190,7 +195,7 @@ class BatchedAnts:
             ptr_t = {np.float64: C.POINTER(C.c_double), np.uint8: C.POINTER(C.c_uint8),
                      np.int32: C.POINTER(C.c_int32)}[dt]
             setattr(hs, k, a.ctypes.data_as(ptr_t))
-        check(self.lib, self.lib.ants_export_state(self._h, C.byref(hs)))
+        check(self.lib, self.lib.ants_export_env_state(self._h, env0, n_envs, C.byref(hs)))
         out["timestep"] = int(hs.timestep)
         out["rw_alias"] = bool(hs.rw_alias)
         out["act_bool"] = bool(hs.act_bool)

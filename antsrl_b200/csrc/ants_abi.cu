@@ -845,29 +845,33 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     return ANTS_OK;
 }
 
-int ants_export_state(AntsBatch *b, AntsHostState *s) {
+int ants_export_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, AntsHostState *s) {
     if (!b || !s) return fail(ANTS_E_ARG, "null argument");
-    CK(cudaSetDevice(b->cfg.device));
     Params &p = b->p;
+    if (env0 < 0 || n_envs < 1 || (int64_t)env0 + n_envs > p.E)
+        return fail(ANTS_E_ARG, "env window [%d, %d) outside the batch of %d envs", env0, env0 + n_envs, p.E);
+    CK(cudaSetDevice(b->cfg.device));
     cudaStream_t st = b->stream;
-    const size_t EN8 = (size_t)p.EN * sizeof(double);
+    const size_t a0 = (size_t)env0 * p.N, an = (size_t)n_envs * p.N;      // the window's ants
     auto down = [&](double *dst, const double *src) -> cudaError_t {
-        return dst ? cudaMemcpyAsync(dst, src, EN8, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+        return dst ? cudaMemcpyAsync(dst, src + a0, an * sizeof(double), cudaMemcpyDeviceToHost, st) : cudaSuccess;
     };
     CK(down(s->x, p.x)); CK(down(s->y, p.y)); CK(down(s->theta, p.theta));
     CK(down(s->prev_x, p.prev_x)); CK(down(s->prev_y, p.prev_y)); CK(down(s->prev_theta, p.prev_theta));
     CK(down(s->holding, p.holding)); CK(down(s->seed, p.seed));
     CK(down(s->rw_holding_prev, p.rw_holding_prev)); CK(down(s->rw_prev_dist, p.rw_prev_dist));
     CK(down(s->rewards, p.rewards));
-    if (s->mandibles) CK(cudaMemcpyAsync(s->mandibles, p.mandibles, p.EN, cudaMemcpyDeviceToHost, st));
-    if (s->reward_state) CK(cudaMemcpyAsync(s->reward_state, p.reward_state, p.EN, cudaMemcpyDeviceToHost, st));
-    std::vector<double> act_t;
+    if (s->mandibles) CK(cudaMemcpyAsync(s->mandibles, p.mandibles + a0, an, cudaMemcpyDeviceToHost, st));
+    if (s->reward_state) CK(cudaMemcpyAsync(s->reward_state, p.reward_state + a0, an, cudaMemcpyDeviceToHost, st));
+    std::vector<double> act_t;                                             // device layout [P][E*N]
     if (s->activation && p.P > 0) {
-        act_t.resize((size_t)p.EN * p.P);
-        CK(cudaMemcpyAsync(act_t.data(), p.act, act_t.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+        act_t.resize(an * p.P);
+        for (int k = 0; k < p.P; ++k)
+            CK(cudaMemcpyAsync(act_t.data() + (size_t)k * an, p.act + (size_t)k * p.EN + a0, an * sizeof(double),
+                               cudaMemcpyDeviceToHost, st));
     }
     // map fields: unpack kernel from the cell records -> device scratch -> dense host array
-    const size_t ncell = (size_t)p.E * p.W * p.H;
+    const size_t ncell = (size_t)n_envs * p.W * p.H;
     void *d_tmp = nullptr;
     if ((s->phero && p.P > 0) || s->food || s->walls || s->explored) {
         size_t need = ncell * 8 * ((s->phero && p.P > 1) ? p.P : 1);
@@ -875,43 +879,45 @@ int ants_export_state(AntsBatch *b, AntsHostState *s) {
         if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "export scratch of %zu bytes: %s", need, cudaGetErrorString(me));
     }
     if (s->phero && p.P > 0) {
-        for (int k = 0; k < p.P; ++k) ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs);
+        for (int k = 0; k < p.P; ++k)
+            ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs, env0, n_envs);
         TRY(check_launch("k_unpack_f64"));
         CK(cudaMemcpyAsync(s->phero, d_tmp, ncell * 8 * p.P, cudaMemcpyDeviceToHost, st));
     }
     if (s->food) {
-        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off, -1, 0u, 0u);
+        ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, 1, 0, p.food_off, -1, 0u, 0u, env0, n_envs);
         TRY(check_launch("k_unpack_f64"));
         CK(cudaMemcpyAsync(s->food, d_tmp, ncell * 8, cudaMemcpyDeviceToHost, st));
     }
     if (s->walls) {
-        ants::k_unpack_u8<<<148 * 8, 256, 0, st>>>(p, (uint8_t *)d_tmp, 0);
+        ants::k_unpack_u8<<<148 * 8, 256, 0, st>>>(p, (uint8_t *)d_tmp, 0, env0, n_envs);
         TRY(check_launch("k_unpack_u8"));
         CK(cudaMemcpyAsync(s->walls, d_tmp, ncell, cudaMemcpyDeviceToHost, st));
     }
     if (s->explored) {
-        ants::k_unpack_u8<<<148 * 8, 256, 0, st>>>(p, (uint8_t *)d_tmp, 1);
+        ants::k_unpack_u8<<<148 * 8, 256, 0, st>>>(p, (uint8_t *)d_tmp, 1, env0, n_envs);
         TRY(check_launch("k_unpack_u8"));
         CK(cudaMemcpyAsync(s->explored, d_tmp, ncell, cudaMemcpyDeviceToHost, st));
     }
     std::vector<int32_t> hill4;
     if (s->anthill_xyr) {
-        hill4.resize((size_t)p.E * 4);
-        CK(cudaMemcpyAsync(hill4.data(), p.hill, hill4.size() * 4, cudaMemcpyDeviceToHost, st));
+        hill4.resize((size_t)n_envs * 4);
+        CK(cudaMemcpyAsync(hill4.data(), p.hill + (size_t)env0 * 4, hill4.size() * 4, cudaMemcpyDeviceToHost, st));
     }
-    if (s->anthill_food) CK(cudaMemcpyAsync(s->anthill_food, p.hill_food, (size_t)p.E * 8, cudaMemcpyDeviceToHost, st));
+    if (s->anthill_food) CK(cudaMemcpyAsync(s->anthill_food, p.hill_food + env0, (size_t)n_envs * 8, cudaMemcpyDeviceToHost, st));
     if (p.R > 0) {
-        if (s->rock_centers) CK(cudaMemcpyAsync(s->rock_centers, p.rock_c, (size_t)p.E * p.R * 16, cudaMemcpyDeviceToHost, st));
-        if (s->rock_radii) CK(cudaMemcpyAsync(s->rock_radii, p.rock_rad, (size_t)p.E * p.R * 8, cudaMemcpyDeviceToHost, st));
-        if (s->rock_weights) CK(cudaMemcpyAsync(s->rock_weights, p.rock_w, (size_t)p.E * p.R * 8, cudaMemcpyDeviceToHost, st));
+        const size_t r0 = (size_t)env0 * p.R, rn = (size_t)n_envs * p.R;
+        if (s->rock_centers) CK(cudaMemcpyAsync(s->rock_centers, p.rock_c + r0 * 2, rn * 16, cudaMemcpyDeviceToHost, st));
+        if (s->rock_radii) CK(cudaMemcpyAsync(s->rock_radii, p.rock_rad + r0, rn * 8, cudaMemcpyDeviceToHost, st));
+        if (s->rock_weights) CK(cudaMemcpyAsync(s->rock_weights, p.rock_w + r0, rn * 8, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
     if (d_tmp) cudaFree(d_tmp);
     if (s->activation && p.P > 0)
-        for (int64_t i = 0; i < p.EN; ++i)
-            for (int k = 0; k < p.P; ++k) s->activation[i * p.P + k] = act_t[(size_t)k * p.EN + i];
+        for (size_t i = 0; i < an; ++i)
+            for (int k = 0; k < p.P; ++k) s->activation[i * p.P + k] = act_t[(size_t)k * an + i];
     if (s->anthill_xyr)
-        for (int e = 0; e < p.E; ++e) {
+        for (int e = 0; e < n_envs; ++e) {
             s->anthill_xyr[3 * e] = hill4[4 * e]; s->anthill_xyr[3 * e + 1] = hill4[4 * e + 1];
             s->anthill_xyr[3 * e + 2] = hill4[4 * e + 2];
         }
@@ -919,6 +925,11 @@ int ants_export_state(AntsBatch *b, AntsHostState *s) {
     s->rw_alias = b->rw_alias;
     s->act_bool = b->act_bool;
     return ANTS_OK;
+}
+
+int ants_export_state(AntsBatch *b, AntsHostState *s) {
+    if (!b) return fail(ANTS_E_ARG, "null argument");
+    return ants_export_env_state(b, 0, b->p.E, s);
 }
 
 int ants_activate_all_pheromones(AntsBatch *b, const double *act, int32_t is_bool) {

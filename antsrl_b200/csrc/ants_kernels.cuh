@@ -1316,18 +1316,20 @@ __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int plane
         }
     }
 }
+// export of the envs [env0, env0 + n_env): dense arrays are indexed by the env's position in that window
 __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_per_env, int k, int byte_off,
-                             int phero_k, uint32_t now, uint32_t now_abs) {
-    const int64_t n = (int64_t)p.E * p.W * p.H;
+                             int phero_k, uint32_t now, uint32_t now_abs, int env0, int n_env) {
+    const int64_t n = (int64_t)n_env * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
-        int64_t e = ex / p.W;
-        int x = (int)(ex - e * p.W);
-        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
-        double v = phero_k >= 0 ? (p.diffuse ? plane_value(p, (int)e, phero_k, x, y) : phero_value(p, r, phero_k, now, now_abs))
+        int64_t el = ex / p.W;
+        int x = (int)(ex - el * p.W);
+        const int e = env0 + (int)el;
+        uint8_t *r = rec_at(p, e, cidx(p, x, y));
+        double v = phero_k >= 0 ? (p.diffuse ? plane_value(p, e, phero_k, x, y) : phero_value(p, r, phero_k, now, now_abs))
                                 : ld_food(p, r);
-        dense[((e * planes_per_env + k) * p.W + x) * p.H + y] = v;
+        dense[((el * planes_per_env + k) * p.W + x) * p.H + y] = v;
     }
 }
 // what: 0 = walls (stored as 0/1), 1 = explored (meta low half: 0xFFFF = explored long ago; occupancy cleared)
@@ -1343,14 +1345,14 @@ __global__ void k_pack_u8(Params p, const uint8_t *__restrict__ dense, int what)
         else { st_explored(p, r, dense[j] ? p.explored_old : 0u); st_occ(p, r, 0u); }
     }
 }
-__global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what) {
-    const int64_t n = (int64_t)p.E * p.W * p.H;
+__global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what, int env0, int n_env) {
+    const int64_t n = (int64_t)n_env * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
-        int64_t e = ex / p.W;
-        int x = (int)(ex - e * p.W);
-        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
+        int64_t el = ex / p.W;
+        int x = (int)(ex - el * p.W);
+        uint8_t *r = rec_at(p, env0 + (int)el, cidx(p, x, y));
         dense[j] = what == 0 ? (ld_wall(p, r) ? 1 : 0) : (ld_explored(p, r) ? 1 : 0);
     }
 }

@@ -134,7 +134,7 @@ class DeviceBridge:
         for k, ph in enumerate(self.pheros):
             ph._phero = st["phero"][0, k]
         self.food._qte = st["food"][0]
-        self.hill._food = float(st["anthill_food"][0])
+        self.hill._food = np.float64(st["anthill_food"][0])       # anthill.py:46: int 0 + np.sum(...)
         if self.rocks is not None:
             self.rocks._centers = st["rock_centers"][0]
         rw = self.api.reward if self.api is not None else None

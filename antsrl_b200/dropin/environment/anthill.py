@@ -15,6 +15,8 @@ class AnthillVisualization(EnvObject):
 
 
 class Anthill(EnvObject):
+    _MIRRORS = ("food",)
+
     def __init__(self, environment: Environment, x, y, radius):
         super().__init__(environment)
         self.w = environment.w

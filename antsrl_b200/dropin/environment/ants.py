@@ -26,6 +26,8 @@ def _device_only(name):
 
 
 class Ants(EnvObject):
+    _MIRRORS = ("ants", "prev_ants", "mandibles", "holding", "reward_state", "phero_activation", "seed")
+
     def __init__(self, environment: Environment, n_ants: int, max_hold, xyt=None):
         super().__init__(environment)
         self.n_ants = n_ants

@@ -14,6 +14,8 @@ class CircleObstaclesVisualization(EnvObject):
 
 
 class CircleObstacles(EnvObject):
+    _MIRRORS = ("centers",)
+
     def __init__(self, environment: Environment, centers, radiuses, weights):
         super().__init__(environment)
         self.w = environment.w

@@ -26,6 +26,27 @@ class EnvObject:
         if env is not None and env._bridge is not None:
             env._bridge.pull()
 
+    # Pickling (main.py:139-147 pickles the list of save_state() copies; Walls.visualize_copy returns the live
+    # object, walls.py:16-17, so the live environment hangs off every snapshot): the pickled state uses the
+    # reference's attribute names, so a file written here loads under the reference's classes (the pygame viewer)
+    # and a file written by the reference loads here.
+    _MIRRORS = ()      # attributes mirrored from the device, kept as _<name> on the host object
+
+    def __getstate__(self):
+        self._pull()
+        d = dict(self.__dict__)
+        for name in self._MIRRORS:
+            if "_" + name in d:
+                d[name] = d.pop("_" + name)
+        return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        for name in self._MIRRORS:
+            if name in d:
+                d["_" + name] = d.pop(name)
+        self.__dict__.update(d)
+
 
 class Environment:
     def __init__(self, w, h, max_time):
@@ -60,6 +81,21 @@ class Environment:
         for obj in self.objects:
             newenv.add_object(obj.visualize_copy(newenv))
         return newenv
+
+    def __getstate__(self):
+        """The reference's attributes (environment.py:22-27); the device handle stays behind, the host mirrors of
+        the objects are refreshed first, so an unpickled Environment continues on a new handle."""
+        if self._bridge is not None:
+            self._bridge.pull()
+        return {"w": self.w, "h": self.h, "objects": self.objects, "max_time": self.max_time,
+                "timestep": self._timestep}
+
+    def __setstate__(self, d):
+        d = dict(d)
+        self._timestep = int(d.pop("timestep", 1))
+        self._bridge = None
+        self.collision_noise = None
+        self.__dict__.update(d)
 
     def device(self):
         """The CUDA backend of this environment (created on first use from the attached objects)."""

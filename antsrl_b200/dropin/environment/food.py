@@ -11,6 +11,8 @@ class FoodVisualization(EnvObject):
 
 
 class Food(EnvObject):
+    _MIRRORS = ("qte",)
+
     def __init__(self, environment: Environment, qte):
         super().__init__(environment)
         self._qte = qte.astype(float)

@@ -21,6 +21,8 @@ class PheromoneVisualization(EnvObject):
 
 
 class Pheromone(EnvObject):
+    _MIRRORS = ("phero",)
+
     def __init__(self, environment: Environment, color=(64, 64, 64), max_val=None, phero=None):
         super().__init__(environment)
         self.color = color

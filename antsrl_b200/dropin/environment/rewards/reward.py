@@ -24,6 +24,26 @@ class Reward(ABC):
         self._rewards = np.zeros(self.ants.n_ants, dtype=float)
         self._aliased = True
 
+    # pickled under the reference's attribute names (see EnvObject.__getstate__)
+    _MIRRORS = ("rewards", "explored_map", "previous_dist", "ants_holding")
+
+    def __getstate__(self):
+        if self.ants is not None:
+            self.ants._pull()
+        d = dict(self.__dict__)
+        for name in self._MIRRORS:
+            if "_" + name in d:
+                d[name] = d.pop("_" + name)
+        return d
+
+    def __setstate__(self, d):
+        d = dict(d)
+        for name in self._MIRRORS:
+            if name in d:
+                d["_" + name] = d.pop(name)
+        d.setdefault("_aliased", False)
+        self.__dict__.update(d)
+
     def observation(self, obs_coords, perception, agent_state):
         pass
 

@@ -22,6 +22,18 @@ class _ExploredMixin:
         return None if m is None else m.copy()
 
 
+def _mirrored(name):
+    """Public attribute of the reference (reward_custom.py:30,52-60) kept as _<name> and refreshed from the device."""
+    def get(self):
+        if self.ants is not None:
+            self.ants._pull()
+        return getattr(self, "_" + name)
+
+    def set_(self, v):
+        setattr(self, "_" + name, v)
+    return property(get, set_)
+
+
 class ExplorationReward(_ExploredMixin, Reward):
     def __init__(self):
         super(ExplorationReward, self).__init__()
@@ -33,6 +45,8 @@ class ExplorationReward(_ExploredMixin, Reward):
 
 
 class Food_Reward(Reward):
+    ants_holding = _mirrored("ants_holding")
+
     def __init__(self):
         super(Food_Reward, self).__init__()
         self._ants_holding = None
@@ -43,6 +57,9 @@ class Food_Reward(Reward):
 
 
 class All_Rewards(_ExploredMixin, Reward):
+    ants_holding = _mirrored("ants_holding")
+    previous_dist = _mirrored("previous_dist")
+
     def __init__(self, fct_explore=1, fct_food=1, fct_anthill=5, fct_explore_holding=0, fct_headinganthill=1):
         super(All_Rewards, self).__init__()
         self._explored_map = None

@@ -142,6 +142,10 @@ int ants_synchronize(AntsBatch *b);
 /* state in / out (host pointers, dense layout).  Also how reference-generated maps reach the GPU. */
 int ants_import_state(AntsBatch *b, const AntsHostState *s);
 int ants_export_state(AntsBatch *b, AntsHostState *s);
+/* the same for the envs [env0, env0 + n_envs) only: the host arrays hold n_envs environments.  This is what
+ * Environment.save_state() (environment.py:36-40: a visualize_copy of every object, pickled by main.py:139-147 for
+ * the viewer) needs for ONE environment of a large batch without moving the other E - 1. */
+int ants_export_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, AntsHostState *s);
 
 /* Ants.activate_all_pheromones, ants.py:86-87.  act: host [E][N][P] */
 int ants_activate_all_pheromones(AntsBatch *b, const double *act, int32_t is_bool);

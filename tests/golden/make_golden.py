@@ -180,3 +180,47 @@ if __name__ == "__main__" and (not sys.argv[1:] or "gen" in sys.argv[1:]):
     make_generator_fixtures()
 if __name__ == "__main__" and (not sys.argv[1:] or "mainloop" in sys.argv[1:]):
     make_mainloop_fixture()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Snapshot fixture: the file main.py:136-147 writes for the viewer -- pickle.dump of the list of
+# env.save_state() copies (environment.py:36-40), one per step -- from the unmodified reference with rocks.
+ARL_CASE = dict(w=48, h=40, n_ants=12, n_rocks=2, walls=(4, 3, 6), food=(6, 3, 5), seed=7, steps=10,
+                np_seed=99, action_seed=5)
+
+
+def make_episode_arl_fixture():
+    import pickle
+    c = ARL_CASE
+    ref = ref_harness.load_reference()
+    ref_harness.set_diffuse(ref, 0, 0.001)
+    ref.gen.n_rocks = c["n_rocks"]                                   # Q17 workaround, as above
+    reward = ref.rewards.All_Rewards(1, 2, 10, 1, 3)
+    api = ref.api.RLApi(reward, 1, 1, 40 / 180 * np.pi, 0.05, 0.5)
+    g = ref.gen.EnvironmentGenerator(c["w"], c["h"], c["n_ants"], 2, c["n_rocks"],
+                                     ref.maps.CirclesGenerator(*c["food"]), ref.maps.CirclesGenerator(*c["walls"]),
+                                     c["steps"], seed=c["seed"])
+    env = g.generate(api)
+    api.ants.activate_all_pheromones(np.ones((c["n_ants"], 2)) * 10)
+    np.random.seed(c["np_seed"])
+    act = np.random.RandomState(c["action_seed"])
+    ref.walls_proxy.noise_row = None
+    api.observation()
+    states = []
+    for t in range(c["steps"]):
+        rot = act.randint(0, 3, c["n_ants"]) - 1
+        ph = act.randint(0, 3, c["n_ants"])
+        api.step(rot, ph)
+        ref.walls_proxy.noise_row = None
+        env.update()
+        states.append(env.save_state())                              # main.py:136-137
+    path = os.path.join(HERE, "episode_s7.arl")
+    with open(path, "wb") as f:
+        pickle.dump(states, f)                                       # main.py:139-147 (first episode: [] + states)
+    with open(os.path.join(HERE, "episode_s7.json"), "w") as f:
+        json.dump(c, f)
+    print("episode_s7.arl %.1f KB, %d states" % (os.path.getsize(path) / 1024, len(states)))
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "arl" in sys.argv[1:]):
+    make_episode_arl_fixture()

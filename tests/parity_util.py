@@ -27,6 +27,11 @@ def stack_init(cfg, inits):
     return out
 
 
+def import_scenarios(batch, scenarios):
+    """Upload the initial states of a list of (cfg, init, tape) scenarios into a BatchedAnts batch."""
+    batch.import_state(stack_init(scenarios[0][0], [i for _, i, _ in scenarios]))
+
+
 def assert_close(a, b, what, rtol=RTOL, atol=ATOL):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
