@@ -224,3 +224,57 @@ def make_episode_arl_fixture():
 
 if __name__ == "__main__" and (not sys.argv[1:] or "arl" in sys.argv[1:]):
     make_episode_arl_fixture()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Long-horizon fixture (BASELINE.json configs[0]: the default 200x200 map with 50 ants driven by random actions for
+# 1000 steps): per-step summaries instead of full observations keep it small.
+LONG_KW = dict(seed=1001, w=200, h=200, n_ants=50, steps=1000, n_walls=10, n_food=20, wall_r=(5, 15), food_r=(5, 10))
+LONG_SNAP_EVERY = 250
+
+
+def long_summary(obs, agent_state, reward, st, cfg):
+    """One row of per-step summary; shared by the recorder and by tests/test_oracle_golden.py."""
+    cells = st["x"].astype(np.int64) * cfg["h"] + st["y"].astype(np.int64)
+    weights = np.arange(1, cells.size + 1, dtype=np.int64)
+    return np.array([st["x"].sum(), st["y"].sum(), st["theta"].sum(), np.asarray(reward, dtype=float).sum(),
+                     st["holding"].sum(), float(st["anthill_food"]), float(np.asarray(st["explored"]).sum()),
+                     st["phero"][0].sum(), st["phero"][1].sum(), st["food"].sum(), np.asarray(obs, dtype=float).sum(),
+                     np.asarray(agent_state, dtype=float).sum(), float((cells * weights).sum()),
+                     float(np.asarray(st["mandibles"]).astype(np.int64).sum()),
+                     float(np.asarray(st["reward_state"]).astype(np.int64).sum())])
+
+
+def make_long_fixture():
+    cfg, init, tape = make_scenario(**LONG_KW)
+    ref = ref_harness.load_reference()
+    ref_harness.set_diffuse(ref, cfg["diffuse_factor"], cfg["evap_factor"])
+    env, api, objs = ref_harness.build_env(ref, cfg, init)
+    objs["ants"].activate_all_pheromones(np.asarray(init["activation"], dtype=float))
+    api.observation()
+    T = tape["rot"].shape[0]
+    rows, snaps = [], {}
+    for t in range(T):
+        obs, agent_state, reward, done = api.step(tape["rot"][t].astype(np.int64), tape["ph"][t].astype(np.int64))
+        ref_harness.run_update(ref, env, tape["noise"][t])
+        st = ref_harness.export_state(env, api, objs)
+        rows.append(long_summary(obs, agent_state, reward, st, cfg))
+        if (t + 1) % LONG_SNAP_EVERY == 0:
+            snaps["snap%d" % (t + 1)] = np.stack([st["x"], st["y"], st["theta"], st["holding"],
+                                                   st["mandibles"].astype(float), st["reward_state"].astype(float)])
+    final = ref_harness.export_state(env, api, objs)
+    out = {"cfg_json": np.array(cfg_to_json(cfg)), "scenario_json": np.array(json.dumps(LONG_KW)),
+           "t_summary": np.array(rows), "done_last": np.bool_(done), "wall_hits": np.int64(ref.walls_proxy.hits)}
+    ref.walls_proxy.hits = 0
+    out.update(snaps)
+    for k in ("x", "y", "theta", "holding", "mandibles", "reward_state", "phero", "food", "explored", "anthill_food",
+              "rewards", "rw_prev_dist", "rw_holding_prev", "timestep"):
+        out["final_" + k] = np.asarray(final[k])
+    path = os.path.join(HERE, "long_200_s1001.npz")
+    np.savez_compressed(path, **out)
+    print("long_200_s1001 T=%d hits=%d anthill_food=%.0f explored=%d  %.1f KB" % (
+        T, int(out["wall_hits"]), float(final["anthill_food"]), int(final["explored"].sum()), os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "long" in sys.argv[1:]):
+    make_long_fixture()

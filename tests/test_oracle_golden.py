@@ -53,3 +53,52 @@ def test_oracle_reproduces_reference(name):
     for k in ("mandibles", "reward_state", "walls", "explored"):
         assert np.array_equal(np.asarray(fin[k]).astype(np.uint8), rec["final_" + k]), "final " + k
     assert int(fin["timestep"]) == int(rec["final_timestep"])
+
+
+def test_oracle_reproduces_1000_step_episode():
+    """BASELINE.json configs[0]'s horizon: the default-sized map (200x200, 50 ants) under random actions for 1000
+    steps, recorded from the unmodified reference as per-step summaries, ant snapshots every 250 steps and the full
+    final state (tests/golden/make_golden.py long)."""
+    import json
+    import os
+    import sys
+    from golden_io import GOLDEN_DIR
+    from scenarios import make_scenario
+    sys.path.insert(0, GOLDEN_DIR)
+    z = np.load(os.path.join(GOLDEN_DIR, "long_200_s1001.npz"))
+    kw = json.loads(str(z["scenario_json"]))
+    for k in ("wall_r", "food_r"):
+        kw[k] = tuple(kw[k])
+    cfg, init, tape = make_scenario(**kw)
+
+    def summary(obs, agent_state, reward, st):       # the recorder's long_summary, restated (it imports the reference)
+        cells = st["x"].astype(np.int64) * cfg["h"] + st["y"].astype(np.int64)
+        weights = np.arange(1, cells.size + 1, dtype=np.int64)
+        return np.array([st["x"].sum(), st["y"].sum(), st["theta"].sum(), np.asarray(reward, dtype=float).sum(),
+                         st["holding"].sum(), float(st["anthill_food"]), float(np.asarray(st["explored"]).sum()),
+                         st["phero"][0].sum(), st["phero"][1].sum(), st["food"].sum(),
+                         np.asarray(obs, dtype=float).sum(), np.asarray(agent_state, dtype=float).sum(),
+                         float((cells * weights).sum()), float(np.asarray(st["mandibles"]).astype(np.int64).sum()),
+                         float(np.asarray(st["reward_state"]).astype(np.int64).sum())])
+
+    env = OracleEnv(cfg, init)
+    env.observation()
+    T = tape["rot"].shape[0]
+    assert T == 1000 == z["t_summary"].shape[0]
+    for t in range(T):
+        obs, agent_state, reward, done = env.step(tape["rot"][t].astype(np.int64), tape["ph"][t].astype(np.int64))
+        env.update(tape["noise"][t])
+        s = env.s
+        _close(summary(obs, agent_state, reward, s), z["t_summary"][t], "summary t=%d" % t)
+        if (t + 1) % 250 == 0:
+            snap = z["snap%d" % (t + 1)]
+            _close(np.stack([s["x"], s["y"], s["theta"], s["holding"]]), snap[:4], "snapshot t=%d" % t)
+            assert np.array_equal(s["mandibles"], snap[4].astype(np.uint8))
+            assert np.array_equal(s["reward_state"], snap[5].astype(np.uint8))
+    assert bool(done) == bool(z["done_last"])
+    fin = env.export()
+    for k in ("x", "y", "theta", "holding", "phero", "food", "anthill_food", "rewards", "rw_prev_dist", "rw_holding_prev"):
+        _close(fin[k], z["final_" + k], "final " + k)
+    for k in ("mandibles", "reward_state", "explored"):
+        assert np.array_equal(np.asarray(fin[k]).astype(np.uint8), z["final_" + k]), "final " + k
+    assert int(fin["timestep"]) == int(z["final_timestep"]) == 1001
