@@ -7,9 +7,16 @@ from .environment import Environment, EnvObject
 DIFFUSE_FACTOR = 0
 EVAP_FACTOR = 0.001
 
-DIFFUSE_FILTER = np.ones((3, 3)) * DIFFUSE_FACTOR
-DIFFUSE_FILTER[1, 1] = 1 - 8 * DIFFUSE_FACTOR
-DIFFUSE_FILTER *= 1 - EVAP_FACTOR
+
+
+def diffuse_filter(diffuse_factor, evap_factor):
+    """The 3x3 stencil of pheromone.py:7-10: ring = factor, centre = 1 - 8 factor, all scaled by (1 - evaporation)."""
+    f = np.full((3, 3), float(diffuse_factor))
+    f[1, 1] = 1 - 8 * diffuse_factor
+    return f * (1 - evap_factor)
+
+
+DIFFUSE_FILTER = diffuse_filter(DIFFUSE_FACTOR, EVAP_FACTOR)    # kept for callers that read it; the device gets the factors
 
 
 class PheromoneVisualization(EnvObject):
