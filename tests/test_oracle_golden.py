@@ -17,7 +17,11 @@ def _close(a, b, what):
 
 @pytest.mark.parametrize("name", golden_names())
 def test_oracle_reproduces_reference(name):
-    cfg, init, tape, rec = load_golden(name)
+    check_oracle_against_record(*load_golden(name))
+
+
+def check_oracle_against_record(cfg, init, tape, rec):
+    """The oracle driven by (init, tape) against a recording of the reference (make_golden.run_reference's keys)."""
     env = OracleEnv(cfg, init)
     obs0, agent_state0, state0 = env.observation()
     _close(obs0, rec["obs0"], "obs0"); _close(agent_state0, rec["agent_state0"], "agent_state0")
