@@ -58,3 +58,45 @@ def test_full_size_generated_env_against_the_reference():
             "noise": rs.random_sample((T, 1024)), "rot_none": np.zeros(T, bool), "ph_none": np.zeros(T, bool)}
     rec = make_golden.run_reference(gen.cfg, init, tape)
     check_oracle_against_record(gen.cfg, init, tape, rec)
+
+
+@pytest.mark.parametrize("n_rocks", [0, 5])
+def test_irregular_call_order_against_the_reference(n_rocks):
+    """tests/test_gpu_parity.py::test_irregular_call_order: observation / step / update in an order main.py never
+    uses, the reference and the oracle driven by the same call string, outputs and full state compared after every
+    call."""
+    import ref_harness
+    from scenarios import make_scenario
+    from oracle.antsrl_oracle import OracleEnv
+    from test_oracle_golden import _close
+    ref = ref_harness.load_reference()
+    for e in range(3):
+        cfg, init, tape = make_scenario(seed=900 + e, w=56, h=48, n_ants=40, n_rocks=n_rocks, steps=16, n_walls=6, n_food=8)
+        ref_harness.set_diffuse(ref, cfg["diffuse_factor"], cfg["evap_factor"])
+        env, api, objs = ref_harness.build_env(ref, cfg, init)
+        objs["ants"].activate_all_pheromones(np.asarray(init["activation"], dtype=float))
+        o = OracleEnv(cfg, init)
+        t = 0
+        for k, op in enumerate("ousussuuosuosusuuussu"):
+            what = "env %d call %d (%s)" % (e, k, op)
+            if op == "o":
+                want, got = api.observation(), o.observation()
+                for a, b_ in zip(got, want):
+                    _close(a, b_, what)
+            elif op == "s":
+                rot, ph = tape["rot"][t].astype(np.int64), tape["ph"][t].astype(np.int64)
+                want, got = api.step(rot, ph), o.step(rot, ph)
+                for a, b_ in zip(got[:3], want[:3]):
+                    _close(a, b_, what)
+                assert bool(got[3]) == bool(want[3]), what
+            else:
+                ref_harness.run_update(ref, env, tape["noise"][t])
+                o.update(tape["noise"][t])
+                t += 1
+            st, mine = ref_harness.export_state(env, api, objs), o.export()
+            for key in ("x", "y", "theta", "prev_x", "prev_y", "prev_theta", "holding", "activation", "phero", "food",
+                        "rewards", "rw_holding_prev", "rw_prev_dist", "rock_centers", "anthill_food"):
+                _close(mine[key], st[key], what + ": " + key)
+            for key in ("mandibles", "reward_state", "explored"):
+                assert np.array_equal(np.asarray(mine[key]).astype(np.uint8), st[key]), what + ": " + key
+            assert int(mine["timestep"]) == int(st["timestep"]), what
