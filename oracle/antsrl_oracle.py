@@ -74,18 +74,12 @@ def anthill_area(w, h, ax, ay, ar):
     return ((ax - xs) ** 2 + (ay - ys) ** 2) ** 0.5 <= ar
 
 
-def philox_uniform(seed, env_id, step, n_ants):
-    """Counter-based collision noise used by the CUDA path in throughput mode (no reference analogue: the
-    reference draws from the global numpy RNG, walls.py:28).  Philox4x32-10, counter = (ant, step, env_id, 0),
-    key = (seed_lo, seed_hi); u = ((r0 >> 5) * 2^26 + (r1 >> 6)) / 2^53."""
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11; Random123): ten rounds of
+    (c0, c1, c2, c3) <- (hi(M1*c2) ^ c1 ^ k0, lo(M1*c2), hi(M0*c0) ^ c3 ^ k1, lo(M0*c0)), the key bumped by the Weyl
+    constants after each round.  Counter words are uint64 arrays holding 32-bit values, the key two Python ints."""
     M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
     W0, W1 = 0x9E3779B9, 0xBB67AE85
-    c0 = np.arange(n_ants, dtype=np.uint64)
-    c1 = np.full(n_ants, step & 0xFFFFFFFF, dtype=np.uint64)
-    c2 = np.full(n_ants, env_id & 0xFFFFFFFF, dtype=np.uint64)
-    c3 = np.zeros(n_ants, dtype=np.uint64)
-    k0 = seed & 0xFFFFFFFF
-    k1 = (seed >> 32) & 0xFFFFFFFF
     mask = np.uint64(0xFFFFFFFF)
     for _ in range(10):
         p0 = M0 * c0
@@ -95,33 +89,33 @@ def philox_uniform(seed, env_id, step, n_ants):
         c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)), lo1, (hi0 ^ c3 ^ np.uint64(k1)), lo0
         k0 = (k0 + W0) & 0xFFFFFFFF
         k1 = (k1 + W1) & 0xFFFFFFFF
-    a = (c0 >> np.uint64(5)).astype(np.float64)
-    b = (c1 >> np.uint64(6)).astype(np.float64)
+    return c0, c1, c2, c3
+
+
+def _ant_counters(seed, env_id, step, n_ants, stream):
+    c0 = np.arange(n_ants, dtype=np.uint64)
+    c1 = np.full(n_ants, step & 0xFFFFFFFF, dtype=np.uint64)
+    c2 = np.full(n_ants, env_id & 0xFFFFFFFF, dtype=np.uint64)
+    c3 = np.full(n_ants, stream, dtype=np.uint64)
+    return philox4x32_10(c0, c1, c2, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+
+
+def philox_uniform(seed, env_id, step, n_ants):
+    """Counter-based collision noise used by the CUDA path in throughput mode (no reference analogue: the
+    reference draws from the global numpy RNG, walls.py:28).  Philox4x32-10, counter = (ant, step, env_id, 0),
+    key = (seed_lo, seed_hi); u = ((r0 >> 5) * 2^26 + (r1 >> 6)) / 2^53."""
+    r0, r1, _, _ = _ant_counters(seed, env_id, step, n_ants, 0)
+    a = (r0 >> np.uint64(5)).astype(np.float64)
+    b = (r1 >> np.uint64(6)).astype(np.float64)
     return (a * 67108864.0 + b) / 9007199254740992.0
 
 
 def philox_actions(seed, env_id, step, n_ants, n_rot=3, n_ph=3):
     """Mirror of the CUDA path's on-device action sampler (ants_sample_actions; the agents' exploration branch,
     collect_agent.py:172-177): Philox4x32-10, counter (ant, step, env_id, 1), value = (r * n) >> 32."""
-    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
-    W0, W1 = 0x9E3779B9, 0xBB67AE85
-    c0 = np.arange(n_ants, dtype=np.uint64)
-    c1 = np.full(n_ants, step & 0xFFFFFFFF, dtype=np.uint64)
-    c2 = np.full(n_ants, env_id & 0xFFFFFFFF, dtype=np.uint64)
-    c3 = np.ones(n_ants, dtype=np.uint64)
-    k0 = seed & 0xFFFFFFFF
-    k1 = (seed >> 32) & 0xFFFFFFFF
-    mask = np.uint64(0xFFFFFFFF)
-    for _ in range(10):
-        p0 = M0 * c0
-        p1 = M1 * c2
-        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
-        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
-        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)), lo1, (hi0 ^ c3 ^ np.uint64(k1)), lo0
-        k0 = (k0 + W0) & 0xFFFFFFFF
-        k1 = (k1 + W1) & 0xFFFFFFFF
-    rot = ((c0 * np.uint64(n_rot)) >> np.uint64(32)).astype(np.int64) - n_rot // 2
-    ph = ((c1 * np.uint64(n_ph)) >> np.uint64(32)).astype(np.int64)
+    r0, r1, _, _ = _ant_counters(seed, env_id, step, n_ants, 1)
+    rot = ((r0 * np.uint64(n_rot)) >> np.uint64(32)).astype(np.int64) - n_rot // 2
+    ph = ((r1 * np.uint64(n_ph)) >> np.uint64(32)).astype(np.int64)
     return rot, ph
 
 
