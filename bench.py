@@ -410,6 +410,13 @@ def run_reference(args):
     emit(line)
 
 
+def torchrun_command(n_gpus, argv, port=None):
+    """The contract's multi-GPU launch of this script: one process per GPU on one node, rendezvous on 127.0.0.1."""
+    port = port or (29500 + os.getpid() % 2000)
+    return [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(int(n_gpus)),
+            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + list(argv)
+
+
 _REAL_STDOUT = None
 
 
@@ -445,6 +452,14 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    if args.impl == "ours" and args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` typed by hand: become the launch the driver uses (one rank per GPU over NCCL)
+        os.dup2(_REAL_STDOUT, 1)
+        cmd = torchrun_command(args.gpus, sys.argv[1:])
+        os.execv(cmd[0], cmd)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and args.gpus != world:
+        sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; running on %d rank(s)\n" % (args.gpus, world, world))
     if args.impl == "reference":
         run_reference(args)
     else:

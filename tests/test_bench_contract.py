@@ -54,3 +54,12 @@ def test_algorithmic_bytes_follow_the_survey():
     assert abs(step - 3109) < 1                                              # bytes per ant-step in the bench line
     peak, src = bench.load_peaks()
     assert 5000 < peak < 9000 and ("measured" in src or "fallback" in src)
+
+
+def test_hand_typed_multi_gpu_run_becomes_the_torchrun_launch():
+    sys.path.insert(0, ROOT)
+    import bench
+    cmd = bench.torchrun_command(4, ["--gpus", "4", "--steps", "50"], port=29777)
+    assert cmd[:3] == [sys.executable, "-m", "torch.distributed.run"]
+    assert cmd[3:10] == ["--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1", "--master-port", "29777"]
+    assert cmd[10] == os.path.join(ROOT, "bench.py") and cmd[11:] == ["--gpus", "4", "--steps", "50"]
