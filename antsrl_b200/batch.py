@@ -170,9 +170,10 @@ class BatchedAnts:
             ptr_t = {np.float64: C.POINTER(C.c_double), np.uint8: C.POINTER(C.c_uint8),
                      np.int32: C.POINTER(C.c_int32)}[dt]
             setattr(hs, k, a.ctypes.data_as(ptr_t))
-        hs.timestep = int(state.get("timestep", 1))
-        hs.rw_alias = 1 if state.get("rw_alias", True) else 0
-        hs.act_bool = 1 if state.get("act_bool", True) else 0
+        # scalars: 0 / -1 = "leave as it is" (a fresh handle starts at timestep 1, aliased reward, bool activations)
+        hs.timestep = int(state["timestep"]) if state.get("timestep") is not None else 0
+        hs.rw_alias = (1 if state["rw_alias"] else 0) if state.get("rw_alias") is not None else -1
+        hs.act_bool = (1 if state["act_bool"] else 0) if state.get("act_bool") is not None else -1
         check(self.lib, self.lib.ants_import_state(self._h, C.byref(hs)))
 
     def export_state(self, keys=None, envs=None):
@@ -262,11 +263,26 @@ class BatchedAnts:
                 raise ValueError("noise must be a contiguous float64 CUDA tensor of shape (E, N)")
         check(self.lib, self.lib.ants_update(self._h, self._ptr(noise)))
 
-    def rollout(self, rot_tape, ph_tape):
-        """T x [step; update] with device-resident int8 tapes (T, E, N); returns the outputs of the last step."""
+    def _check_tape(self, a, name, T=None):
+        if a is None:
+            return None, T
+        t = self._torch
+        if not (isinstance(a, t.Tensor) and a.is_cuda and a.dtype == t.int8 and a.is_contiguous() and a.dim() == 3
+                and tuple(a.shape[1:]) == (self.E, self.N)):
+            raise ValueError("%s must be a contiguous int8 CUDA tensor of shape (T, E, N) or None" % name)
+        if T is not None and int(a.shape[0]) != T:
+            raise ValueError("%s holds %d steps, expected %d" % (name, int(a.shape[0]), T))
+        return a, int(a.shape[0])
+
+    def rollout(self, rot_tape, ph_tape, n_steps=None):
+        """T x [step; update] with device-resident int8 tapes (T, E, N) (either may be None = the reference's None
+        action, then ``n_steps`` gives T) and Philox collision noise; returns the outputs of the last step."""
         o = self._buffers()
-        T = int(rot_tape.shape[0])
-        check(self.lib, self.lib.ants_rollout(self._h, self._ptr(rot_tape), self._ptr(ph_tape), T,
+        rot, T = self._check_tape(rot_tape, "rot_tape", None if n_steps is None else int(n_steps))
+        ph, T = self._check_tape(ph_tape, "ph_tape", T)
+        if T is None:
+            raise ValueError("rollout without tapes needs n_steps")
+        check(self.lib, self.lib.ants_rollout(self._h, self._ptr(rot), self._ptr(ph), T,
                                               self._ptr(o["obs"]), self._ptr(o["agent_state"]), self._ptr(o["reward"])))
         return o["obs"], o["agent_state"], o["reward"]
 

@@ -158,6 +158,11 @@ int collect_timings(AntsBatch *b) {
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+struct Scratch {                   // device scratch of import / export, freed on every return path
+    void *ptr = nullptr;
+    ~Scratch() { if (ptr) cudaFree(ptr); }
+};
+
 // Launch of a step-loop kernel with programmatic stream serialisation: the kernel may be scheduled while the last
 // blocks of its predecessor still run; every such kernel starts with pdl_begin() (griddepcontrol.wait) before it
 // touches memory.  Off while profiling (events between the launches), with ANTS_NO_PDL set, and for small batches
@@ -226,7 +231,9 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
     int blocks = 0;
     {
         LaunchScope ls(b, F_PERCEIVE);
-        const int layout = b->perceive_layout;
+        // (the straight-line layouts of k_perceive decode pheromones from the record words; in diffusion mode the field
+        //  lives in the f64 planes, which only its generic channel code reads)
+        const int layout = (p.diffuse && !b->perceive_rows) ? 0 : b->perceive_layout;
         const uint32_t magic = (1u << 20) / (uint32_t)p.S2 + 1u;   // f / S2 == (f * magic) >> 20 for f < 2048
         const int threads = b->perceive_threads;
         blocks = (int)cdiv(p.EN, threads);
@@ -632,6 +639,13 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
             v = nv < 0.01 ? 0.0 : nv;
         }
         p.tab_len = (int)tab.size();
+        if (p.lazy && cfg->has_max_val && tab.back() != 0.0) {
+            // a saturated deposit must decay to 0 within the table (boxed deposits read 0 beyond it, and the 15-bit
+            // deposit step of the 8-byte records is recycled every 16384 updates)
+            ants_destroy(b);
+            return fail(ANTS_E_ARG, "evap_factor %g: a max_val deposit needs more than %d updates to fall below 0.01; "
+                        "use evap_mode DENSE or ACTIVE_TILES", cfg->evap_factor, kTabCap);
+        }
         double *d_table = nullptr;
         float *d_tobs = nullptr;
         if (dev_alloc(b, &d_table, p.tab_len) != ANTS_OK || dev_alloc(b, &d_tobs, p.tab_len) != ANTS_OK) {
@@ -776,12 +790,13 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         b->prev_synced = 1;
     // map fields: dense host array -> device scratch -> pack kernel into the cell records
     const size_t ncell = (size_t)p.E * p.W * p.H;
-    void *d_tmp = nullptr;
+    Scratch scratch;
     if (s->phero || s->food || s->walls || s->explored) {
         size_t need = ncell * 8 * ((s->phero && p.P > 1) ? p.P : 1);
-        cudaError_t me = cudaMalloc(&d_tmp, need);
+        cudaError_t me = cudaMalloc(&scratch.ptr, need);
         if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "import scratch of %zu bytes: %s", need, cudaGetErrorString(me));
     }
+    void *const d_tmp = scratch.ptr;
     if (s->phero && p.P > 0) {
         CK(cudaMemcpyAsync(d_tmp, s->phero, ncell * 8 * p.P, cudaMemcpyHostToDevice, st));
         for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs);
@@ -834,14 +849,16 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         TRY(check_launch("k_rock_grid_build"));
     }
     CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(p.absorb_count, 0, 2 * sizeof(uint32_t), st));
-    b->wall_flags_valid = 0;
+    // queued anthill absorbs refer to the old food field / disc: dropped only when one of them is replaced (the
+    // sweep of the next update takes whatever lies in the disc, Q10)
+    if (s->food || s->anthill_xyr) CK(cudaMemsetAsync(p.absorb_count, 0, 2 * sizeof(uint32_t), st));
+    if (s->x || s->y) b->wall_flags_valid = 0;
     b->owner_phase = 0;
-    b->timestep = s->timestep > 0 ? s->timestep : 1;
-    b->rw_alias = s->rw_alias ? 1 : 0;
-    b->act_bool = s->act_bool ? 1 : 0;
+    // batch-wide scalars: only when the caller provides them (0 / negative = leave as they are)
+    if (s->timestep > 0) b->timestep = s->timestep;
+    if (s->rw_alias >= 0) b->rw_alias = s->rw_alias ? 1 : 0;
+    if (s->act_bool >= 0) b->act_bool = s->act_bool ? 1 : 0;
     CK(cudaStreamSynchronize(st));   // host temporaries above must outlive the copies
-    if (d_tmp) cudaFree(d_tmp);
     return ANTS_OK;
 }
 
@@ -872,12 +889,13 @@ int ants_export_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, AntsHostSt
     }
     // map fields: unpack kernel from the cell records -> device scratch -> dense host array
     const size_t ncell = (size_t)n_envs * p.W * p.H;
-    void *d_tmp = nullptr;
+    Scratch scratch;
     if ((s->phero && p.P > 0) || s->food || s->walls || s->explored) {
         size_t need = ncell * 8 * ((s->phero && p.P > 1) ? p.P : 1);
-        cudaError_t me = cudaMalloc(&d_tmp, need);
+        cudaError_t me = cudaMalloc(&scratch.ptr, need);
         if (me != cudaSuccess) return fail(ANTS_E_ALLOC, "export scratch of %zu bytes: %s", need, cudaGetErrorString(me));
     }
+    void *const d_tmp = scratch.ptr;
     if (s->phero && p.P > 0) {
         for (int k = 0; k < p.P; ++k)
             ants::k_unpack_f64<<<148 * 8, 256, 0, st>>>(p, (double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs, env0, n_envs);
@@ -912,7 +930,6 @@ int ants_export_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, AntsHostSt
         if (s->rock_weights) CK(cudaMemcpyAsync(s->rock_weights, p.rock_w + r0, rn * 8, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaStreamSynchronize(st));
-    if (d_tmp) cudaFree(d_tmp);
     if (s->activation && p.P > 0)
         for (size_t i = 0; i < an; ++i)
             for (int k = 0; k < p.P; ++k) s->activation[i * p.P + k] = act_t[(size_t)k * an + i];

@@ -159,14 +159,28 @@ class DeviceBridge:
     def step(self, rotation, pheromone):
         n = self.ants.n_ants
 
-        def as_i8(a, what):
+        def as_rot(a):
+            # RL_api.py:191 multiplies whatever array it gets by max_rot_speed; the kernels take whole turns in int8
+            # (what the agents produce: argmax / randint minus n // 2).  Anything else is refused, not truncated.
             if a is None:
                 return None
             a = np.asarray(a)
             if a.shape != (n,):
-                raise ValueError("%s must have shape (%d,)" % (what, n))
-            return np.ascontiguousarray(a.astype(np.int8)[None])
-        obs, ast, rew, done = self.batch.step_host(as_i8(rotation, "rotation"), as_i8(pheromone, "on_off_pheromones"))
+                raise ValueError("rotation must have shape (%d,)" % n)
+            r = np.rint(a)
+            if not (np.array_equal(r, a) and np.all(np.abs(r) <= 127)):
+                raise ValueError("rotation must hold whole numbers in [-127, 127] (units of max_rot_speed)")
+            return np.ascontiguousarray(r.astype(np.int8)[None])
+
+        def as_ph(a):
+            # ants.py:89-96: 0 -> off, 1 -> first pheromone, ANY other value -> second pheromone
+            if a is None:
+                return None
+            a = np.asarray(a)
+            if a.shape != (n,):
+                raise ValueError("on_off_pheromones must have shape (%d,)" % n)
+            return np.ascontiguousarray(np.where(a == 0, 0, np.where(a == 1, 1, 2)).astype(np.int8)[None])
+        obs, ast, rew, done = self.batch.step_host(as_rot(rotation), as_ph(pheromone))
         self.version += 1
         return obs[0].astype(np.float64), ast[0].astype(np.float64), rew[0].copy(), done
 

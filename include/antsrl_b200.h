@@ -112,6 +112,7 @@ typedef struct AntsHostState {
     int32_t *anthill_xyr;                     /* Anthill.x,y,radius anthill.py:22-24 [E][3] */
     double *anthill_food;                     /* Anthill.food, anthill.py:27    [E] */
     double *rock_centers, *rock_radii, *rock_weights;   /* circle_obstacles.py:22-24 [E][R][2],[E][R],[E][R] */
+    /* batch-wide scalars.  On import: timestep <= 0, rw_alias < 0, act_bool < 0 leave the handle's value untouched */
     int64_t timestep;                         /* Environment.timestep, environment.py:27 (all envs in lockstep) */
     int32_t rw_alias;                         /* reward still aliases Ants.holding, reward_custom.py:66-67 */
     int32_t act_bool;                         /* phero_activation still has bool dtype, ants.py:83 */

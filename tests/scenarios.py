@@ -97,3 +97,26 @@ GOLDEN_SCENARIOS = [
     ("fast_backward", dict(seed=22, w=48, h=48, n_ants=40, steps=60, carry_speed_reduction=0.3,
                            max_speed=1.7, n_food=12)),
 ]
+
+
+def conservation_scenario(steps=150):
+    """A scenario in which food is conserved EXACTLY (food plane + carried + delivered == initial amount after every
+    step): 64 ants start on a 32-cell lattice of a 256x256 map, so no two of them act on the food of the same cell in
+    the same step (the reference's last-writer scatter, quirk Q1, would otherwise duplicate or lose units).  That
+    property of this seed is checked on the oracle by tests/test_oracle_golden.py::test_conservation_scenario."""
+    cfg, init, tape = make_scenario(seed=4242, w=256, h=256, n_ants=64, steps=steps, n_walls=10, n_food=60,
+                                    wall_r=(5, 12), food_r=(6, 12))
+    gx, gy = np.meshgrid(16 + 32 * np.arange(8), 16 + 32 * np.arange(8), indexing="ij")
+    x, y = gx.reshape(-1).astype(float) + 0.5, gy.reshape(-1).astype(float) + 0.5
+    walls = init["walls"].astype(bool)
+    for k in range(64):                      # lattice points inside walls slide along x to the next free cell
+        while walls[int(x[k]) % 256, int(y[k])]:
+            x[k] = (x[k] + 1.0) % 256
+    init["x"], init["y"] = x, y
+    return cfg, init, tape
+
+
+def food_total(state):
+    """food plane + carried + delivered, for one env's state dict or a batched one."""
+    return (np.asarray(state["food"], dtype=float).sum() + np.asarray(state["holding"], dtype=float).sum() +
+            np.asarray(state["anthill_food"], dtype=float).sum())

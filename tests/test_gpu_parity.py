@@ -213,17 +213,18 @@ def test_lazy_timestamp_fold():
         np.testing.assert_allclose(outs[fmt]["phero"], outs["tiles"]["phero"], rtol=1e-5, atol=0)
 
 
-def test_rollout_equals_step_update_loop():
+@pytest.mark.parametrize("record,n_rocks", [("compact8", 0), ("compact8", 4), ("compact", 0), ("f64", 4)])
+def test_rollout_equals_step_update_loop(record, n_rocks):
     """ants_rollout (device-resident action tapes, C loop) == the same steps issued one by one."""
     import torch
     from antsrl_b200 import BatchedAnts
-    scen = [make_scenario(seed=800 + e, w=48, h=48, n_ants=40, steps=12, n_walls=6) for e in range(3)]
+    scen = [make_scenario(seed=800 + e, w=48, h=48, n_ants=40, n_rocks=n_rocks, steps=12, n_walls=6) for e in range(3)]
     cfg = scen[0][0]
     rot = torch.from_numpy(np.stack([[s[2]["rot"][t] for s in scen] for t in range(12)])).cuda().contiguous()
     ph = torch.from_numpy(np.stack([[s[2]["ph"][t] for s in scen] for t in range(12)])).cuda().contiguous()
     outs = []
     for mode in ("loop", "rollout"):
-        b = BatchedAnts(cfg, 3, evap_mode="lazy", record="compact", rng_seed=3)
+        b = BatchedAnts(cfg, 3, evap_mode="lazy", record=record, rng_seed=3)
         b.import_state(stack_init(cfg, [i for _, i, _ in scen]))
         b.observe()
         if mode == "loop":
@@ -314,8 +315,15 @@ def test_random_configurations(case):
     """Seeded fuzz over the configuration space; record format and evaporation mode rotate with the case."""
     rng = np.random.RandomState(9000 + case)
     kw = _random_config(rng)
-    mode, record = [("dense", "f64"), ("tiles", "f64"), ("lazy", "f64"), ("lazy", "compact")][case % 4]
+    mode, record = [("dense", "f64"), ("tiles", "f64"), ("lazy", "f64"), ("lazy", "compact"), ("lazy", "compact8")][case % 5]
     run_parity(_variants(kw, 2), evap_mode=mode, record=record)
+
+
+@pytest.mark.parametrize("case", range(24, 36))
+def test_random_configurations_compact8(case):
+    """The bench's cell-record format (8-byte records, lazy field) over twelve more seeded random configurations."""
+    kw = _random_config(np.random.RandomState(9000 + case))
+    run_parity(_variants(kw, 2), evap_mode="lazy", record="compact8")
 
 
 def _cmp_outputs(gpu, refs, what):
@@ -372,7 +380,8 @@ def test_irregular_call_order(record, n_rocks):
     b.close()
 
 
-def test_reimport_moves_anthill_and_walls():
+@pytest.mark.parametrize("record", ["compact8", "compact"])
+def test_reimport_moves_anthill_and_walls(record):
     """A handle is reused for a new episode (main.py:66-79 generates a new map per episode): the second import moves
     the anthill (the disc bit of the cell records), the walls and the rocks; nothing of the first map may survive."""
     import torch
@@ -384,7 +393,7 @@ def test_reimport_moves_anthill_and_walls():
         scen = [make_scenario(seed=seed0 + e, w=64, h=64, n_ants=48, n_rocks=4, steps=10, n_walls=5) for e in range(2)]
         cfg = scen[0][0]
         if b is None:
-            b = BatchedAnts(cfg, 2, evap_mode="lazy", record="compact")
+            b = BatchedAnts(cfg, 2, evap_mode="lazy", record=record)
         oracles = [OracleEnv(c, i) for c, i, _ in scen]
         # a COMPLETE state (import leaves missing members untouched): the oracle's own initial state
         b.import_state(stack_init(cfg, [dict(o.s) for o in oracles]))
@@ -506,10 +515,11 @@ def test_parity_with_programmatic_dependent_launch(monkeypatch):
     """Large batches launch the step kernels with programmatic stream serialisation (each kernel may be scheduled while
     its predecessor drains and waits for it with griddepcontrol.wait); the parity batches are small, so force it."""
     monkeypatch.setenv("ANTS_FORCE_PDL", "1")
-    for name in ("rocks", "crowded", "default_small"):
-        kw = dict(GOLDEN_SCENARIOS)[name]
-        rep = run_parity(_variants(kw, 3), evap_mode="lazy", record="compact")
-        assert rep["state_checks"] == kw["steps"]
+    for record in ("compact8", "compact"):
+        for name in ("rocks", "crowded", "default_small"):
+            kw = dict(GOLDEN_SCENARIOS)[name]
+            rep = run_parity(_variants(kw, 3), evap_mode="lazy", record=record)
+            assert rep["state_checks"] == kw["steps"]
 
 
 def test_compact8_step_counter_wraps():

@@ -106,3 +106,21 @@ def test_oracle_reproduces_1000_step_episode():
     for k in ("mandibles", "reward_state", "explored"):
         assert np.array_equal(np.asarray(fin[k]).astype(np.uint8), z["final_" + k]), "final " + k
     assert int(fin["timestep"]) == int(z["final_timestep"]) == 1001
+
+
+def test_conservation_scenario():
+    """tests/scenarios.py::conservation_scenario is duplicate-free: in the oracle (pinned to the reference above) food
+    plane + carried + delivered stays exactly the initial amount after every step and update -- the precondition of
+    tests/test_gpu_bench_conditions.py::test_food_conservation_large_batch."""
+    from scenarios import conservation_scenario, food_total
+    cfg, init, tape = conservation_scenario(150)
+    env = OracleEnv(cfg, init)
+    total0 = food_total(env.s)
+    assert total0 == init["food"].sum() > 0
+    env.observation()
+    for t in range(150):
+        env.step(tape["rot"][t].astype(np.int64), tape["ph"][t].astype(np.int64))
+        assert food_total(env.s) == total0, "after step %d" % t
+        env.update(tape["noise"][t])
+        assert food_total(env.s) == total0, "after update %d" % t
+    assert env.s["holding"].sum() > 0

@@ -1,4 +1,5 @@
-"""The oracle against the LIVE reference (build container only: needs /root/reference, skipped elsewhere) on exactly
+"""The oracle against the LIVE reference (the checkout in the build container, oracle/_ref -- the same modules
+byte-compiled by oracle/build_ref.py -- on the GPU box; skipped only where neither exists) on exactly
 the configurations the GPU parity tests compare the CUDA path with the oracle on -- the odd configurations (radius 1
 and 5, 0 / 1 / 3 pheromones, tiny maps, diffusion over several tiles, rocks with a custom channel list) and the seeded
 random configurations of tests/test_gpu_parity.py, with the same per-env seeds.  Together with the committed
@@ -12,8 +13,11 @@ import pytest
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.environ.get("ANTSRL_REFERENCE", "/root/reference")),
-                                reason="needs the reference checkout (build container only)")
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import ref_harness as _rh                                    # noqa: E402
+
+pytestmark = pytest.mark.skipif(not _rh.reference_available(),
+                                reason="needs the reference (checkout or oracle/_ref built by oracle/build_ref.py)")
 
 from test_gpu_parity import ODD_CONFIGS, _random_config, _variants      # noqa: E402
 from test_oracle_golden import check_oracle_against_record              # noqa: E402

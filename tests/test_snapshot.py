@@ -120,7 +120,13 @@ def test_dropin_file_has_the_reference_structure(tmp_path):
     assert set(vars(rw_g)) - set(vars(rw_r)) <= {"_aliased"}
 
 
-@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def _reference_root():
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    from oracle import ref_harness
+    return ref_harness.REFERENCE_ROOT if ref_harness.reference_available() else None
+
+
+@pytest.mark.skipif(_reference_root() is None, reason="needs the reference (checkout or oracle/_ref built by oracle/build_ref.py)")
 def test_dropin_file_loads_under_the_reference_classes(tmp_path):
     """The direction the viewer needs: a file written by the drop-in layer, opened by the reference's own classes."""
     path = _dropin_blob(tmp_path, "states = [env.save_state()]")
@@ -128,12 +134,12 @@ def test_dropin_file_loads_under_the_reference_classes(tmp_path):
 import sys, types, pickle
 for name in ("noise", "matplotlib", "matplotlib.pyplot"):
     sys.modules[name] = types.ModuleType(name)
-sys.path.insert(0, "/root/reference")
+sys.path.insert(0, %r)
 import numpy as np
-"""
+""" % _reference_root()
     out = run_snippet("""
         import environment.ants as m
-        assert m.__file__.startswith("/root/reference")
+        assert m.__file__.startswith(%r)
         from environment.ants import Ants, AntsVisualization
         from environment.walls import Walls
         from environment.pheromone import Pheromone, PheromoneVisualization
@@ -157,7 +163,7 @@ import numpy as np
         live.update()
         assert obs.shape == (12, 7, 7, 7) and live.timestep == 2
         print("reference loaded ok")
-    """ % path, prelude=prelude)
+    """ % (_reference_root(), path), prelude=prelude)
     assert "reference loaded ok" in out
 
 
