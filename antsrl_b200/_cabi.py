@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "ants_import_state", "ants_export_state", "ants_activate_all_pheromones", "ants_observe", "ants_step",
     "ants_update", "ants_rollout", "ants_host_alloc", "ants_host_free", "ants_observe_host", "ants_step_host",
     "ants_update_host", "ants_get_stats", "ants_set_profiling", "ants_get_kernel_ms", "ants_reset_kernel_ms",
-    "ants_sample_actions", "ants_export_env_state",
+    "ants_sample_actions", "ants_export_env_state", "ants_packed_layout", "ants_step_host_packed", "ants_unpack_obs",
 ]
 
 
@@ -63,6 +63,12 @@ class AntsStats(C.Structure):
                 ("food_commits", C.c_int64), ("absorb_events", C.c_int64), ("device_bytes", C.c_int64)]
 
 
+class AntsPackedLayout(C.Structure):
+    _fields_ = [("supported", C.c_int32), ("n_samples", C.c_int32), ("n_channels", C.c_int32), ("n_visible", C.c_int32),
+                ("sample_bytes", C.c_int32), ("bytes_per_ant", C.c_int64), ("flag_channel", C.c_int32 * 8),
+                ("value_channel", C.c_int32 * 2), ("food_channel", C.c_int32), ("visible_index", C.c_uint8 * 228)]
+
+
 class AntsError(RuntimeError):
     pass
 
@@ -102,6 +108,9 @@ def load_library(path=None):
     lib.ants_observe_host.argtypes = [vp, vp, vp, vp, vp]
     lib.ants_step_host.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(i32)]
     lib.ants_update_host.argtypes = [vp, vp]
+    lib.ants_packed_layout.argtypes = [C.POINTER(AntsConfig), C.POINTER(AntsPackedLayout)]
+    lib.ants_step_host_packed.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(i32)]
+    lib.ants_unpack_obs.argtypes = [C.POINTER(AntsPackedLayout), vp, i64, vp, i32]
     lib.ants_get_stats.argtypes = [vp, C.POINTER(AntsStats)]
     lib.ants_set_profiling.argtypes = [vp, i32]
     lib.ants_get_kernel_ms.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i64)]

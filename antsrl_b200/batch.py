@@ -22,7 +22,8 @@ DEFAULT_MASK = np.array([[0, 0, 1, 1, 1, 0, 0],
 
 _REWARD_KINDS = {"all": _cabi.REWARD_ALL, "explore": _cabi.REWARD_EXPLORE, "food": _cabi.REWARD_FOOD}
 _EVAP_MODES = {"dense": _cabi.EVAP_DENSE, "tiles": _cabi.EVAP_ACTIVE_TILES, "lazy": _cabi.EVAP_LAZY}
-KERNEL_FAMILIES = ("move", "food_commit", "perceive", "collide", "rocks", "evaporate", "deposit", "absorb", "misc")
+KERNEL_FAMILIES = ("move", "food_commit", "perceive", "collide", "rocks", "evaporate", "deposit", "absorb", "misc",
+                   "env_move", "env_update", "env_update_move", "pack")
 
 
 def make_config(w, h, n_ants, n_phero=2, n_rocks=0, max_time=1000, radius=3, mask="default", fwd_delta=4,
@@ -338,6 +339,46 @@ class BatchedAnts:
         check(self.lib, self.lib.ants_step_host(self._h, hp(rotation), hp(pheromone), obs.ctypes.data_as(C.c_void_p),
                                                 ast.ctypes.data_as(C.c_void_p), rw.ctypes.data_as(C.c_void_p), C.byref(done)))
         return obs, ast, rw, bool(done.value)
+
+    def packed_layout(self):
+        """AntsPackedLayout of this handle's observation (include/antsrl_b200.h)."""
+        if not hasattr(self, "_layout"):
+            L = _cabi.AntsPackedLayout()
+            check(self.lib, self.lib.ants_packed_layout(C.byref(self._c_cfg), C.byref(L)))
+            self._layout = L
+        return self._layout
+
+    def step_host_packed(self, rotation, pheromone):
+        """RLApi.step with the observation left in its packed PCIe form on the host (a pinned uint8 array
+        (E, N, bytes_per_ant) owned by this object); :meth:`unpack_obs` expands all or part of it."""
+        L = self.packed_layout()
+        if not L.supported:
+            raise AntsError("this configuration has no packed observation form")
+        packed = self.pinned("packed", (self.E, self.N, int(L.bytes_per_ant)), np.uint8)
+        _, ast, _, rw = self._host_out()
+
+        def hp(a):
+            if a is None:
+                return C.c_void_p(0)
+            if not (isinstance(a, np.ndarray) and a.dtype == np.int8 and a.flags.c_contiguous and a.shape == (self.E, self.N)):
+                raise ValueError("actions must be contiguous int8 numpy arrays of shape (E, N)")
+            return a.ctypes.data_as(C.c_void_p)
+        done = C.c_int32(0)
+        check(self.lib, self.lib.ants_step_host_packed(self._h, hp(rotation), hp(pheromone), packed.ctypes.data_as(C.c_void_p),
+                                                       ast.ctypes.data_as(C.c_void_p), rw.ctypes.data_as(C.c_void_p), C.byref(done)))
+        return packed, ast, rw, bool(done.value)
+
+    def unpack_obs(self, packed, out=None, n_threads=0):
+        """packed (..., bytes_per_ant) uint8 -> dense float32 (..., S, S, C), bit-identical to what step_host returns."""
+        L = self.packed_layout()
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        n = packed.size // int(L.bytes_per_ant)
+        shape = packed.shape[:-1] + (self.S, self.S, self.C)
+        if out is None:
+            out = np.empty(shape, np.float32)
+        check(self.lib, self.lib.ants_unpack_obs(C.byref(L), packed.ctypes.data_as(C.c_void_p), n,
+                                                 out.ctypes.data_as(C.c_void_p), int(n_threads)))
+        return out
 
     def update_host(self, noise=None):
         if noise is None:

@@ -4,6 +4,8 @@
 // arrays and the pitched HBM layout.
 #include "../../include/antsrl_b200.h"
 #include "ants_kernels.cuh"
+#include "ants_pack.cuh"
+#include "ants_host_unpack.h"
 
 #include <math.h>
 #include <stdarg.h>
@@ -11,7 +13,11 @@
 #include <string.h>
 #include <stdlib.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 using ants::Params;
@@ -37,14 +43,115 @@ int fail(int code, const char *fmt, ...) {
             return fail(ANTS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-enum Fam { F_MOVE = 0, F_FOOD, F_PERCEIVE, F_COLLIDE, F_ROCKS, F_EVAP, F_DEPOSIT, F_ABSORB, F_MISC, F_COUNT };
+enum Fam { F_MOVE = 0, F_FOOD, F_PERCEIVE, F_COLLIDE, F_ROCKS, F_EVAP, F_DEPOSIT, F_ABSORB, F_MISC, F_ENV_MOVE, F_ENV_UPDATE,
+           F_ENV_FUSED, F_PACK, F_COUNT };
 const char *kFamName[F_COUNT] = {"move", "food_commit", "perceive", "collide", "rocks", "evaporate",
-                                 "deposit", "absorb", "misc"};
+                                 "deposit", "absorb", "misc", "env_move", "env_update", "env_update_move", "pack"};
 
 struct TimedLaunch {
     cudaEvent_t a, b;
     int fam;
 };
+
+// Worker threads of the host-buffer path (process-wide, created on first use): they expand packed observation chunks
+// into the caller's dense array while the next chunk is still crossing PCIe.
+class HostPool {
+public:
+    static HostPool &get() {
+        static HostPool pool;
+        return pool;
+    }
+    int size() const { return (int)threads_.size(); }
+    void submit(std::function<void()> fn) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            q_.push_back(std::move(fn));
+            ++pending_;
+        }
+        cv_.notify_one();
+    }
+    void wait_idle() {
+        std::unique_lock<std::mutex> lk(m_);
+        idle_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    HostPool() {
+        int n = 0;
+        if (const char *x = getenv("ANTS_HOST_THREADS")) n = atoi(x);
+        if (n <= 0) {
+            n = (int)std::thread::hardware_concurrency();
+            int ranks = 1;                                   // one process per GPU on a node shares the host cores
+            if (const char *x = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(x) > 0 ? atoi(x) : 1;
+            n = n / ranks;
+        }
+        n = n < 1 ? 1 : (n > 64 ? 64 : n);
+        for (int t = 0; t < n; ++t) threads_.emplace_back([this] { run(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    void run() {
+        for (;;) {
+            std::function<void()> fn;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                fn = std::move(q_.front());
+                q_.erase(q_.begin());
+            }
+            fn();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) idle_.notify_all();
+            }
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_, idle_;
+    std::vector<std::function<void()>> q_;
+    std::vector<std::thread> threads_;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
+// the packed form of a configuration's observation (ants_pack.cuh): which samples, which channel goes where
+void packed_layout_of(const AntsConfig *cfg, AntsPackedLayout *L) {
+    memset(L, 0, sizeof *L);
+    const int S = 2 * cfg->radius + 1, S2 = S * S, C = cfg->n_channels;
+    L->n_samples = S2; L->n_channels = C; L->sample_bytes = ants::kPackSampleBytes;
+    for (int k = 0; k < 8; ++k) L->flag_channel[k] = -1;
+    L->value_channel[0] = L->value_channel[1] = -1; L->food_channel = -1;
+    int nf = 0, nv = 0, nfood = 0;
+    bool ok = C >= 1 && C <= 8 && S2 <= 225;
+    for (int c = 0; ok && c < C; ++c) {
+        const int k = cfg->channel_kind[c];
+        if (k == ANTS_CH_PHERO) { if (nv < 2) L->value_channel[nv] = c; ++nv; }
+        else if (k == ANTS_CH_FOOD) { if (nfood < 1) L->food_channel = c; ++nfood; }
+        else { if (nf < 8) L->flag_channel[nf] = c; ++nf; }
+    }
+    ok = ok && nv <= 2 && nfood <= 1 && nf <= 8;
+    int V = 0;
+    for (int k = 0; k < S2 && k < 228; ++k)
+        if (!cfg->has_mask || cfg->mask[k]) L->visible_index[V++] = (uint8_t)k;
+    L->n_visible = V;
+    L->bytes_per_ant = (int64_t)V * ants::kPackSampleBytes;
+    L->supported = (ok && V > 0) ? 1 : 0;
+}
+void unpack_plan_of(const AntsPackedLayout *L, AntsUnpackPlan *u) {
+    memset(u, 0, sizeof *u);
+    u->V = L->n_visible; u->S2 = L->n_samples; u->C = L->n_channels;
+    for (int v = 0; v < L->n_visible; ++v) u->vis[v] = L->visible_index[v];
+    for (int k = 0; k < 8; ++k) u->flag_ch[k] = L->flag_channel[k];
+    u->val_ch[0] = L->value_channel[0]; u->val_ch[1] = L->value_channel[1]; u->food_ch = L->food_channel;
+    ants_unpack_plan_finish(u);
+}
 
 }  // namespace
 
@@ -81,6 +188,18 @@ struct AntsBatch {
     uint32_t *tile_list = nullptr;
     int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128, perceive_slow_wrap = 0;
     int perceive_rows = 0, rows_smem = 0;   // 1 = k_perceive_rows serves this configuration (default channel list, 7x7 window)
+    // block-per-environment kernels (ants_env_fused.cuh): move / update / update+move in one launch each
+    int fused = 0, env_group = 1, env_apt = 4, env_smem = 0;
+    int move_done = 0;              // ants_rollout: the move of the coming step already ran inside the last update launch
+    // packed observation transport of the host-buffer path (ants_pack.cuh)
+    AntsPackedLayout pack_layout;
+    AntsUnpackPlan *unpack_plan = nullptr;
+    ants::PackArgs pack_args;
+    uint8_t *st_packed = nullptr;   // device [EN][bytes_per_ant]
+    uint8_t *h_packed = nullptr;    // pinned staging of the same size
+    uint32_t *d_pack_fail = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    int pack_disabled = 0;          // a value without a packed form was seen (non-integer food): dense copies until the next import
 };
 
 namespace {
@@ -274,6 +393,116 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
     return check_launch("k_perceive");
 }
 
+
+// ------------------------------------------------------------------------------------------------ block-per-env path
+template <bool UPDATE, bool MOVE>
+void launch_env(AntsBatch *b, const ants::EnvArgs &a) {
+    const Params &p = b->p;
+    const unsigned grid = (unsigned)cdiv(p.E, b->env_group);
+    if (b->env_apt == 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
+    else if (b->env_apt == 2) launch_step(b, ants::k_env<UPDATE, MOVE, 2>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
+    else launch_step(b, ants::k_env<UPDATE, MOVE, 4>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
+}
+
+// host bookkeeping at the start of a step: generation folds, the step's occupancy generation, the move's arguments
+void env_args_move(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, ants::EnvArgs *a) {
+    maybe_fold_generations(b);
+    a->rot = d_rot; a->ph = d_ph;
+    a->occ_gen = next_occ_gen(b);
+    a->all_stamp = b->prev_synced ? 0 : 1;
+    a->act_on = b->act_bool ? 1.0 : 256.0;
+    a->group = b->env_group; a->cap = b->env_apt * ants::kEnvThreads;
+}
+// ... of an update: timestep, the lazy field's counters (a fold of plain values / expired deposits before they wrap)
+int env_args_update(AntsBatch *b, const double *d_noise, ants::EnvArgs *a) {
+    Params &p = b->p;
+    a->step_id = (uint32_t)b->timestep;
+    b->timestep += 1;                                               // environment.py:45
+    if (p.P > 0 && p.lazy) {
+        const bool unbox = p.rec8 ? ((b->lazy_abs & 0x3FFFu) == 0x3FFFu) : (b->lazy_abs >= ants::kBoxMask - 2u);
+        if (b->lazy_now >= p.ts_mask - 1u || unbox) {
+            LaunchScope ls(b, F_EVAP);
+            ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now, b->lazy_abs, unbox ? 1 : 0);
+            b->lazy_now = 0;
+            if (unbox && !p.rec8) b->lazy_abs = 0;
+            TRY(check_launch("k_lazy_fold"));
+        }
+        b->lazy_now += 1;
+        b->lazy_abs += 1;
+    }
+    a->noise = d_noise;
+    a->use_flag = b->wall_flags_valid;
+    a->now = b->lazy_now; a->now_abs = b->lazy_abs;
+    a->group = b->env_group; a->cap = b->env_apt * ants::kEnvThreads;
+    return ANTS_OK;
+}
+
+int finish_update(AntsBatch *b) {
+    const Params &p = b->p;
+    b->wall_flags_valid = 0;
+    b->stats.active_tiles = 0;
+    if (b->needs_sweep) {          // Anthill (order 1000) after an import: whatever the generator put into the disc (Q10)
+        LaunchScope ls(b, F_ABSORB);
+        ants::k_absorb_sweep<<<p.E, 256, 0, b->stream>>>(p);
+        b->needs_sweep = 0;
+        TRY(check_launch("absorb"));
+    }
+    b->prev_synced = 1;
+    b->stats.updates++;
+    return ANTS_OK;
+}
+
+int do_step_fused(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs, float *d_as, double *d_reward,
+                  int32_t *done) {
+    if (!b->move_done) {
+        ants::EnvArgs a = {};
+        env_args_move(b, d_rot, d_ph, &a);
+        {
+            LaunchScope ls(b, F_ENV_MOVE);
+            launch_env<false, true>(b, a);
+        }
+        TRY(check_launch("k_env<move>"));
+    }
+    b->move_done = 0;
+    b->prev_synced = 0;
+    b->wall_flags_valid = 1;
+    TRY(launch_perceive(b, d_obs, d_as, nullptr, d_reward, 1));
+    if (done) *done = (b->cfg.max_time == b->timestep) ? 1 : 0;   // RL_api.py:200 (Q15)
+    b->stats.steps++;
+    return ANTS_OK;
+}
+
+int do_update_fused(AntsBatch *b, const double *d_noise) {
+    ants::EnvArgs a = {};
+    TRY(env_args_update(b, d_noise, &a));
+    {
+        LaunchScope ls(b, F_ENV_UPDATE);
+        launch_env<true, false>(b, a);
+    }
+    TRY(check_launch("k_env<update>"));
+    return finish_update(b);
+}
+
+// update_k ; move of step_{k+1} in ONE launch (ants_rollout): legal because nothing between an update and the next
+// step's move reads what either writes (quirk Q2 only forbids fusing a step with ITS OWN update)
+int do_update_move_fused(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph) {
+    if (b->needs_sweep) return fail(ANTS_E_STATE, "internal: fused update+move with a pending anthill sweep");
+    ants::EnvArgs a = {};
+    TRY(env_args_update(b, nullptr, &a));
+    b->prev_synced = 1;
+    env_args_move(b, d_rot, d_ph, &a);
+    {
+        LaunchScope ls(b, F_ENV_FUSED);
+        launch_env<true, true>(b, a);
+    }
+    TRY(check_launch("k_env<update, move>"));
+    b->wall_flags_valid = 0;
+    b->stats.active_tiles = 0;
+    b->stats.updates++;
+    b->move_done = 1;
+    return ANTS_OK;
+}
+
 int do_observe(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward) {
     if (!d_obs || !d_as) return fail(ANTS_E_ARG, "ants_observe: obs and agent_state buffers are required");
     const Params &p = b->p;
@@ -295,6 +524,7 @@ int do_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs,
     const Params &p = b->p;
     if (d_ph && p.P != 2)
         return fail(ANTS_E_ARG, "pheromone actions need exactly two pheromones (ants.py:92-96), have %d", p.P);
+    if (b->fused) return do_step_fused(b, d_rot, d_ph, d_obs, d_as, d_reward, done);
     maybe_fold_generations(b);
     uint32_t phase = next_owner_phase(b);
     uint32_t occ = next_occ_gen(b);
@@ -320,6 +550,7 @@ int do_step(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, float *d_obs,
 }
 
 int do_update(AntsBatch *b, const double *d_noise) {
+    if (b->fused) return do_update_fused(b, d_noise);
     Params &p = b->p;
     int blocks = (int)cdiv(p.EN, 256);
     uint32_t step_id = (uint32_t)b->timestep;
@@ -420,6 +651,73 @@ int ensure_staging(AntsBatch *b) {
     TRY(dev_alloc(b, &b->st_reward, p.EN, false));
     TRY(dev_alloc(b, &b->st_noise, p.EN, false));
     return ANTS_OK;
+}
+
+int ensure_packed(AntsBatch *b) {
+    if (b->st_packed) return ANTS_OK;
+    const int64_t bytes = b->p.EN * b->pack_layout.bytes_per_ant;
+    TRY(dev_alloc(b, &b->st_packed, bytes + 64, false));
+    TRY(dev_alloc(b, &b->d_pack_fail, 1));
+    if (cudaHostAlloc((void **)&b->h_packed, (size_t)bytes + 64, cudaHostAllocDefault) != cudaSuccess)
+        return fail(ANTS_E_ALLOC, "cudaHostAlloc of %lld bytes (packed observation staging) failed", (long long)bytes);
+    b->chunk_ev.resize(16);
+    for (auto &e : b->chunk_ev)
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
+            return fail(ANTS_E_CUDA, "cudaEventCreate failed");
+    return ANTS_OK;
+}
+
+// The observation of the last step (dense in st_obs) -> packed on the device -> host, in chunks; with h_obs the chunks
+// are expanded into the dense host array by the worker threads while the following ones are still on the bus.
+// Returns 1 if some value of this step has no packed form (the caller copies dense).
+int packed_transfer(AntsBatch *b, uint8_t *h_dst, float *h_obs, float *h_agent_state, double *h_reward) {
+    const Params &p = b->p;
+    const AntsPackedLayout &L = b->pack_layout;
+    const int64_t EN = p.EN, bpa = L.bytes_per_ant, dense = (int64_t)p.S2 * p.C;
+    CK(cudaMemsetAsync(b->d_pack_fail, 0, sizeof(uint32_t), b->stream));
+    int n_chunks = (int)(EN / 16384);
+    n_chunks = n_chunks < 1 ? 1 : (n_chunks > (int)b->chunk_ev.size() ? (int)b->chunk_ev.size() : n_chunks);
+    const int64_t per = (cdiv(EN, n_chunks) + 63) / 64 * 64;
+    int used = 0;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int64_t a0 = c * per, n = EN - a0 < per ? EN - a0 : per;
+        if (n <= 0) break;
+        {
+            LaunchScope ls(b, F_PACK);
+            ants::k_pack_obs<<<(unsigned)cdiv(n * L.n_visible, 256), 256, 0, b->stream>>>(b->pack_args, b->st_obs, b->st_packed, a0, n,
+                                                                                       b->d_pack_fail);
+        }
+        TRY(check_launch("k_pack_obs"));
+        CK(cudaMemcpyAsync(h_dst + a0 * bpa, b->st_packed + a0 * bpa, (size_t)(n * bpa), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaEventRecord(b->chunk_ev[c], b->stream));
+        used = c + 1;
+    }
+    CK(cudaMemcpyAsync(h_agent_state, b->st_as, (size_t)EN * 8, cudaMemcpyDeviceToHost, b->stream));
+    if (h_reward) CK(cudaMemcpyAsync(h_reward, b->st_reward, (size_t)EN * 8, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(b->h_counts + 8, b->d_pack_fail, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
+    if (h_obs) {
+        HostPool &pool = HostPool::get();
+        const AntsUnpackPlan *plan = b->unpack_plan;
+        const int T = pool.size();
+        for (int c = 0; c < used; ++c) {
+            const int64_t a0 = c * per, n = EN - a0 < per ? EN - a0 : per;
+            CK(cudaEventSynchronize(b->chunk_ev[c]));
+            const int64_t piece = cdiv(n, T);
+            for (int64_t s0 = 0; s0 < n; s0 += piece) {
+                const int64_t cnt = n - s0 < piece ? n - s0 : piece, first = a0 + s0;
+                pool.submit([=] { ants_unpack_range(plan, h_dst + first * bpa, cnt, h_obs + first * dense); });
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(b->stream));
+    if (h_obs) HostPool::get().wait_idle();
+    return b->h_counts[8] ? 1 : ANTS_OK;
+}
+
+bool packed_path_wanted(const AntsBatch *b) {
+    if (!b->pack_layout.supported || b->pack_disabled || getenv("ANTS_E2E_DENSE")) return false;
+    if (getenv("ANTS_E2E_PACKED")) return true;                        // (tests: also for small batches)
+    return b->p.EN * b->p.S2 * b->p.C * 4 >= (int64_t)(4 << 20);       // small batches: one dense copy is cheaper
 }
 
 }  // namespace
@@ -540,6 +838,18 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     p.log2_keep = p.filt_center > 0.0 ? log2(p.filt_center) : -1e300;
     p.rng_seed = cfg->rng_seed; p.env_id_base = cfg->env_id_base;
 
+    {   // block-per-environment kernels: lazy field (no pass between the rocks and the deposit), <= 1024 ants per env,
+        // (env-in-block, cell) keys in 32 bits
+        const int cap = p.N <= 256 ? 256 : (p.N <= 512 ? 512 : 1024);
+        int g = cap / (p.N > 0 ? p.N : 1);
+        g = g < 1 ? 1 : (g > ants::kEnvMaxGroup ? ants::kEnvMaxGroup : g);
+        while (g > 1 && (int64_t)g * p.plane >= 0xFFFFFFF0ll) --g;
+        b->fused = ((p.lazy || p.P == 0) && cfg->diffuse_factor == 0.0 && p.N <= 1024 && p.plane < 0xFFFFFFF0ll &&
+                    !getenv("ANTS_NO_FUSED")) ? 1 : 0;
+        b->env_group = g;
+        b->env_apt = cap / ants::kEnvThreads;
+        b->env_smem = cap * 32 + g * p.R * 4;
+    }
     int rc = ANTS_OK;
     auto A = [&](int r) { if (rc == ANTS_OK) rc = r; };
     const int64_t EN = p.EN, cells = (int64_t)p.E * p.plane;
@@ -556,7 +866,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         A(dev_alloc(b, &p.phero_pl, 2 * cells * p.P));
         p.phero_alt = p.phero_pl ? p.phero_pl + cells * p.P : nullptr;
     }
-    A(dev_alloc(b, &p.owner, cells));
+    if (!b->fused) A(dev_alloc(b, &p.owner, cells));       // (the block-per-env kernels find owners in shared memory)
     if (cfg->evap_mode == ANTS_EVAP_ACTIVE_TILES && cfg->diffuse_factor == 0.0)
     {
         A(dev_alloc(b, &p.tile_active, (int64_t)p.E * p.tiles_x * p.tiles_y));
@@ -570,7 +880,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     A(dev_alloc(b, &p.rock_touch, (int64_t)p.E * p.R));
     A(dev_alloc(b, &p.food_delta, EN, false));
     A(dev_alloc(b, &p.commit_list, EN, false)); A(dev_alloc(b, &p.commit_count, 2));
-    A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, 2));
+    A(dev_alloc(b, &p.absorb_list, EN * 2, false)); A(dev_alloc(b, &p.absorb_count, b->fused ? (p.E > 2 ? p.E : 2) : 2));
     A(dev_alloc(b, &p.wall_hit, EN));
     A(dev_alloc(b, &p.tile_counter, 1));
     A(dev_alloc(b, &p.plain_flag, 1));
@@ -719,6 +1029,18 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
                         cudaGetErrorString(e));
         }
     }
+    {   // packed observation transport
+        packed_layout_of(cfg, &b->pack_layout);
+        b->unpack_plan = new AntsUnpackPlan();
+        unpack_plan_of(&b->pack_layout, b->unpack_plan);
+        ants::PackArgs &pa = b->pack_args;
+        memset(&pa, 0, sizeof pa);
+        pa.V = b->pack_layout.n_visible; pa.S2 = p.S2; pa.C = p.C;
+        for (int k = 0; k < 8; ++k) pa.flag_ch[k] = b->pack_layout.flag_channel[k];
+        pa.val_ch[0] = b->pack_layout.value_channel[0]; pa.val_ch[1] = b->pack_layout.value_channel[1];
+        pa.food_ch = b->pack_layout.food_channel;
+        for (int v = 0; v < pa.V; ++v) pa.vis[v] = b->pack_layout.visible_index[v];
+    }
     if (cudaHostAlloc((void **)&b->h_counts, 64, cudaHostAllocDefault) != cudaSuccess) {
         ants_destroy(b);
         return fail(ANTS_E_ALLOC, "cudaHostAlloc failed");
@@ -741,6 +1063,9 @@ int ants_destroy(AntsBatch *b) {
     for (auto e : b->event_pool) cudaEventDestroy(e);
     for (void *d : b->allocs) cudaFree(d);
     if (b->h_counts) cudaFreeHost(b->h_counts);
+    if (b->h_packed) cudaFreeHost(b->h_packed);
+    for (auto e : b->chunk_ev) cudaEventDestroy(e);
+    delete b->unpack_plan;
     if (b->own_stream) cudaStreamDestroy(b->own_stream);
     delete b;
     return ANTS_OK;
@@ -848,10 +1173,13 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
         ants::k_rock_grid_build<<<p.E, 128, 0, st>>>(p);
         TRY(check_launch("k_rock_grid_build"));
     }
-    CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
+    if (p.owner) CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
+    b->move_done = 0;
+    if (s->food) b->pack_disabled = 0;
     // queued anthill absorbs refer to the old food field / disc: dropped only when one of them is replaced (the
     // sweep of the next update takes whatever lies in the disc, Q10)
-    if (s->food || s->anthill_xyr) CK(cudaMemsetAsync(p.absorb_count, 0, 2 * sizeof(uint32_t), st));
+    if (s->food || s->anthill_xyr)
+        CK(cudaMemsetAsync(p.absorb_count, 0, (size_t)(b->fused && p.E > 2 ? p.E : 2) * sizeof(uint32_t), st));
     if (s->x || s->y) b->wall_flags_valid = 0;
     b->owner_phase = 0;
     // batch-wide scalars: only when the caller provides them (0 / negative = leave as they are)
@@ -989,11 +1317,18 @@ int ants_rollout(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape
                  float *d_agent_state, double *d_reward) {
     if (!b) return fail(ANTS_E_ARG, "null handle");
     CK(cudaSetDevice(b->cfg.device));
+    const int64_t EN = b->p.EN;
     for (int t = 0; t < n_steps; ++t) {
-        const int8_t *r = d_rot_tape ? d_rot_tape + (int64_t)t * b->p.EN : nullptr;
-        const int8_t *h = d_ph_tape ? d_ph_tape + (int64_t)t * b->p.EN : nullptr;
+        const int8_t *r = d_rot_tape ? d_rot_tape + (int64_t)t * EN : nullptr;
+        const int8_t *h = d_ph_tape ? d_ph_tape + (int64_t)t * EN : nullptr;
         TRY(do_step(b, r, h, d_obs, d_agent_state, d_reward, nullptr));
-        TRY(do_update(b, nullptr));
+        if (b->fused && t + 1 < n_steps && !b->needs_sweep) {
+            // update_t and the move of step_{t+1} in one launch; do_step(t + 1) then only perceives
+            if (h && b->p.P != 2) return fail(ANTS_E_ARG, "pheromone actions need exactly two pheromones");
+            TRY(do_update_move_fused(b, d_rot_tape ? r + EN : nullptr, d_ph_tape ? h + EN : nullptr));
+        } else {
+            TRY(do_update(b, nullptr));
+        }
     }
     return ANTS_OK;
 }
@@ -1049,10 +1384,67 @@ int ants_step_host(AntsBatch *b, const int8_t *h_rot, const int8_t *h_ph, float 
     if (h_rot) CK(cudaMemcpyAsync(b->st_rot, h_rot, (size_t)p.EN, cudaMemcpyHostToDevice, b->stream));
     if (h_ph) CK(cudaMemcpyAsync(b->st_ph, h_ph, (size_t)p.EN, cudaMemcpyHostToDevice, b->stream));
     TRY(do_step(b, h_rot ? b->st_rot : nullptr, h_ph ? b->st_ph : nullptr, b->st_obs, b->st_as, b->st_reward, done));
+    if (packed_path_wanted(b)) {
+        // the observation crosses PCIe packed (visible samples, 12 bytes each) and is expanded by the host threads
+        TRY(ensure_packed(b));
+        const int rc = packed_transfer(b, b->h_packed, h_obs, h_agent_state, h_reward);
+        if (rc == ANTS_OK) return ANTS_OK;
+        if (rc != 1) return rc;
+        b->pack_disabled = 1;              // e.g. a non-integer amount of food: this and the following steps go dense
+    }
     CK(cudaMemcpyAsync(h_obs, b->st_obs, (size_t)p.EN * p.S2 * p.C * 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(h_agent_state, b->st_as, (size_t)p.EN * 8, cudaMemcpyDeviceToHost, b->stream));
     if (h_reward) CK(cudaMemcpyAsync(h_reward, b->st_reward, (size_t)p.EN * 8, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
+    return ANTS_OK;
+}
+
+int ants_packed_layout(const AntsConfig *cfg, AntsPackedLayout *out) {
+    if (!cfg || !out) return fail(ANTS_E_ARG, "null argument");
+    if (cfg->radius < 0 || cfg->radius > ANTS_MAX_RADIUS || cfg->n_channels < 1 || cfg->n_channels > ANTS_MAX_CHANNELS)
+        return fail(ANTS_E_ARG, "radius / n_channels out of range");
+    packed_layout_of(cfg, out);
+    return ANTS_OK;
+}
+
+int ants_step_host_packed(AntsBatch *b, const int8_t *h_rot, const int8_t *h_ph, void *h_packed, float *h_agent_state,
+                          double *h_reward, int32_t *done) {
+    if (!b || !h_packed || !h_agent_state) return fail(ANTS_E_ARG, "null argument");
+    if (!b->pack_layout.supported) return fail(ANTS_E_ARG, "this configuration has no packed observation form");
+    CK(cudaSetDevice(b->cfg.device));
+    TRY(ensure_staging(b));
+    TRY(ensure_packed(b));
+    const Params &p = b->p;
+    if (h_rot) CK(cudaMemcpyAsync(b->st_rot, h_rot, (size_t)p.EN, cudaMemcpyHostToDevice, b->stream));
+    if (h_ph) CK(cudaMemcpyAsync(b->st_ph, h_ph, (size_t)p.EN, cudaMemcpyHostToDevice, b->stream));
+    TRY(do_step(b, h_rot ? b->st_rot : nullptr, h_ph ? b->st_ph : nullptr, b->st_obs, b->st_as, b->st_reward, done));
+    const int rc = packed_transfer(b, (uint8_t *)h_packed, nullptr, h_agent_state, h_reward);
+    if (rc == 1)
+        return fail(ANTS_E_STATE, "an observation value of this step has no packed form (non-integer food): the step was "
+                                  "taken; read it with ants_observe-style dense copies (ants_step_host)");
+    return rc;
+}
+
+int ants_unpack_obs(const AntsPackedLayout *layout, const void *h_packed, int64_t n_ants, float *h_obs, int32_t n_threads) {
+    if (!layout || !h_packed || !h_obs || n_ants < 0) return fail(ANTS_E_ARG, "null argument");
+    if (!layout->supported) return fail(ANTS_E_ARG, "unsupported packed layout");
+    AntsUnpackPlan *plan = new AntsUnpackPlan();
+    unpack_plan_of(layout, plan);
+    const int64_t bpa = layout->bytes_per_ant, dense = (int64_t)layout->n_samples * layout->n_channels;
+    const uint8_t *src = (const uint8_t *)h_packed;
+    if (n_threads == 1 || n_ants < 1024) {
+        ants_unpack_range(plan, src, n_ants, h_obs);
+    } else {
+        HostPool &pool = HostPool::get();
+        int T = n_threads <= 0 ? pool.size() : (n_threads < pool.size() ? n_threads : pool.size());
+        const int64_t piece = cdiv(n_ants, (int64_t)T * 4);
+        for (int64_t s0 = 0; s0 < n_ants; s0 += piece) {
+            const int64_t cnt = n_ants - s0 < piece ? n_ants - s0 : piece;
+            pool.submit([=] { ants_unpack_range(plan, src + s0 * bpa, cnt, h_obs + s0 * dense); });
+        }
+        pool.wait_idle();
+    }
+    delete plan;
     return ANTS_OK;
 }
 
@@ -1076,8 +1468,8 @@ int ants_get_stats(AntsBatch *b, AntsStats *out) {
     CK(cudaMemcpyAsync(b->h_counts + 1, b->p.absorb_count + b->absorb_par, 4, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b->h_counts + 2, b->p.tile_counter, 8, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    b->stats.food_commits = b->h_counts[0];
-    b->stats.absorb_events = b->h_counts[1];
+    b->stats.food_commits = b->fused ? 0 : b->h_counts[0];     // (counted by the flat kernels only)
+    b->stats.absorb_events = b->fused ? 0 : b->h_counts[1];
     if (b->p.tile_active) {
         unsigned long long t;
         memcpy(&t, b->h_counts + 2, 8);

@@ -396,39 +396,50 @@ __device__ __forceinline__ unsigned long long rock_candidates(const Params &p, i
 __device__ __forceinline__ double rock_reach(const Params &p, double rad) {
     return rad + ((double)p.radius * p.delta * 1.4142135623730951 + 1.75);
 }
-// k-th sample offset of the box [-L, L] walked in grid steps, the far edge included: -L, -L + 16, ..., L
-__device__ __forceinline__ bool rock_box_offset(double L, int k, double *o) {
-    const double step = (double)(1 << kGridShift);
-    const double v = -L + (double)k * step;
-    if (k > 0 && v - step >= L) return false;          // the previous sample already was the far edge
-    *o = v > L ? L : v;
-    return true;
+// Grid cells (16 map cells wide; the last one of an axis is narrower when the map size is not a multiple of 16) that
+// the interval [lo, hi] of unwrapped coordinates overlaps on a torus of n cells.  grid_first / grid_next walk them:
+//     for (int x = grid_first(lo); x <= grid_last(hi); x = grid_next(x, n)) g = grid_of(x, n);
+// An interval as long as the map visits every grid cell (some twice: marking is idempotent).
+__device__ __forceinline__ int grid_first(double lo) { return (int)floor(lo); }
+__device__ __forceinline__ int grid_last(double hi) { return (int)floor(hi); }
+__device__ __forceinline__ int grid_of(int x, int n) { return imod(x, n) >> kGridShift; }
+__device__ __forceinline__ int grid_next(int x, int n) {
+    const int w = imod(x, n);
+    const int to_cell_end = (1 << kGridShift) - (w & ((1 << kGridShift) - 1)), to_seam = n - w;
+    return x + (to_cell_end < to_seam ? to_cell_end : to_seam);
 }
-__device__ __forceinline__ void rock_grid_touch(const Params &p, int e, int r, double x, double y, bool set) {
-    const int gx = cell_of(pymod_near(x, (double)p.W), p.W) >> kGridShift;
-    const int gy = cell_of(pymod_near(y, (double)p.H), p.H) >> kGridShift;
+__device__ __forceinline__ int grid_count(double lo, double hi, int n) {
+    int c = 0;
+    for (int x = grid_first(lo); x <= grid_last(hi); x = grid_next(x, n)) ++c;
+    return c;
+}
+__device__ __forceinline__ void rock_grid_touch(const Params &p, int e, int r, int gx, int gy, bool set) {
     unsigned long long *g = p.rock_grid + ((int64_t)e * p.grid_w + gx) * p.grid_h + gy;
     const unsigned long long bit = 1ull << r;
     if (set) atomicOr(g, bit); else atomicAnd(g, ~bit);
 }
-// every grid cell the box [c - L, c + L] overlaps gets (or loses) the rock's bit; one thread
+// every grid cell the box [c - L, c + L] overlaps (on the torus: ants and their perception windows wrap, RL_api.py:118-119,
+// ants.py:69-71) gets (or loses) the rock's bit; one thread
 __device__ __forceinline__ void rock_grid_mark(const Params &p, int e, int r, double cx, double cy, double rad, bool set = true) {
     const double L = rock_reach(p, rad);
-    double ox, oy;
-    for (int i = 0; rock_box_offset(L, i, &ox); ++i)
-        for (int j = 0; rock_box_offset(L, j, &oy); ++j) rock_grid_touch(p, e, r, cx + ox, cy + oy, set);
+    for (int x = grid_first(cx - L); x <= grid_last(cx + L); x = grid_next(x, p.W))
+        for (int y = grid_first(cy - L); y <= grid_last(cy + L); y = grid_next(y, p.H))
+            rock_grid_touch(p, e, r, grid_of(x, p.W), grid_of(y, p.H), set);
 }
-// the same by a whole warp: lane = (i, j) of the box samples (boxes of up to 5 x 5 samples, else lane 0 alone)
+// the same by a whole warp: lane = (i, j) of the box's grid cells (up to 32 of them, else lane 0 alone)
 __device__ __forceinline__ void rock_grid_mark_warp(const Params &p, int e, int r, double cx, double cy, double rad, bool set, int lane) {
     const double L = rock_reach(p, rad);
-    double o;
-    if (rock_box_offset(L, 5, &o)) {                   // more than 5 samples per axis: serial fallback
+    const int nx = grid_count(cx - L, cx + L, p.W), ny = grid_count(cy - L, cy + L, p.H);
+    if (nx * ny > 32) {
         if (lane == 0) rock_grid_mark(p, e, r, cx, cy, rad, set);
         return;
     }
-    if (lane < 25) {
-        double ox, oy;
-        if (rock_box_offset(L, lane / 5, &ox) && rock_box_offset(L, lane % 5, &oy)) rock_grid_touch(p, e, r, cx + ox, cy + oy, set);
+    if (lane < nx * ny) {
+        const int i = lane / ny, j = lane - i * ny;
+        int x = grid_first(cx - L), y = grid_first(cy - L);
+        for (int k = 0; k < i; ++k) x = grid_next(x, p.W);
+        for (int k = 0; k < j; ++k) y = grid_next(y, p.H);
+        rock_grid_touch(p, e, r, grid_of(x, p.W), grid_of(y, p.H), set);
     }
 }
 
@@ -1459,3 +1470,4 @@ __global__ void k_tiles_from_phero(Params p) {
 }  // namespace ants
 
 #include "ants_perceive_rows.cuh"
+#include "ants_env_fused.cuh"

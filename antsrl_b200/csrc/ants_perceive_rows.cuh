@@ -186,7 +186,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const int warp = tid >> 5, lane = tid & 31;
     const int W = p.W, H = p.H;
     const int nby64 = p.nby << 6;
-    const uint32_t tab_len = (uint32_t)p.tab_len;
+    // ages that still show a value: the table's last entry is the 0 the reference's < 0.01 cut produced
+    const uint32_t tab_len = p.tab_len > 0 ? (uint32_t)p.tab_len - 1u : 0u;
     const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
     const bool eager = (REC == 0) && !p.lazy;                       // f64 fields hold plain current values (no decay on read)
     const bool eager_planes = eager && p.diffuse != 0;              // ... in the diffusion planes (sign bit = wall)

@@ -8,10 +8,15 @@ Philox collision noise).  value = envs x ants x steps / time, whole job over all
 shard is fixed; N = 8 of the default workload is BASELINE.json configs[3]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg2] [--envs E] [--evap lazy|tiles|dense]
-    python bench.py --impl reference ...      # the reference algorithm (oracle port) on the host cores
+    python bench.py --impl reference ...      # the UNMODIFIED reference (oracle/_ref) on the host cores
 
-Extra JSON keys: roofline (dominant kernel vs measured HBM peak), cpu_baseline (oracle on host cores, bounded
-sample), e2e (host buffers through the C ABI, copies inside the timed region), kernels (per-family ms), clocks.
+The timed region is ONE C call (ants_rollout over a device-resident action tape): per step one launch of the perception
+kernel and one of the block-per-environment kernel (update_k ; move of step_{k+1}); no Python between the steps.
+
+Extra JSON keys: roofline (dominant kernel vs measured HBM peak; dram_frac = ncu-measured DRAM bytes of the same launch),
+late (the same K steps re-timed around step 900 of the episode, ants dispersed), cpu_baseline (the UNMODIFIED reference,
+oracle/_ref, on the host cores; bounded sample), e2e (host buffers through the C ABI, copies inside the timed region),
+e2e_packed (the observation left in its packed PCIe form), kernels (per-family ms), clocks.
 """
 import argparse
 import json
@@ -137,41 +142,62 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU baseline
+def _reference_available():
+    try:
+        from oracle import ref_harness
+        return ref_harness.reference_available()
+    except Exception:
+        return False
+
+
 def _cpu_worker(args):
-    """One independent env per process: the oracle (numpy port of the reference loop, scipy convolve2d included)."""
+    """One independent env per process.  kind "reference": the UNMODIFIED reference (oracle/_ref = its modules byte-compiled
+    by oracle/build_ref.py, or the checkout) driven through RLApi.step / Environment.update exactly as main.py:88-138
+    drives it, its own global-RNG collision noise included.  kind "port": the oracle (numpy restatement)."""
     os.environ["OMP_NUM_THREADS"] = "1"
     os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    wl, env_id, warm, steps = args
-    from oracle.antsrl_oracle import OracleEnv, philox_uniform
+    wl, env_id, warm, steps, kind = args
     g = make_generator(wl, warm + steps + 1)
     st = g.generate_states(1, env_id)[0]
-    env = OracleEnv(g.cfg, st)
-    env.activate_all_pheromones(np.ones((wl["n_ants"], wl["n_phero"])) * 10.0)
+    N, P = wl["n_ants"], wl["n_phero"]
     rs = np.random.RandomState(12345 + env_id)
-    env.observation()
+    if kind == "reference":
+        from oracle import ref_harness
+        ref = ref_harness.load_reference()
+        ref_harness.set_diffuse(ref, g.cfg["diffuse_factor"], g.cfg["evap_factor"])
+        env, api, objs = ref_harness.build_env(ref, g.cfg, st)
+        objs["ants"].activate_all_pheromones(np.ones((N, P)) * 10.0)        # agent.initialize, collect_agent.py:100-102
+        np.random.seed(777 + env_id)
+        api.observation()                                                    # main.py:88
+        step = lambda rot, ph, t: (api.step(rot, ph), ref_harness.run_update(ref, env, None))
+    else:
+        from oracle.antsrl_oracle import OracleEnv, philox_uniform
+        env = OracleEnv(g.cfg, st)
+        env.activate_all_pheromones(np.ones((N, P)) * 10.0)
+        env.observation()
+        step = lambda rot, ph, t: (env.step(rot, ph), env.update(philox_uniform(0, env_id, t + 1, N)))
     t0 = None
     for t in range(warm + steps):
         if t == warm:
             t0 = time.perf_counter()
-        rot = rs.randint(0, 3, wl["n_ants"]) - 1
-        ph = rs.randint(0, 3, wl["n_ants"])
-        env.step(rot, ph)
-        env.update(philox_uniform(0, env_id, t + 1, wl["n_ants"]))
+        step(rs.randint(0, 3, N) - 1, rs.randint(0, 3, N), t)
     return time.perf_counter() - t0
 
 
 def run_cpu_baseline(wl, warm, steps, procs=None):
     procs = procs or (os.cpu_count() or 1)
+    kind = "reference" if _reference_available() else "port"
     t_wall = time.perf_counter()
     with mp.get_context("fork").Pool(procs) as pool:
-        times = pool.map(_cpu_worker, [(wl, e, warm, steps) for e in range(procs)])
+        times = pool.map(_cpu_worker, [(wl, e, warm, steps, kind) for e in range(procs)])
     t_wall = time.perf_counter() - t_wall
     worst = max(times)
     value = procs * wl["n_ants"] * steps / worst
-    return {"value": value, "unit": "ant-steps/s", "cores": procs, "kind": "port",
+    what = ("the unmodified reference (oracle/_ref: its own RLApi.step + Environment.update, scipy convolve2d, global-RNG "
+            "collision noise)" if kind == "reference" else "oracle = numpy port of the reference loop incl. scipy convolve2d")
+    return {"value": value, "unit": "ant-steps/s", "cores": procs, "kind": kind,
             "sample": "%d independent envs (one per process, %d processes) x %d timed steps of step()+update() after "
-                      "%d warm-up, %dx%d map, %d ants/env, oracle = numpy port of the reference loop incl. scipy "
-                      "convolve2d" % (procs, procs, steps, warm, wl["w"], wl["h"], wl["n_ants"]),
+                      "%d warm-up, %dx%d map, %d ants/env, %s" % (procs, procs, steps, warm, wl["w"], wl["h"], wl["n_ants"], what),
             "ms_per_env_step": 1000.0 * float(np.mean(times)) / steps, "wall_s": t_wall}
 
 
@@ -197,20 +223,31 @@ def algorithmic_bytes(fam, wl, E, C, stats):
         return EN * (16 + 4 + 8 * P + 16)
     if fam == "rocks":
         return EN * (16 + 16 + 24) + E * wl["n_rocks"] * 48
+    # the block-per-environment kernels do the work of the flat families they replace: the same algorithmic bytes
+    if fam == "env_move":
+        return algorithmic_bytes("move", wl, E, C, stats)
+    if fam == "env_update":
+        return sum(algorithmic_bytes(f, wl, E, C, stats) for f in ("collide", "deposit")) + \
+            (algorithmic_bytes("rocks", wl, E, C, stats) if wl["n_rocks"] else 0)
+    if fam == "env_update_move":
+        return algorithmic_bytes("env_update", wl, E, C, stats) + algorithmic_bytes("move", wl, E, C, stats)
     return 0
 
 
 def ncu_traffic(fam, n_ants):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/latest_traffic.json,
-    written by scripts/profile_summary.py: dram__bytes_read.sum + dram__bytes_write.sum per ant x ants)."""
+    written by scripts/profile_summary.py: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch).  Used as it
+    is when the capture was taken at this batch size, else scaled per ant (and said so)."""
     path = os.path.join(ROOT, "profiles", "latest_traffic.json")
     try:
         d = json.load(open(path))
         if d.get("kernel", "").replace("k_", "") == fam:
-            return d["dram_bytes_per_ant"] * n_ants
+            exact = int(d.get("ants", 0)) == int(n_ants)
+            return d["dram_bytes_per_ant"] * n_ants, ("ncu capture of this launch size (%s)" % d.get("tag", "") if exact else
+                                                      "ncu capture at %d ants, scaled per ant" % int(d.get("ants", 0)))
     except Exception:
         pass
-    return None
+    return None, None
 
 
 def load_peaks():
@@ -238,7 +275,8 @@ def run_ours(args):
     E = args.envs or wl["envs_per_gpu"]
     N = wl["n_ants"]
     K, W_ = args.steps, args.warmup
-    total_steps = W_ + 2 * K + args.e2e_steps + 8
+    late_start = args.late_start
+    total_steps = max(W_ + 3 * K, late_start + K) + 2 * args.e2e_steps + 16
 
     t_setup = time.perf_counter()
     gen = make_generator(wl, total_steps + 10)
@@ -253,51 +291,56 @@ def run_ours(args):
     batch.activate_all_pheromones(np.ones((E, N, wl["n_phero"])) * 10.0)      # agent.initialize, collect_agent.py:100
     C = len(gen.cfg["channels"])
     rs = np.random.RandomState(12345 + rank)
-    n_tape = min(64, total_steps)
+    n_tape = max(K, 32)                                                       # the pre-recorded action sequence
     rot_tape = torch.from_numpy((rs.randint(0, 3, size=(n_tape, E, N)) - 1).astype(np.int8)).cuda()
     ph_tape = torch.from_numpy(rs.randint(0, 3, size=(n_tape, E, N)).astype(np.int8)).cuda()
     batch.observe()                                                           # main.py:88
     t_setup = time.perf_counter() - t_setup
+    episode_step = [0]
 
-    step_no = [0]
-
-    def one_step():
-        t = step_no[0] % n_tape
-        batch.step(rot_tape[t], ph_tape[t])
-        batch.update(None)
-        step_no[0] += 1
+    def run_steps(n):
+        """n x [step(actions_t); update()] as C calls over the device-resident tape (ants_rollout: no Python, no host
+        round trip between the steps)."""
+        done = 0
+        while done < n:
+            m = min(n_tape, n - done)
+            batch.rollout(rot_tape[:m], ph_tape[:m])
+            done += m
+        episode_step[0] += n
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W_):
-        one_step()
-    barrier()
-    launches0 = batch.stats()["kernel_launches"]
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
+    def timed(n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
-        for _ in range(K):
-            one_step()
+        run_steps(n)
         ev1.record()
         barrier()
-    ms = ev0.elapsed_time(ev1)
+        t = ev0.elapsed_time(ev1)
+        if world > 1:
+            tmax = torch.tensor([t], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            t = float(tmax.item())
+        return t
+
+    run_steps(W_)
+    barrier()
+    launches0 = batch.stats()["kernel_launches"]
+    first_timed_step = episode_step[0]
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(K)
     launches = batch.stats()["kernel_launches"] - launches0
-    if world > 1:
-        tmax = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        ms = float(tmax.item())
     value = world * E * N * K / (ms / 1000.0)
 
-    # ---- per-kernel timing (same K steps, CUDA events around every launch on the launching stream)
+    # ---- per-kernel timing (the following K steps, CUDA events around every launch on the launching stream)
     batch.set_profiling(True)
     batch.reset_kernel_ms()
     barrier()
-    for _ in range(K):
-        one_step()
+    run_steps(K)
     barrier()
     kms = batch.kernel_ms()
     st = batch.stats()
@@ -314,55 +357,90 @@ def run_ours(args):
     if dom == "rocks":
         dom_ms_per_launch = kernels[dom]["ms_per_step"]
     achieved = abytes / (dom_ms_per_launch / 1000.0) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, E * N)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic(dom, E * N), "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "dram_frac": (traffic / (dom_ms_per_launch / 1000.0) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": abytes, "ms_per_launch": dom_ms_per_launch,
-                "note": "algorithmic bytes = SURVEY.md 8-d (the reference's f64 fields at element granularity, f32 obs); "
-                        "the compact cell records move fewer bytes than that, see traffic (ncu DRAM bytes per launch)"}
-    # whole-step view: algorithmic bytes of every family per step / step time
+                "note": "frac: algorithmic bytes = SURVEY.md 8-d (the reference's f64 fields at element granularity, f32 obs) "
+                        "/ event time / peak, i.e. how fast the reference's bytes are served; dram_frac: the DRAM bytes ncu "
+                        "measured for this launch / event time / peak, i.e. how busy the HBM is (the 8-byte cell records "
+                        "move far fewer bytes than the f64 planes)"}
     step_bytes = sum(algorithmic_bytes(f, wl, E, C, st) for f in kernels)
     roofline["step_achieved"] = step_bytes / (ms / K / 1000.0) / 1e9
     roofline["step_frac"] = roofline["step_achieved"] / peak
     roofline["bytes_per_ant_step"] = step_bytes / (E * N)
 
+    # ---- the same K steps late in the episode (ants dispersed, long trails): untimed fast-forward, then timed
+    late = None
+    if late_start > 0:
+        if episode_step[0] < late_start:
+            run_steps(late_start - episode_step[0])
+        late_first = episode_step[0]
+        late_ms = timed(K)
+        late = {"first_step": late_first, "steps": K, "ms_per_step": late_ms / K,
+                "value": world * E * N * K / (late_ms / 1000.0), "vs_early": (late_ms / K) / (ms / K)}
+
     # ---- end to end through the host-buffer C ABI (numpy in, numpy out; copies inside the timed region)
-    e2e = None
+    e2e, e2e_packed = None, None
     if args.e2e_steps > 0:
         h_rot = batch.pinned("rot", (E, N), np.int8)
         h_ph = batch.pinned("ph", (E, N), np.int8)
         h_rot[:] = rot_tape[0].cpu().numpy()
         h_ph[:] = ph_tape[0].cpu().numpy()
-        batch.step_host(h_rot, h_ph)
-        batch.update_host(None)
-        barrier()
-        t0 = time.perf_counter()
-        ev0.record()
-        for _ in range(args.e2e_steps):
-            batch.step_host(h_rot, h_ph)
+        L = batch.packed_layout()
+
+        def time_e2e(step_fn):
+            step_fn(h_rot, h_ph)
             batch.update_host(None)
-        ev1.record()
-        barrier()
-        e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1000.0)
-        if world > 1:
-            tmax = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            e_ms = float(tmax.item())
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            for _ in range(args.e2e_steps):
+                step_fn(h_rot, h_ph)
+                batch.update_host(None)
+            ev1.record()
+            barrier()
+            e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1000.0)
+            if world > 1:
+                tmax = torch.tensor([e_ms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+                e_ms = float(tmax.item())
+            return e_ms
+        dense_bytes = E * N * (49 * C * 4 + 8 + 8)
+        packed = bool(L.supported) and not os.environ.get("ANTS_E2E_DENSE") and E * N * 49 * C * 4 >= (4 << 20)
+        pcie_bytes = E * N * (int(L.bytes_per_ant) + 8 + 8) if packed else dense_bytes
+        e_ms = time_e2e(batch.step_host)
+        pcie_peak = 56.3e9                     # pinned D2H copy measured on this pool (scripts/microbench/host_bw.cu)
         e2e = {"value": world * E * N * args.e2e_steps / (e_ms / 1000.0), "unit": "ant-steps/s",
-               "h2d_bytes_per_step": 2 * E * N, "d2h_bytes_per_step": E * N * (49 * C * 4 + 8 + 8),
+               "h2d_bytes_per_step": 2 * E * N, "d2h_bytes_per_step": pcie_bytes, "host_result_bytes_per_step": dense_bytes,
                "steps": args.e2e_steps, "ms_per_step": e_ms / args.e2e_steps,
-               "api": "ants_step_host + ants_update_host (pinned numpy buffers)"}
+               "pcie_frac": pcie_bytes / (e_ms / args.e2e_steps / 1000.0) / pcie_peak,
+               "host_write_gbs": dense_bytes / (e_ms / args.e2e_steps / 1000.0) / 1e9,
+               "api": "ants_step_host + ants_update_host (pinned numpy buffers in, dense (E,N,7,7,C) f32 numpy out); "
+                      + ("the observation crosses PCIe packed (visible samples, 12 B each) and is expanded to the dense array "
+                         "by host threads inside the call" if packed else "dense device-to-host copy")}
+        if packed:
+            p_ms = time_e2e(batch.step_host_packed)
+            e2e_packed = {"value": world * E * N * args.e2e_steps / (p_ms / 1000.0), "unit": "ant-steps/s",
+                          "h2d_bytes_per_step": 2 * E * N, "d2h_bytes_per_step": pcie_bytes, "steps": args.e2e_steps,
+                          "ms_per_step": p_ms / args.e2e_steps,
+                          "pcie_frac": pcie_bytes / (p_ms / args.e2e_steps / 1000.0) / pcie_peak,
+                          "api": "ants_step_host_packed + ants_update_host: the observation stays in its packed form on "
+                                 "the host (ants_unpack_obs expands what the consumer needs)"}
 
     # ---- optional end-of-rollout statistics reduction (the only collective of the design)
-    rollout_stats = None
     fin = batch.export_state(keys=("anthill_food", "holding"))
     local = torch.tensor([float(fin["anthill_food"].sum()), float(fin["holding"].sum())], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(local, op=dist.ReduceOp.SUM)
-    rollout_stats = {"anthill_food_total": float(local[0].item()), "carried_food_total": float(local[1].item())}
+    rollout_stats = {"anthill_food_total": float(local[0].item()), "carried_food_total": float(local[1].item()),
+                     "episode_steps": episode_step[0]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = run_cpu_baseline(wl, 2, args.cpu_steps)
+        cpu = run_cpu_baseline(wl, 3, args.cpu_steps)
 
     if rank == 0:
         line = {
@@ -372,6 +450,7 @@ def run_ours(args):
             "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "envs_per_gpu": E, "envs_total": E * world,
                        "ants_per_env": N, "map": [wl["w"], wl["h"]], "pheromones": wl["n_phero"], "rocks": wl["n_rocks"],
                        "obs": "7x7x%d f32" % C, "evaporation": st["evap_mode"], "cell_record": record,
+                       "timed_steps": "steps %d-%d of the episode, one ants_rollout call" % (first_timed_step, first_timed_step + K),
                        "precision": "f64 positions / headings / sample coordinates; %s; f32 obs" % (
                            {"compact": "16 B cell records (f32 pheromone, bit-exact for saturated deposits via the decay "
                                        "table; f32 food)",
@@ -380,8 +459,7 @@ def run_ours(args):
                        % (st["device_bytes"] / 1e9), "parallelism": "env-sharded x%d, no per-step collective" % world,
                        "noise": "in-kernel Philox", "actions": "uniform random, pre-recorded tape on device"},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "kernels": kernels,
-            "e2e": e2e, "cpu_baseline": cpu, "rollout_stats": rollout_stats,
-            "active_tile_fraction": (st["active_tiles"] / st["total_tiles"]) if st["total_tiles"] else None,
+            "late": late, "e2e": e2e, "e2e_packed": e2e_packed, "cpu_baseline": cpu, "rollout_stats": rollout_stats,
             "setup_s": t_setup,
         }
         emit(line)
@@ -391,17 +469,18 @@ def run_ours(args):
 
 
 def run_reference(args):
-    """The reference's own CPU algorithm for the path (oracle port; the Python reference cannot travel to the GPU
-    box), all host cores, one env per process; each bench step = one step()+update() of every env."""
+    """The reference's own CPU implementation of the path: the UNMODIFIED reference (oracle/_ref, byte-compiled from
+    /root/reference by oracle/build_ref.py; the oracle port only if that is missing), all host cores, one env per
+    process; each bench step = one step()+update() of every env."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
     procs = os.cpu_count() or 1
-    r = run_cpu_baseline(wl, args.warmup, args.steps, procs)
+    r = run_cpu_baseline(wl, max(args.warmup, 3), args.steps, procs)
     line = {"impl": "reference", "metric": "ant-steps/sec (envs x ants x steps)", "value": r["value"],
             "unit": "ant-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": r["ms_per_env_step"], "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": r["ms_per_env_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, wl["desc"]), "envs_total": procs,
                        "ants_per_env": wl["n_ants"], "map": [wl["w"], wl["h"]]},
@@ -446,8 +525,10 @@ def main():
     ap.add_argument("--evap", default="lazy", choices=["lazy", "tiles", "dense"])
     ap.add_argument("--record", default="compact8", choices=["compact8", "compact", "f64"],
                     help="cell record format (compact8 = 8 B, compact = 16 B: lazy mode only)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--late-start", type=int, default=900,
+                    help="episode step at which the K steps are timed again (0 = skip the late window)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

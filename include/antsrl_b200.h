@@ -186,10 +186,39 @@ int ants_step_host(AntsBatch *b, const int8_t *h_rot, const int8_t *h_ph, float 
                    double *h_reward, int32_t *done);
 int ants_update_host(AntsBatch *b, const double *h_noise);
 
+/* ---- packed observations: what crosses PCIe on the host-buffer path.
+ * The dense observation is 4 C bytes per sample (1372 B per ant for the generator's 7x7x7 window); only the visible
+ * samples carry information (environment_generator.py:35-41 masks 12 of 49 to the constant -1, RL_api.py:147-148), the
+ * ants / anthill / walls / rocks channels are 0/1 (RL_api.py:128-142) and the food channel holds integer counts.  Packed
+ * form, per ant: n_visible samples of 12 bytes { f32 value_channel[0]; f32 value_channel[1]; u16 food; u8 flags; u8 0 }
+ * (flags bit k = flag_channel[k]); ants_unpack_obs rebuilds the dense (N, S, S, C) f32 array bit for bit on host
+ * threads.  ants_step_host uses this transport internally (same signature, same result, ~3x fewer PCIe bytes);
+ * ants_step_host_packed hands the packed buffer to the caller, who expands all of it, part of it or none. */
+typedef struct AntsPackedLayout {
+    int32_t supported;               /* 0: this configuration has no packed form (more than two pheromone channels, ...) */
+    int32_t n_samples, n_channels;   /* S*S, C of the dense observation */
+    int32_t n_visible;               /* samples per ant in the packed form */
+    int32_t sample_bytes;            /* 12 */
+    int64_t bytes_per_ant;           /* n_visible * sample_bytes */
+    int32_t flag_channel[8];         /* dense channel behind bit k of the flags byte, -1 = unused */
+    int32_t value_channel[2];        /* dense channels stored as f32 (pheromones), -1 = unused */
+    int32_t food_channel;            /* dense channel stored as u16 count, -1 = none */
+    uint8_t visible_index[228];      /* row-major sample index of packed sample v */
+} AntsPackedLayout;
+/* pure function of the configuration (needs no device) */
+int ants_packed_layout(const AntsConfig *cfg, AntsPackedLayout *out);
+/* RLApi.step with host buffers; the observation arrives packed: h_packed holds E*N*bytes_per_ant (+16) bytes.  Returns
+ * ANTS_E_STATE if a value of this step has no packed form (a non-integer amount of food): use ants_step_host then. */
+int ants_step_host_packed(AntsBatch *b, const int8_t *h_rot, const int8_t *h_ph, void *h_packed, float *h_agent_state,
+                          double *h_reward, int32_t *done);
+/* packed -> dense for n_ants consecutive ants, on n_threads host threads (0 = all cores).  Host code only. */
+int ants_unpack_obs(const AntsPackedLayout *layout, const void *h_packed, int64_t n_ants, float *h_obs, int32_t n_threads);
+
 int ants_get_stats(AntsBatch *b, AntsStats *out);
 /* time (ms) spent by the named kernel family since the last reset, measured with CUDA events on the handle's
- * stream when profiling is enabled with ants_set_profiling(b, 1): "move", "food_commit", "perceive",
- * "collide", "rocks", "evaporate", "deposit", "absorb" */
+ * stream when profiling is enabled with ants_set_profiling(b, 1): "perceive", "env_move", "env_update",
+ * "env_update_move" (block-per-environment kernels), "evaporate", "absorb", "misc", "pack"; and for handles on the
+ * flat kernels (non-lazy field, > 1024 ants per env) "move", "food_commit", "collide", "rocks", "deposit" */
 int ants_set_profiling(AntsBatch *b, int32_t on);
 int ants_get_kernel_ms(AntsBatch *b, const char *name, double *ms, int64_t *launches);
 int ants_reset_kernel_ms(AntsBatch *b);

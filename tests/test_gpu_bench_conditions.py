@@ -177,6 +177,7 @@ def test_reference_1000_step_episode(mode):
 
 # ------------------------------------------------------------------------------------------------ BASELINE configs[1]
 _CFG2 = {}
+PLANES_EVERY = 20          # plane summaries (remaining food, explored count, pheromone mass) every 20th step
 
 
 def _cfg2_oracle_worker(k):
@@ -203,9 +204,10 @@ def _cfg2_oracle_worker(k):
         assert np.array_equal(c["mandibles"][t, k], s["mandibles"]), what + ": mandibles"
         assert np.array_equal(c["reward_state"][t, k], s["reward_state"]), what + ": reward_state"
         assert c["anthill_food"][t, k] == float(s["anthill_food"]), what + ": anthill_food"
-        assert c["food_sum"][t, k] == s["food"].sum(), what + ": food"
-        assert c["explored_count"][t, k] == int(np.asarray(s["explored"]).sum()), what + ": explored"
-        np.testing.assert_allclose(c["phero_sum"][t, k], s["phero"].sum(axis=(1, 2)), rtol=1e-5, err_msg=what + ": phero")
+        if t % PLANES_EVERY == PLANES_EVERY - 1:
+            assert c["food_sum"][t, k] == s["food"].sum(), what + ": food"
+            assert c["explored_count"][t, k] == int(np.asarray(s["explored"]).sum()), what + ": explored"
+            np.testing.assert_allclose(c["phero_sum"][t, k], s["phero"].sum(axis=(1, 2)), rtol=1e-5, err_msg=what + ": phero")
     compare_state(c["final"][k], [o], "env %d final" % e, c["cfg"])
     return float(o.s["anthill_food"])
 
@@ -214,8 +216,8 @@ def test_configs1_1024_envs_1000_steps():
     """BASELINE.json configs[1]: the reference's default generated map (200x200, 50 ants, walls + food
     + anthill from the generator, seeds 1000 + e) batched to 1024 envs on one GPU, random actions replayed from a
     recorded tape, main.py's loop for 1000 steps; 32 of the envs are compared with the oracle at EVERY step
-    (observations, rewards, ant cells bit-exact, positions, carried food, mandibles, reward_state, delivered / remaining
-    food, explored count, pheromone mass) and in full at the end."""
+    (observations, rewards, ant cells bit-exact, positions, carried food, mandibles, reward_state, delivered food), their
+    planes every 20th step (remaining food, explored count, pheromone mass) and in full at the end."""
     import torch
     from antsrl_b200 import BatchedAnts
     from antsrl_b200.generator import BatchedEnvironmentGenerator, CirclesGenerator, stack_states
@@ -251,11 +253,12 @@ def test_configs1_1024_envs_1000_steps():
         st = b.export_state(keys=("x", "y", "theta", "holding", "mandibles", "reward_state", "anthill_food"))
         for k in ("x", "y", "theta", "holding", "mandibles", "reward_state", "anthill_food"):
             rec[k][t] = st[k][picks]
-        for j, e in enumerate(picks):
-            pl = b.export_state(keys=("food", "explored", "phero"), envs=(e, 1))
-            rec["food_sum"][t, j] = pl["food"].sum()
-            rec["explored_count"][t, j] = int(pl["explored"].sum())
-            rec["phero_sum"][t, j] = pl["phero"][0].sum(axis=(1, 2))
+        if t % PLANES_EVERY == PLANES_EVERY - 1:                  # the planes of the picked envs (one export per env)
+            for j, e in enumerate(picks):
+                pl = b.export_state(keys=("food", "explored", "phero"), envs=(e, 1))
+                rec["food_sum"][t, j] = pl["food"].sum()
+                rec["explored_count"][t, j] = int(pl["explored"].sum())
+                rec["phero_sum"][t, j] = pl["phero"][0].sum(axis=(1, 2))
     final = [b.export_state(envs=(e, 1)) for e in picks]
     whole = b.export_state(keys=("anthill_food", "holding"))
     b.close()

@@ -21,13 +21,17 @@ def _variants(kw, n):
 
 
 @pytest.mark.parametrize("name,kw", GOLDEN_SCENARIOS, ids=[n for n, _ in GOLDEN_SCENARIOS])
-@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy", "lazy_compact", "lazy_compact8"])
-def test_cuda_matches_oracle_every_step(name, kw, evap_mode):
+@pytest.mark.parametrize("evap_mode", ["dense", "tiles", "lazy", "lazy_compact", "lazy_compact8", "lazy_compact8_flat"])
+def test_cuda_matches_oracle_every_step(name, kw, evap_mode, monkeypatch):
     """3 envs per scenario family (different seeds), device-pointer API, taped collision noise; every evaporation
-    mode and both cell-record formats."""
+    mode and every cell-record format.  Lazy handles run the block-per-environment kernels (ants_env_fused.cuh);
+    "_flat" forces the flat kernels the other modes use onto the 8-byte records as well."""
     kw = dict(kw)
     kw["steps"] = min(kw["steps"], 40)
     record = "f64"
+    if evap_mode.endswith("_flat"):
+        monkeypatch.setenv("ANTS_NO_FUSED", "1")
+        evap_mode = evap_mode[:-5]
     if evap_mode.startswith("lazy_compact"):
         if kw.get("diffuse_factor", 0.0) != 0.0:
             pytest.skip("compact records exist for the lazy (diffusion-free) field only")
@@ -164,6 +168,12 @@ ODD_CONFIGS = [
     # diffusion on a map of several, partly filled 64x64 stencil tiles (TMA zero fill at every border), with rocks
     ("diffuse_tiles", dict(seed=37, w=130, h=70, n_ants=40, n_rocks=3, steps=20, diffuse_factor=0.03, evap_factor=0.005,
                            n_walls=8, n_food=6)),
+    # diffusion with the DEFAULT channel list but windows the row kernel does not serve (radius 4 and 1): the generic
+    # kernel must read the f64 planes, not the (empty) record fields
+    ("diffuse_r4", dict(seed=38, w=60, h=52, n_ants=40, steps=20, diffuse_factor=0.02, evap_factor=0.01, radius=4,
+                        mask=None, fwd_delta=2)),
+    ("diffuse_r1", dict(seed=39, w=44, h=40, n_ants=30, steps=20, diffuse_factor=0.03, evap_factor=0.02, radius=1,
+                        mask=None, fwd_delta=0)),
     # rocks with a non-default channel list (generic perception path) on a non-square map
     ("rocks_generic", dict(seed=36, w=72, h=56, n_ants=40, n_rocks=5, steps=30,
                            channels=["rocks", "food", "ants", "phero1", "walls"])),
@@ -333,9 +343,10 @@ def _cmp_outputs(gpu, refs, what):
     assert_close(rew, np.stack([r[2] for r in refs]), what + ": reward")
 
 
+@pytest.mark.parametrize("flat", [False, True], ids=["env_kernels", "flat_kernels"])
 @pytest.mark.parametrize("record", ["compact", "compact8", "f64"])
 @pytest.mark.parametrize("n_rocks", [0, 5])
-def test_irregular_call_order(record, n_rocks):
+def test_irregular_call_order(record, n_rocks, flat, monkeypatch):
     """observe / step / update in an order main.py never uses (update before the first step, two steps in a row, two
     updates in a row, a stand-alone observation in between): the per-call bookkeeping the kernels share across calls
     (wall flags written by the move, the double-buffered absorb counter, deposit ownership phases, generation stamps)
@@ -344,6 +355,8 @@ def test_irregular_call_order(record, n_rocks):
     from antsrl_b200 import BatchedAnts
     from parity_util import compare_state
     from oracle.antsrl_oracle import OracleEnv
+    if flat:
+        monkeypatch.setenv("ANTS_NO_FUSED", "1")
     scen = [make_scenario(seed=900 + e, w=56, h=48, n_ants=40, n_rocks=n_rocks, steps=16, n_walls=6, n_food=8)
             for e in range(3)]
     cfg = scen[0][0]
@@ -551,3 +564,85 @@ def test_compact8_step_counter_wraps():
     assert outs["tiles"][3].max() > 0
     for a, c in zip(outs["tiles"], outs["compact8"]):
         np.testing.assert_allclose(c, a, rtol=1e-5, atol=0)
+
+
+def test_generic_perception_kernel_in_diffusion_mode(monkeypatch):
+    """ANTS_PERCEIVE_GENERIC routes the default channel list through k_perceive: with DIFFUSE_FACTOR != 0 it must
+    read the pheromone planes like k_perceive_rows does (the straight-line record layouts would show zeros)."""
+    monkeypatch.setenv("ANTS_PERCEIVE_GENERIC", "1")
+    for name in ("diffuse", "rocks", "default_small"):
+        kw = dict(dict(GOLDEN_SCENARIOS)[name])
+        kw["steps"] = 25
+        run_parity(_variants(kw, 2), evap_mode="dense")
+    kw = dict(dict(GOLDEN_SCENARIOS)["default_small"], steps=25)
+    run_parity(_variants(kw, 2), evap_mode="lazy", record="compact8")
+
+
+def test_lazy_mode_rejects_slow_evaporation():
+    """A max_val deposit that does not decay below 0.01 within the 16384-entry table cannot be boxed: ants_create
+    refuses lazy evaporation for such factors instead of silently zeroing the field at age 16384; the eager modes
+    take them."""
+    from antsrl_b200 import BatchedAnts, AntsError
+    cfg, init, tape = make_scenario(seed=45, w=32, h=32, n_ants=8, steps=4, evap_factor=0.0005)
+    with pytest.raises(AntsError, match="evap_factor"):
+        BatchedAnts(cfg, 1, evap_mode="lazy", record="compact8")
+    with pytest.raises(AntsError, match="evap_factor"):
+        BatchedAnts(cfg, 1, evap_mode="lazy")
+    run_parity([(cfg, init, tape)], evap_mode="tiles")
+
+
+def test_partial_import_keeps_scalars():
+    """Patching positions mid-episode must not rewind the timestep (done flag, Philox counter), flip the activation
+    dtype (deposit strength 256 vs 1) or re-alias the reward."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    cfg, init, tape = make_scenario(seed=46, w=32, h=32, n_ants=12, steps=6)
+    b = BatchedAnts(cfg, 1, evap_mode="lazy", record="compact8")
+    b.import_state(stack_init(cfg, [init]))
+    b.observe()
+    for t in range(3):
+        b.step(torch.from_numpy(tape["rot"][t][None]).cuda(), torch.from_numpy(tape["ph"][t][None]).cuda())
+        b.update(None)
+    before = b.export_state()
+    b.import_state({"x": before["x"], "y": before["y"]})
+    after = b.export_state()
+    assert after["timestep"] == before["timestep"] == 4
+    assert after["act_bool"] == before["act_bool"] and after["rw_alias"] == before["rw_alias"] is False
+    for k in ("holding", "phero", "food", "explored", "theta"):
+        assert np.array_equal(before[k], after[k]), k
+    b.close()
+
+
+@pytest.mark.parametrize("record,n_rocks,n_ants,n_envs", [("compact8", 6, 300, 3), ("compact8", 0, 50, 7), ("compact", 4, 520, 2),
+                                                          ("f64", 3, 1024, 2), ("compact8", 2, 1100, 2)])
+def test_rollout_matches_oracle(record, n_rocks, n_ants, n_envs):
+    """ants_rollout (update_k and the move of step_{k+1} in ONE launch of the block-per-environment kernel; 1, 2 or 4
+    ants per thread, several envs per block for small N; 1100 ants per env falls back to the flat kernels) against the
+    oracle: last observation / reward and the full final state after 30 steps, Philox noise, crowded hill (shared
+    cells: the last-writer scatters) and food near it."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from oracle.antsrl_oracle import OracleEnv, philox_uniform
+    from parity_util import compare_state
+    T = 30
+    scen = [make_scenario(seed=1200 + e, w=72, h=64, n_ants=n_ants, n_rocks=n_rocks, steps=T, n_walls=6, n_food=14)
+            for e in range(n_envs)]
+    cfg = scen[0][0]
+    oracles = [OracleEnv(c, i) for c, i, _ in scen]
+    b = BatchedAnts(cfg, n_envs, evap_mode="lazy", record=record, rng_seed=21, env_id_base=5)
+    b.import_state(stack_init(cfg, [i for _, i, _ in scen]))
+    b.observe()
+    for o in oracles:
+        o.observation()
+    rot = torch.from_numpy(np.stack([[s[2]["rot"][t] for s in scen] for t in range(T)])).cuda().contiguous()
+    ph = torch.from_numpy(np.stack([[s[2]["ph"][t] for s in scen] for t in range(T)])).cuda().contiguous()
+    obs, ast, rew = b.rollout(rot, ph)
+    refs = []
+    for e, o in enumerate(oracles):
+        for t in range(T):
+            r = o.step(scen[e][2]["rot"][t].astype(np.int64), scen[e][2]["ph"][t].astype(np.int64))
+            o.update(philox_uniform(21, 5 + e, int(o.s["timestep"]), n_ants))
+        refs.append(r)
+    _cmp_outputs((obs, ast, rew), refs, "last step of the rollout")
+    compare_state(b.export_state(), oracles, "after the rollout", cfg)
+    b.close()
