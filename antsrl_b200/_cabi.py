@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "ants_update", "ants_rollout", "ants_host_alloc", "ants_host_free", "ants_observe_host", "ants_step_host",
     "ants_update_host", "ants_get_stats", "ants_set_profiling", "ants_get_kernel_ms", "ants_reset_kernel_ms",
     "ants_sample_actions", "ants_export_env_state", "ants_packed_layout", "ants_step_host_packed", "ants_unpack_obs",
+    "ants_import_env_state",
 ]
 
 
@@ -60,7 +61,8 @@ class AntsHostState(C.Structure):
 class AntsStats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("updates", C.c_int64), ("observations", C.c_int64),
                 ("kernel_launches", C.c_int64), ("active_tiles", C.c_int64), ("total_tiles", C.c_int64),
-                ("food_commits", C.c_int64), ("absorb_events", C.c_int64), ("device_bytes", C.c_int64)]
+                ("food_commits", C.c_int64), ("absorb_events", C.c_int64), ("device_bytes", C.c_int64),
+                ("e2e_dense_permille", C.c_int64)]
 
 
 class AntsPackedLayout(C.Structure):
@@ -96,6 +98,7 @@ def load_library(path=None):
     lib.ants_import_state.argtypes = [vp, C.POINTER(AntsHostState)]
     lib.ants_export_state.argtypes = [vp, C.POINTER(AntsHostState)]
     lib.ants_export_env_state.argtypes = [vp, i32, i32, C.POINTER(AntsHostState)]
+    lib.ants_import_env_state.argtypes = [vp, i32, i32, C.POINTER(AntsHostState)]
     lib.ants_activate_all_pheromones.argtypes = [vp, vp, i32]
     lib.ants_observe.argtypes = [vp, vp, vp, vp, vp]
     lib.ants_step.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(i32)]

@@ -152,12 +152,16 @@ class BatchedAnts:
                   rock_weights=(E, R))
         return sh
 
-    def import_state(self, state):
+    def import_state(self, state, envs=None):
         """state: dict of numpy arrays with a leading env axis (missing keys are left untouched); scalars
-        ``timestep``, ``rw_alias``, ``act_bool`` apply to the whole batch."""
+        ``timestep``, ``rw_alias``, ``act_bool`` apply to the whole batch.  With ``envs=(env0, n)`` the arrays hold
+        only that window of environments (a new episode for some envs; a large batch uploaded in slices)."""
+        env0, n_envs = (0, self.E) if envs is None else (int(envs[0]), int(envs[1]))
+        if env0 < 0 or n_envs < 1 or env0 + n_envs > self.E:
+            raise ValueError("env window (%d, %d) outside the batch of %d envs" % (env0, n_envs, self.E))
         hs = AntsHostState()
         keep = []
-        sh = self._shapes()
+        sh = self._shapes(n_envs)
         for k in _STATE_F64 + _STATE_U8 + ("anthill_xyr",):
             if k not in state or state[k] is None:
                 continue
@@ -175,7 +179,7 @@ class BatchedAnts:
         hs.timestep = int(state["timestep"]) if state.get("timestep") is not None else 0
         hs.rw_alias = (1 if state["rw_alias"] else 0) if state.get("rw_alias") is not None else -1
         hs.act_bool = (1 if state["act_bool"] else 0) if state.get("act_bool") is not None else -1
-        check(self.lib, self.lib.ants_import_state(self._h, C.byref(hs)))
+        check(self.lib, self.lib.ants_import_env_state(self._h, env0, n_envs, C.byref(hs)))
 
     def export_state(self, keys=None, envs=None):
         """The state dict of the whole batch, or with ``envs=(env0, n)`` of that window of environments only

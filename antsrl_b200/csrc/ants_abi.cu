@@ -13,6 +13,7 @@
 #include <string.h>
 #include <stdlib.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -70,9 +71,14 @@ public:
         }
         cv_.notify_one();
     }
-    void wait_idle() {
+    // blocks until every submitted task has run; returns when the last one finished (seconds on the steady clock)
+    double wait_idle() {
         std::unique_lock<std::mutex> lk(m_);
         idle_.wait(lk, [&] { return pending_ == 0; });
+        return last_idle_;
+    }
+    static double now() {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
     }
 
 private:
@@ -109,7 +115,7 @@ private:
             fn();
             {
                 std::lock_guard<std::mutex> lk(m_);
-                if (--pending_ == 0) idle_.notify_all();
+                if (--pending_ == 0) { last_idle_ = now(); idle_.notify_all(); }
             }
         }
     }
@@ -118,6 +124,7 @@ private:
     std::vector<std::function<void()>> q_;
     std::vector<std::thread> threads_;
     int pending_ = 0;
+    double last_idle_ = 0.0;
     bool stop_ = false;
 };
 
@@ -200,6 +207,10 @@ struct AntsBatch {
     uint32_t *d_pack_fail = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
     int pack_disabled = 0;          // a value without a packed form was seen (non-integer food): dense copies until the next import
+    // ants_step_host fills the dense host array from two sides: the DMA engine copies the last `dense_frac` of the ants
+    // dense while the host threads expand the packed rest; the split follows whichever side finished later
+    double dense_frac = 0.2;
+    int dense_frac_fixed = 0;
 };
 
 namespace {
@@ -674,13 +685,22 @@ int packed_transfer(AntsBatch *b, uint8_t *h_dst, float *h_obs, float *h_agent_s
     const Params &p = b->p;
     const AntsPackedLayout &L = b->pack_layout;
     const int64_t EN = p.EN, bpa = L.bytes_per_ant, dense = (int64_t)p.S2 * p.C;
+    const double t_start = HostPool::now();
+    // ants [0, n_packed) cross PCIe packed (and are expanded by the host threads when a dense array is wanted); ants
+    // [n_packed, EN) are copied dense by the DMA engine
+    int64_t n_dense = 0;
+    if (h_obs) {
+        n_dense = (int64_t)(b->dense_frac * (double)EN) / 64 * 64;
+        n_dense = n_dense < 0 ? 0 : (n_dense > EN ? EN : n_dense);
+    }
+    const int64_t n_packed = EN - n_dense;
     CK(cudaMemsetAsync(b->d_pack_fail, 0, sizeof(uint32_t), b->stream));
-    int n_chunks = (int)(EN / 16384);
+    int n_chunks = (int)(n_packed / 16384);
     n_chunks = n_chunks < 1 ? 1 : (n_chunks > (int)b->chunk_ev.size() ? (int)b->chunk_ev.size() : n_chunks);
-    const int64_t per = (cdiv(EN, n_chunks) + 63) / 64 * 64;
+    const int64_t per = (cdiv(n_packed > 0 ? n_packed : 1, n_chunks) + 63) / 64 * 64;
     int used = 0;
     for (int c = 0; c < n_chunks; ++c) {
-        const int64_t a0 = c * per, n = EN - a0 < per ? EN - a0 : per;
+        const int64_t a0 = c * per, n = n_packed - a0 < per ? n_packed - a0 : per;
         if (n <= 0) break;
         {
             LaunchScope ls(b, F_PACK);
@@ -692,6 +712,9 @@ int packed_transfer(AntsBatch *b, uint8_t *h_dst, float *h_obs, float *h_agent_s
         CK(cudaEventRecord(b->chunk_ev[c], b->stream));
         used = c + 1;
     }
+    if (n_dense > 0)
+        CK(cudaMemcpyAsync(h_obs + n_packed * dense, b->st_obs + n_packed * dense, (size_t)(n_dense * dense) * sizeof(float),
+                           cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(h_agent_state, b->st_as, (size_t)EN * 8, cudaMemcpyDeviceToHost, b->stream));
     if (h_reward) CK(cudaMemcpyAsync(h_reward, b->st_reward, (size_t)EN * 8, cudaMemcpyDeviceToHost, b->stream));
     CK(cudaMemcpyAsync(b->h_counts + 8, b->d_pack_fail, sizeof(uint32_t), cudaMemcpyDeviceToHost, b->stream));
@@ -700,7 +723,7 @@ int packed_transfer(AntsBatch *b, uint8_t *h_dst, float *h_obs, float *h_agent_s
         const AntsUnpackPlan *plan = b->unpack_plan;
         const int T = pool.size();
         for (int c = 0; c < used; ++c) {
-            const int64_t a0 = c * per, n = EN - a0 < per ? EN - a0 : per;
+            const int64_t a0 = c * per, n = n_packed - a0 < per ? n_packed - a0 : per;
             CK(cudaEventSynchronize(b->chunk_ev[c]));
             const int64_t piece = cdiv(n, T);
             for (int64_t s0 = 0; s0 < n; s0 += piece) {
@@ -710,7 +733,16 @@ int packed_transfer(AntsBatch *b, uint8_t *h_dst, float *h_obs, float *h_agent_s
         }
     }
     CK(cudaStreamSynchronize(b->stream));
-    if (h_obs) HostPool::get().wait_idle();
+    if (h_obs) {
+        const double t_dma = HostPool::now();
+        const double t_cpu = used > 0 ? HostPool::get().wait_idle() : t_dma;
+        if (!b->dense_frac_fixed && !b->h_counts[8]) {
+            // move the split towards the side that finished first (half of the imbalance per step)
+            const double total = HostPool::now() - t_start;
+            if (total > 0.0) b->dense_frac += 0.5 * (t_cpu - t_dma) / total * (b->dense_frac > 0.05 ? b->dense_frac + 0.3 : 0.35);
+            b->dense_frac = b->dense_frac < 0.0 ? 0.0 : (b->dense_frac > 0.9 ? 0.9 : b->dense_frac);
+        }
+    }
     return b->h_counts[8] ? 1 : ANTS_OK;
 }
 
@@ -1030,6 +1062,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         }
     }
     {   // packed observation transport
+        if (const char *x = getenv("ANTS_E2E_DENSE_FRACTION")) { b->dense_frac = atof(x); b->dense_frac_fixed = 1; }
         packed_layout_of(cfg, &b->pack_layout);
         b->unpack_plan = new AntsUnpackPlan();
         unpack_plan_of(&b->pack_layout, b->unpack_plan);
@@ -1085,14 +1118,18 @@ int ants_synchronize(AntsBatch *b) {
     return ANTS_OK;
 }
 
-int ants_import_state(AntsBatch *b, const AntsHostState *s) {
+int ants_import_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, const AntsHostState *s) {
     if (!b || !s) return fail(ANTS_E_ARG, "null argument");
-    CK(cudaSetDevice(b->cfg.device));
     Params &p = b->p;
+    if (env0 < 0 || n_envs < 1 || (int64_t)env0 + n_envs > p.E)
+        return fail(ANTS_E_ARG, "env window [%d, %d) outside the batch of %d envs", env0, env0 + n_envs, p.E);
+    CK(cudaSetDevice(b->cfg.device));
     cudaStream_t st = b->stream;
-    const size_t EN8 = (size_t)p.EN * sizeof(double);
+    const bool whole = n_envs == p.E;
+    const size_t a0 = (size_t)env0 * p.N, an = (size_t)n_envs * p.N;      // the window's ants
+    const size_t AN8 = an * sizeof(double);
     auto up = [&](double *dst, const double *src) -> cudaError_t {
-        return src ? cudaMemcpyAsync(dst, src, EN8, cudaMemcpyHostToDevice, st) : cudaSuccess;
+        return src ? cudaMemcpyAsync(dst + a0, src, AN8, cudaMemcpyHostToDevice, st) : cudaSuccess;
     };
     CK(up(p.x, s->x)); CK(up(p.y, s->y)); CK(up(p.theta, s->theta));
     CK(up(p.prev_x, s->prev_x ? s->prev_x : s->x)); CK(up(p.prev_y, s->prev_y ? s->prev_y : s->y));
@@ -1100,21 +1137,24 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     CK(up(p.holding, s->holding)); CK(up(p.seed, s->seed));
     CK(up(p.rw_holding_prev, s->rw_holding_prev)); CK(up(p.rw_prev_dist, s->rw_prev_dist));
     CK(up(p.rewards, s->rewards));
-    if (s->mandibles) CK(cudaMemcpyAsync(p.mandibles, s->mandibles, p.EN, cudaMemcpyHostToDevice, st));
-    if (s->reward_state) CK(cudaMemcpyAsync(p.reward_state, s->reward_state, p.EN, cudaMemcpyHostToDevice, st));
+    if (s->mandibles) CK(cudaMemcpyAsync(p.mandibles + a0, s->mandibles, an, cudaMemcpyHostToDevice, st));
+    if (s->reward_state) CK(cudaMemcpyAsync(p.reward_state + a0, s->reward_state, an, cudaMemcpyHostToDevice, st));
     std::vector<double> act_t;
-    if (s->activation && p.P > 0) {
-        act_t.resize((size_t)p.EN * p.P);
-        for (int64_t i = 0; i < p.EN; ++i)
-            for (int k = 0; k < p.P; ++k) act_t[(size_t)k * p.EN + i] = s->activation[i * p.P + k];
-        CK(cudaMemcpyAsync(p.act, act_t.data(), act_t.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (s->activation && p.P > 0) {                                        // device layout [P][E*N]
+        act_t.resize(an * p.P);
+        for (size_t i = 0; i < an; ++i)
+            for (int k = 0; k < p.P; ++k) act_t[(size_t)k * an + i] = s->activation[i * p.P + k];
+        for (int k = 0; k < p.P; ++k)
+            CK(cudaMemcpyAsync(p.act + (size_t)k * p.EN + a0, act_t.data() + (size_t)k * an, AN8, cudaMemcpyHostToDevice, st));
     }
-    if (s->x && s->prev_x && s->prev_y && s->y)
-        b->prev_synced = (memcmp(s->x, s->prev_x, EN8) == 0 && memcmp(s->y, s->prev_y, EN8) == 0) ? 1 : 0;
-    else if (s->x)
+    if (s->x && s->prev_x && s->prev_y && s->y) {
+        const bool same = memcmp(s->x, s->prev_x, AN8) == 0 && memcmp(s->y, s->prev_y, AN8) == 0;
+        b->prev_synced = same ? (whole ? 1 : b->prev_synced) : 0;          // (one flag for the batch: unsynced wins)
+    } else if (s->x && whole) {
         b->prev_synced = 1;
+    }
     // map fields: dense host array -> device scratch -> pack kernel into the cell records
-    const size_t ncell = (size_t)p.E * p.W * p.H;
+    const size_t ncell = (size_t)n_envs * p.W * p.H;
     Scratch scratch;
     if (s->phero || s->food || s->walls || s->explored) {
         size_t need = ncell * 8 * ((s->phero && p.P > 1) ? p.P : 1);
@@ -1124,53 +1164,57 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     void *const d_tmp = scratch.ptr;
     if (s->phero && p.P > 0) {
         CK(cudaMemcpyAsync(d_tmp, s->phero, ncell * 8 * p.P, cudaMemcpyHostToDevice, st));
-        for (int k = 0; k < p.P; ++k) ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs);
+        for (int k = 0; k < p.P; ++k)
+            ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, p.P, k, 8 * k, k, b->lazy_now, b->lazy_abs, env0, n_envs);
         TRY(check_launch("k_pack_f64"));
         if (p.tile_active) {
-            ants::k_tiles_from_phero<<<148 * 4, 256, 0, st>>>(p);
+            ants::k_tiles_from_phero<<<148 * 4, 256, 0, st>>>(p, env0, n_envs);
             TRY(check_launch("k_tiles_from_phero"));
         }
     }
     if (s->food) {
         CK(cudaMemcpyAsync(d_tmp, s->food, ncell * 8, cudaMemcpyHostToDevice, st));
-        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off, -1, 0u, 0u);
+        ants::k_pack_f64<<<148 * 8, 256, 0, st>>>(p, (const double *)d_tmp, 1, 0, p.food_off, -1, 0u, 0u, env0, n_envs);
         TRY(check_launch("k_pack_f64"));
         b->needs_sweep = 1;
     }
     if (s->walls) {
         CK(cudaMemcpyAsync(d_tmp, s->walls, ncell, cudaMemcpyHostToDevice, st));
-        ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 0);      // Walls.__init__: astype(bool)
+        ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 0, env0, n_envs);      // Walls.__init__: astype(bool)
         TRY(check_launch("k_pack_u8"));
     }
     if (p.diffuse && (s->walls || s->phero)) {         // the planes carry the wall bit in their sign
-        ants::k_plane_walls<<<148 * 8, 256, 0, st>>>(p);
+        ants::k_plane_walls<<<148 * 8, 256, 0, st>>>(p, env0, n_envs);
         TRY(check_launch("k_plane_walls"));
     }
     if (s->explored) {
         CK(cudaMemcpyAsync(d_tmp, s->explored, ncell, cudaMemcpyHostToDevice, st));
-        ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 1);
+        ants::k_pack_u8<<<148 * 8, 256, 0, st>>>(p, (const uint8_t *)d_tmp, 1, env0, n_envs);
         TRY(check_launch("k_pack_u8"));
-        b->obs_gen = 0; b->occ_gen = 0;
+        // explored cells are stored as "explored long ago" / 0 and occupancy as 0: valid under any generation, so the
+        // counters only restart when the whole batch was replaced
+        if (whole) { b->obs_gen = 0; b->occ_gen = 0; }
     }
     std::vector<int32_t> hill4;
     if (s->anthill_xyr) {
-        hill4.resize((size_t)p.E * 4);
-        for (int e = 0; e < p.E; ++e) {
+        hill4.resize((size_t)n_envs * 4);
+        for (int e = 0; e < n_envs; ++e) {
             int32_t r = s->anthill_xyr[3 * e + 2];
             hill4[4 * e] = s->anthill_xyr[3 * e]; hill4[4 * e + 1] = s->anthill_xyr[3 * e + 1];
             hill4[4 * e + 2] = r; hill4[4 * e + 3] = r < 0 ? -1 : r * r;
         }
-        CK(cudaMemcpyAsync(p.hill, hill4.data(), hill4.size() * 4, cudaMemcpyHostToDevice, st));
-        ants::k_hill_mark<<<148 * 8, 256, 0, st>>>(p);
+        CK(cudaMemcpyAsync(p.hill + (size_t)env0 * 4, hill4.data(), hill4.size() * 4, cudaMemcpyHostToDevice, st));
+        ants::k_hill_mark<<<148 * 8, 256, 0, st>>>(p, env0, n_envs);
         TRY(check_launch("k_hill_mark"));
         b->needs_sweep = 1;
     }
-    if (s->anthill_food) CK(cudaMemcpyAsync(p.hill_food, s->anthill_food, (size_t)p.E * 8, cudaMemcpyHostToDevice, st));
+    if (s->anthill_food) CK(cudaMemcpyAsync(p.hill_food + env0, s->anthill_food, (size_t)n_envs * 8, cudaMemcpyHostToDevice, st));
     if (p.R > 0) {
-        if (s->rock_centers) CK(cudaMemcpyAsync(p.rock_c, s->rock_centers, (size_t)p.E * p.R * 16, cudaMemcpyHostToDevice, st));
-        if (s->rock_radii) CK(cudaMemcpyAsync(p.rock_rad, s->rock_radii, (size_t)p.E * p.R * 8, cudaMemcpyHostToDevice, st));
-        if (s->rock_weights) CK(cudaMemcpyAsync(p.rock_w, s->rock_weights, (size_t)p.E * p.R * 8, cudaMemcpyHostToDevice, st));
-        ants::k_rock_grid_build<<<p.E, 128, 0, st>>>(p);
+        const size_t r0 = (size_t)env0 * p.R, rn = (size_t)n_envs * p.R;
+        if (s->rock_centers) CK(cudaMemcpyAsync(p.rock_c + r0 * 2, s->rock_centers, rn * 16, cudaMemcpyHostToDevice, st));
+        if (s->rock_radii) CK(cudaMemcpyAsync(p.rock_rad + r0, s->rock_radii, rn * 8, cudaMemcpyHostToDevice, st));
+        if (s->rock_weights) CK(cudaMemcpyAsync(p.rock_w + r0, s->rock_weights, rn * 8, cudaMemcpyHostToDevice, st));
+        ants::k_rock_grid_build<<<n_envs, 128, 0, st>>>(p, env0);
         TRY(check_launch("k_rock_grid_build"));
     }
     if (p.owner) CK(cudaMemsetAsync(p.owner, 0, (size_t)p.E * p.plane * sizeof(uint32_t), st));
@@ -1178,8 +1222,12 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     if (s->food) b->pack_disabled = 0;
     // queued anthill absorbs refer to the old food field / disc: dropped only when one of them is replaced (the
     // sweep of the next update takes whatever lies in the disc, Q10)
-    if (s->food || s->anthill_xyr)
-        CK(cudaMemsetAsync(p.absorb_count, 0, (size_t)(b->fused && p.E > 2 ? p.E : 2) * sizeof(uint32_t), st));
+    if (s->food || s->anthill_xyr) {
+        if (b->fused) CK(cudaMemsetAsync(p.absorb_count + env0, 0, (size_t)n_envs * sizeof(uint32_t), st));
+        else if (whole) CK(cudaMemsetAsync(p.absorb_count, 0, 2 * sizeof(uint32_t), st));
+        // (flat kernels, partial import: the batch-wide queue is kept; its cells are absorbed by the next update, which
+        //  is what the sweep of that update would do to them anyway)
+    }
     if (s->x || s->y) b->wall_flags_valid = 0;
     b->owner_phase = 0;
     // batch-wide scalars: only when the caller provides them (0 / negative = leave as they are)
@@ -1188,6 +1236,11 @@ int ants_import_state(AntsBatch *b, const AntsHostState *s) {
     if (s->act_bool >= 0) b->act_bool = s->act_bool ? 1 : 0;
     CK(cudaStreamSynchronize(st));   // host temporaries above must outlive the copies
     return ANTS_OK;
+}
+
+int ants_import_state(AntsBatch *b, const AntsHostState *s) {
+    if (!b) return fail(ANTS_E_ARG, "null argument");
+    return ants_import_env_state(b, 0, b->p.E, s);
 }
 
 int ants_export_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, AntsHostState *s) {
@@ -1478,6 +1531,7 @@ int ants_get_stats(AntsBatch *b, AntsStats *out) {
         b->stats.active_tiles = b->stats.total_tiles;
     }
     b->stats.device_bytes = b->device_bytes;
+    b->stats.e2e_dense_permille = (int64_t)(b->dense_frac * 1000.0 + 0.5);
     *out = b->stats;
     return ANTS_OK;
 }

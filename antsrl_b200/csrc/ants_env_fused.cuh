@@ -76,6 +76,79 @@ __device__ __forceinline__ void env_absorb_cell(const Params &p, int e, int cell
 
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
+// Heavy or rare pieces of the per-ant work are kept out of line: the kernel body is unrolled over the ants of a thread,
+// and inlining them four times made it 12 000 instructions (ncu: 2.5 stall cycles per instruction waiting for the
+// instruction cache).
+__device__ __noinline__ double env_wrap(double v, double n) { return pymod_near(v, n); }
+__device__ __noinline__ void env_sincos(double t, double *s, double *c) { sincos(t, s, c); }
+__device__ __noinline__ double env_noise(const Params &p, int e, uint32_t step_id, int ant) {
+    return philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)ant);
+}
+// the owner of a cell adds its activations and clamps (ants.py:98-100, pheromone.py:36-41)
+__device__ __noinline__ void env_deposit(const Params &p, uint8_t *rec, int64_t i, uint32_t now, uint32_t now_abs) {
+    for (int q = 0; q < p.P; ++q) {
+        const double av = p.act[(int64_t)q * p.EN + i];
+        if (av == 0.0) continue;
+        double v = phero_value(p, rec, q, now, now_abs) + av;                           // (evaporated up to this update)
+        if (p.has_max_val) v = fmin(v, p.phero_max_val);
+        phero_store(p, rec, q, v, now, now_abs);
+    }
+}
+// the owner writes the food of its cell (ants.py:116); returns what is stored (f32 in compact records)
+__device__ __noinline__ double env_food_commit(const Params &p, uint8_t *fr, double v) {
+    st_food(p, fr, v);
+    return ld_food(p, fr);
+}
+__device__ __noinline__ double env_ld_food(const Params &p, const uint8_t *r) { return ld_food(p, r); }
+
+// the rock-grid entries follow a rock that moved (clear the old box, set the new one); a whole warp calls this
+__device__ __noinline__ void env_move_rock_grid(const Params &p, int e, int r, double cx, double cy, double nx, double ny, double rad, int lane) {
+    rock_grid_mark_warp(p, e, r, cx, cy, rad, false, lane);
+    __syncwarp();                                      // orders the clears before the sets (the boxes overlap)
+    rock_grid_mark_warp(p, e, r, nx, ny, rad, true, lane);
+}
+// rock-grid word of an ant position (positions of the step loop lie in [0, W] x [0, H]: ants.py:69-71; W itself is
+// quirk Q14 and maps to cell 0 like everywhere else)
+__device__ __forceinline__ const unsigned long long *env_grid_word(const Params &p, int e, double x, double y) {
+    int gx = cell_of(x, p.W) >> kGridShift, gy = cell_of(y, p.H) >> kGridShift;
+    gx = min(max(gx, 0), p.grid_w - 1); gy = min(max(gy, 0), p.grid_h - 1);
+    return p.rock_grid + ((int64_t)e * p.grid_w + gx) * p.grid_h + gy;
+}
+
+// which of the candidate rocks does an ant standing at (x, y) push (circle_obstacles.py:35-37)?  Out of line: one copy of
+// the f64 square roots instead of one per unrolled ant.
+__device__ __noinline__ void env_touch_rocks(const Params &p, int e, double x, double y, unsigned long long rm, uint32_t *touch_row,
+                                             uint32_t chunk_bit) {
+    const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+    const double *rr = p.rock_rad + (int64_t)e * p.R;
+    while (rm) {
+        const int r = __ffsll((long long)rm) - 1;
+        rm &= rm - 1;
+        const double vx = rc[2 * r] - x, vy = rc[2 * r + 1] - y;
+        if (!(sqrt(vx * vx + vy * vy) > rr[r])) atomicOr(&touch_row[r], chunk_bit);
+    }
+}
+// rocks push the ant (circle_obstacles.py:53-58): candidates in rock order like np.sum(axis=1); the centres were just
+// rewritten by this block, so they are read past the L1
+__device__ __noinline__ void env_push_by_rocks(const Params &p, int e, unsigned long long rm, double *x, double *y) {
+    const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+    const double *rr = p.rock_rad + (int64_t)e * p.R;
+    double sx = 0.0, sy = 0.0;
+    while (rm) {
+        const int r = __ffsll((long long)rm) - 1;
+        rm &= rm - 1;
+        const double vx = __ldcg(rc + 2 * r) - *x, vy = __ldcg(rc + 2 * r + 1) - *y;
+        const double d = sqrt(vx * vx + vy * vy);
+        const double rad = rr[r];
+        if (!(d > rad)) {
+            const double fac = 1.0 - rad / (d + 0.001);
+            sx += vx * fac; sy += vy * fac;
+        }
+    }
+    *x = env_wrap(*x + sx, (double)p.W);                               // translate_ants -> warp_xy
+    *y = env_wrap(*y + sy, (double)p.H);
+}
+
 template <bool UPDATE, bool MOVE, int APT>
 __global__ void __launch_bounds__(kEnvThreads, 4)
 k_env(const __grid_constant__ Params p, const EnvArgs a) {
@@ -97,6 +170,17 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     const int W = p.W, H = p.H;
     const double Wd = (double)W, Hd = (double)H;
 
+    // The mandible rule (RL_api.py:180-184, quirk Q5) walks perceived_objects: food ORs (food > 0) into the mandibles,
+    // the anthill ANDs (not in hill).  Both are idempotent, so only the last rule and whether the other kind precedes it
+    // matter: 0 none, 1 OR, 2 AND, 3 (m | f) & !h, 4 (m & !h) | f.
+    int rule_mode = 0;
+    if (MOVE) {
+        bool seen_or = false, seen_and = false;
+        for (int q = 0; q < p.rule_n; ++q) {
+            if (p.rule_op[q] == 0) { seen_or = true; rule_mode = seen_and ? 4 : 1; }
+            else { seen_and = true; rule_mode = seen_or ? 3 : 2; }
+        }
+    }
     for (int k = tid; k < 2 * CAP; k += kEnvThreads) { hkeys[k] = 0u; hvals[k] = 0u; }
     if (UPDATE && p.R > 0)
         for (int k = tid; k < n_env * p.R; k += kEnvThreads) touch[k] = 0u;
@@ -105,6 +189,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     // together, with the index of an idle slot clamped to the block's last ant: the kernel lives on memory-level
     // parallelism (two random DRAM sectors per ant: the cell it deposits on and the cell it moves to).
     double th[APT];
+    int newcell[APT];              // MOVE: the cell the ant moves to
     int cell[APT];                 // UPDATE: the cell the ant ends the update in; MOVE alone: its prev cell
     int el[APT];                   // environment within the block
     int lac[APT];                  // the ant's slot in the block (clamped)
@@ -114,9 +199,14 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         const int la = tid + k * kEnvThreads;
         valid[k] = la < n_loc;
         lac[k] = valid[k] ? la : (n_loc - 1);
-        el[k] = lac[k] / p.N;
-        th[k] = 0.0; cell[k] = 0;
+        el[k] = a.group == 1 ? 0 : lac[k] / p.N;
+        th[k] = 0.0; cell[k] = 0; newcell[k] = 0;
     }
+    // record of cell c of the block's env g: (g * plane + c) fits 32 bits (the hash keys rely on the same bound)
+    uint8_t *const cells0 = p.cells + (((int64_t)env0 * p.plane) << p.rec_shift);
+    const uint32_t plane32 = (uint32_t)p.plane;
+    const int rshift = p.rec_shift;
+    auto rec_of = [&](int g, int c) -> uint8_t * { return cells0 + ((size_t)((uint32_t)g * plane32 + (uint32_t)c) << rshift); };
 
     if (UPDATE) {
         // ---- Anthill.update (anthill.py:41-46) for the cells queued by the previous move: nothing else in the update
@@ -151,11 +241,12 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             const int64_t i = i0 + lac[k];
             x[k] = p.x[i]; y[k] = p.y[i]; th[k] = p.theta[i];
             in_wall[k] = a.use_flag ? p.wall_hit[i] != 0 : false;
+            if (p.P > 0) { prefetch_l2(p.act + i); if (p.P > 1) prefetch_l2(p.act + p.EN + i); }   // read by the depositing owners
         }
         if (!a.use_flag) {
 #pragma unroll
             for (int k = 0; k < APT; ++k)
-                in_wall[k] = ld_wall(p, rec_at(p, env0 + el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));
+                in_wall[k] = ld_wall(p, rec_of(el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));
         }
         unsigned long long rm[APT];
 #pragma unroll
@@ -164,26 +255,18 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             const int e = env0 + el[k], ant = lac[k] - el[k] * p.N;
             if (in_wall[k]) {
                 x[k] = p.prev_x[i]; y[k] = p.prev_y[i];
-                const double u = a.noise ? a.noise[i] : philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), a.step_id, (uint32_t)ant);
+                const double u = a.noise ? a.noise[i] : env_noise(p, e, a.step_id, ant);
                 th[k] += u - 0.5;                                      // not re-wrapped (Q3)
             }
-            rm[k] = p.R > 0 ? rock_candidates(p, e, x[k], y[k]) : 0ull;
+            rm[k] = p.R > 0 ? *env_grid_word(p, e, x[k], y[k]) : 0ull;
         }
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
             if (!valid[k]) continue;
             xs[lac[k]] = x[k]; ys[lac[k]] = y[k];
             if (rm[k]) {
-                const int e = env0 + el[k], ant = lac[k] - el[k] * p.N;
-                const double *rc = p.rock_c + (int64_t)e * p.R * 2;
-                const double *rr = p.rock_rad + (int64_t)e * p.R;
-                unsigned long long m = rm[k];
-                while (m) {
-                    const int r = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const double vx = rc[2 * r] - x[k], vy = rc[2 * r + 1] - y[k];
-                    if (!(sqrt(vx * vx + vy * vy) > rr[r])) atomicOr(&touch[el[k] * p.R + r], 1u << (ant / Gc));
-                }
+                const int ant = lac[k] - el[k] * p.N;
+                env_touch_rocks(p, env0 + el[k], x[k], y[k], rm[k], touch + el[k] * p.R, 1u << (ant / Gc));
             }
         }
         if (p.R > 0) {
@@ -227,48 +310,28 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 }
                 const double nx = cx - sx / wt, ny = cy - sy / wt;
                 if (lane == 0) { rc[2 * r] = nx; rc[2 * r + 1] = ny; }
-                if (nx != cx || ny != cy) {
-                    rock_grid_mark_warp(p, e, r, cx, cy, rad, false, lane);
-                    __syncwarp();
-                    rock_grid_mark_warp(p, e, r, nx, ny, rad, true, lane);
-                }
+                if (nx != cx || ny != cy) env_move_rock_grid(p, e, r, cx, cy, nx, ny, rad, lane);
             }
             __threadfence_block();
             __syncthreads();
             // ---- rocks push ants (circle_obstacles.py:53-58).  The grid and the centres were just rewritten by this
             //      block: read them past the L1.
 #pragma unroll
-            for (int k = 0; k < APT; ++k) {
-                const int gx = cell_of(pymod_near(x[k], Wd), W) >> kGridShift, gy = cell_of(pymod_near(y[k], Hd), H) >> kGridShift;
-                rm[k] = __ldcg(p.rock_grid + ((int64_t)(env0 + el[k]) * p.grid_w + gx) * p.grid_h + gy);
-            }
+            for (int k = 0; k < APT; ++k) rm[k] = __ldcg(env_grid_word(p, env0 + el[k], x[k], y[k]));
 #pragma unroll
-            for (int k = 0; k < APT; ++k) {
-                if (!rm[k]) continue;
-                const int e = env0 + el[k];
-                const double *rc = p.rock_c + (int64_t)e * p.R * 2;
-                const double *rr = p.rock_rad + (int64_t)e * p.R;
-                double sx = 0.0, sy = 0.0;
-                unsigned long long m = rm[k];
-                while (m) {                                            // candidates in rock order like np.sum(axis=1)
-                    const int r = __ffsll((long long)m) - 1;
-                    m &= m - 1;
-                    const double vx = __ldcg(rc + 2 * r) - x[k], vy = __ldcg(rc + 2 * r + 1) - y[k];
-                    const double d = sqrt(vx * vx + vy * vy);
-                    const double rad = rr[r];
-                    if (!(d > rad)) {
-                        const double fac = 1.0 - rad / (d + 0.001);
-                        sx += vx * fac; sy += vy * fac;
-                    }
-                }
-                x[k] = pymod_near(x[k] + sx, Wd);                      // translate_ants -> warp_xy
-                y[k] = pymod_near(y[k] + sy, Hd);
-            }
+            for (int k = 0; k < APT; ++k)
+                if (rm[k]) env_push_by_rocks(p, env0 + el[k], rm[k], &x[k], &y[k]);
         }
         // ---- prev snapshot and reward_state decay (ants.py:124,130), ownership of the deposit cell (pheromone.py:39, Q1)
         uint8_t rs[APT];
+        double hold0[APT];
+        int8_t rot0[APT];
 #pragma unroll
-        for (int k = 0; k < APT; ++k) rs[k] = p.reward_state[i0 + lac[k]];
+        for (int k = 0; k < APT; ++k) {
+            const int64_t i = i0 + lac[k];
+            rs[k] = p.reward_state[i];
+            if (MOVE) { hold0[k] = p.holding[i]; rot0[k] = a.rot != nullptr ? a.rot[i] : (int8_t)0; }
+        }
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
             if (!valid[k]) continue;
@@ -280,8 +343,25 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             p.reward_state[i] = (uint8_t)((double)rs[k] * 0.9);        // ants.py:130
             cell[k] = cidx(p, cell_of(x[k], W), cell_of(y[k], H));
             if (p.P > 0 || MOVE) {
-                prefetch_l2(rec_at(p, env0 + el[k], cell[k]));        // consumed after the barrier
+                prefetch_l2(rec_of(el[k], cell[k]));                   // consumed after the barrier
                 env_hash_max(hkeys, hvals, HMASK, (uint32_t)(el[k] * p.plane + cell[k]) + 1u, (uint32_t)ant + 1u);
+            }
+            if (MOVE) {
+                // The move of the coming step (ants.py:62-80), ahead of the mandible rule: heading and rotation do not
+                // depend on the food, the speed only through the holding of an ant that picks up or drops in this very
+                // step -- those few are moved again below.  This takes the record of the NEW cell (a second random
+                // DRAM sector) out of the dependency chain behind the record of the current one.
+                double t = th[k];
+                if (a.rot != nullptr) t = env_wrap(t + (double)rot0[k] * p.max_rot_speed, 6.283185307179586);    // ants.py:62-67
+                double fwd = (1.0 * p.max_speed) * (1.0 - hold0[k] * p.csr);            // RL_api.py:194
+                if (fwd < 0.0) fwd *= p.bsr;                                            // RL_api.py:195
+                double sn, cs;
+                env_sincos(t, &sn, &cs);
+                const double x1 = env_wrap(x[k] + cs * fwd, Wd);                        // ants.py:69-80
+                const double y1 = env_wrap(y[k] + sn * fwd, Hd);
+                p.x[i] = x1; p.y[i] = y1; p.theta[i] = t;
+                newcell[k] = cidx(p, cell_of(x1, W), cell_of(y1, H));
+                prefetch_l2(rec_of(el[k], newcell[k]));
             }
         }
         __syncthreads();
@@ -290,9 +370,8 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     // ---- MOVE alone: the mandible rule reads the food of the PREV cell (RL_api.py:178); its winner is found here
     double fd[APT];
     int flags[APT];                // bit 0: this ant owns its cell; bit 1: delta != 0; bit 2: the prev cell lies in the hill
-    int newcell[APT];
 #pragma unroll
-    for (int k = 0; k < APT; ++k) { fd[k] = 0.0; flags[k] = 0; newcell[k] = 0; }
+    for (int k = 0; k < APT; ++k) { fd[k] = 0.0; flags[k] = 0; }
     if (MOVE && !UPDATE) {
         double px[APT], py[APT];
 #pragma unroll
@@ -304,7 +383,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
             cell[k] = cidx(p, cell_of(px[k], W), cell_of(py[k], H));
-            fd[k] = ld_food(p, rec_at(p, env0 + el[k], cell[k]));
+            fd[k] = env_ld_food(p, rec_of(el[k], cell[k]));
         }
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
@@ -328,39 +407,29 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         for (int k = 0; k < APT; ++k) {
             const int64_t i = i0 + lac[k];
             hold[k] = p.holding[i]; mand[k] = p.mandibles[i];
-            rot[k] = a.rot != nullptr ? a.rot[i] : (int8_t)0;
+            rot[k] = (!UPDATE && a.rot != nullptr) ? a.rot[i] : (int8_t)0;
         }
     }
     if (UPDATE && MOVE) {
 #pragma unroll
-        for (int k = 0; k < APT; ++k) fd[k] = ld_food(p, rec_at(p, env0 + el[k], cell[k]));   // prev cell == this cell after an update
+        for (int k = 0; k < APT; ++k) fd[k] = env_ld_food(p, rec_of(el[k], cell[k]));   // prev cell == this cell after an update
     }
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         if (!valid[k]) continue;
         const int64_t i = i0 + lac[k];
         const int e = env0 + el[k], ant = lac[k] - el[k] * p.N;
-        uint8_t *rec = rec_at(p, e, cell[k]);
+        uint8_t *rec = rec_of(el[k], cell[k]);
         const bool own = env_hash_get(hkeys, hvals, HMASK, (uint32_t)(el[k] * p.plane + cell[k]) + 1u) == (uint32_t)ant + 1u;
-        if (UPDATE && own && p.P > 0) {
-            for (int q = 0; q < p.P; ++q) {
-                const double av = p.act[(int64_t)q * p.EN + i];
-                if (av == 0.0) continue;
-                double v = phero_value(p, rec, q, a.now, a.now_abs) + av;               // (evaporated up to this update)
-                if (p.has_max_val) v = fmin(v, p.phero_max_val);
-                phero_store(p, rec, q, v, a.now, a.now_abs);
-            }
-        }
+        if (UPDATE && own && p.P > 0) env_deposit(p, rec, i, a.now, a.now_abs);
         if (MOVE) {
             const double x0 = xs[lac[k]], y0 = ys[lac[k]];
             const bool hill = in_hill(p.hill + 4 * e, cell_of(x0, W), cell_of(y0, H));  // RL_api.py:184
             double h = hold[k];
             const int m_old = mand[k] != 0;
-            int m = m_old;
-            for (int q = 0; q < p.rule_n; ++q) {                                        // RL_api.py:180-184 (Q5)
-                if (p.rule_op[q] == 0) m |= (fd[k] > 0.0) ? 1 : 0;
-                else m &= hill ? 0 : 1;
-            }
+            const int fpos = fd[k] > 0.0 ? 1 : 0, out = hill ? 0 : 1;                   // RL_api.py:180-184 (Q5)
+            const int m = rule_mode == 0 ? m_old : rule_mode == 1 ? (m_old | fpos) : rule_mode == 2 ? (m_old & out)
+                          : rule_mode == 3 ? ((m_old | fpos) & out) : ((m_old & out) | fpos);
             const bool closing = m && !m_old, opening = !m && m_old;                    // ants.py:103-104
             const double taken = closing ? fmin(p.max_hold, fmax(0.0, fd[k])) : 0.0;    // ants.py:111
             const double dropped = opening ? h : 0.0;                                   // ants.py:114
@@ -371,17 +440,21 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             // (after an update the prev cell IS the current cell: its hill bit decides whether dropped food is queued)
             flags[k] = (own ? 1 : 0) | (delta != 0.0 ? 2 : 0) | ((UPDATE && hill) ? 4 : 0);
             fd[k] = fd[k] + delta;                                                      // what the owner will write (ants.py:116)
-            double t = th[k];
-            if (a.rot != nullptr) t = pymod_near(t + (double)rot[k] * p.max_rot_speed, 6.283185307179586);   // ants.py:62-67
-            double fwd = (1.0 * p.max_speed) * (1.0 - h * p.csr);                       // RL_api.py:194
-            if (fwd < 0.0) fwd *= p.bsr;                                                // RL_api.py:195
-            double sn, cs;
-            sincos(t, &sn, &cs);
-            const double x = pymod_near(x0 + cs * fwd, Wd);                             // ants.py:69-80
-            const double y = pymod_near(y0 + sn * fwd, Hd);
-            p.x[i] = x; p.y[i] = y; p.theta[i] = t;
-            newcell[k] = cidx(p, cell_of(x, W), cell_of(y, H));
-            prefetch_l2(rec_at(p, e, newcell[k]));
+            if (!UPDATE || h != hold[k]) {
+                // MOVE alone: the move itself.  After an update it already ran with the old holding (above): only an
+                // ant whose holding just changed moves again, with the speed that goes with it
+                double t = UPDATE ? p.theta[i] : th[k];
+                if (!UPDATE && a.rot != nullptr) t = env_wrap(t + (double)rot[k] * p.max_rot_speed, 6.283185307179586);   // ants.py:62-67
+                double fwd = (1.0 * p.max_speed) * (1.0 - h * p.csr);                   // RL_api.py:194
+                if (fwd < 0.0) fwd *= p.bsr;                                            // RL_api.py:195
+                double sn, cs;
+                env_sincos(t, &sn, &cs);
+                const double x = env_wrap(x0 + cs * fwd, Wd);                           // ants.py:69-80
+                const double y = env_wrap(y0 + sn * fwd, Hd);
+                p.x[i] = x; p.y[i] = y; p.theta[i] = t;
+                newcell[k] = cidx(p, cell_of(x, W), cell_of(y, H));
+                prefetch_l2(rec_of(el[k], newcell[k]));
+            }
         }
     }
     if (!MOVE) return;
@@ -395,9 +468,8 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         const int64_t i = i0 + lac[k];
         const int e = env0 + el[k];
         if ((flags[k] & 3) == 3) {
-            uint8_t *fr = rec_at(p, e, cell[k]);
-            st_food(p, fr, fd[k]);
-            const double nv = ld_food(p, fr);                          // as stored (f32 in compact records)
+            uint8_t *fr = rec_of(el[k], cell[k]);
+            const double nv = env_food_commit(p, fr, fd[k]);
             bool queue = nv != 0.0;
             if (queue) {
                 if (UPDATE) queue = (flags[k] & 4) != 0;
@@ -421,7 +493,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         if (!valid[k]) continue;
-        uint8_t *orec = rec_at(p, env0 + el[k], newcell[k]);
+        uint8_t *orec = rec_of(el[k], newcell[k]);
         p.wall_hit[i0 + lac[k]] = ld_wall(p, orec) ? 1 : 0;            // for Walls.update of the coming update
         st_occ(p, orec, a.occ_gen);
     }

@@ -5,6 +5,7 @@
 // against 78 GB/s with regular ones on the 16-core B200 host).
 #include "ants_host_unpack.h"
 
+#include <stdlib.h>
 #include <string.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -52,6 +53,7 @@ void ants_unpack_plan_finish(AntsUnpackPlan *p) {
     p->simd = 0;
 #if defined(__x86_64__)
     if (p->C <= 8 && __builtin_cpu_supports("avx2")) p->simd = 1;
+    if (p->simd && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && !getenv("ANTS_NO_AVX512")) p->simd = 2;
 #endif
 }
 
@@ -120,8 +122,60 @@ __attribute__((target("avx2"))) static void unpack_avx2(const AntsUnpackPlan *p,
 }
 #endif
 
+#if defined(__x86_64__)
+// AVX-512 (F + VL): a sample is stored through a lane mask (no spill into the next sample, no repair list) and the
+// staged ants leave in 64-byte non-temporal stores
+__attribute__((target("avx512f,avx512vl,avx2"))) static void stream_out512(float *dst, const float *src, size_t bytes) {
+    uint8_t *d = (uint8_t *)dst;
+    const uint8_t *s = (const uint8_t *)src;
+    size_t head = ((uintptr_t)d & 63) ? 64 - ((uintptr_t)d & 63) : 0;
+    if (head > bytes) head = bytes;
+    memcpy(d, s, head);
+    d += head; s += head; bytes -= head;
+    const size_t nv = bytes / 64;
+    for (size_t k = 0; k < nv; ++k)
+        _mm512_stream_si512((__m512i *)d + k, _mm512_loadu_si512((const __m512i *)s + k));
+    memcpy(d + nv * 64, s + nv * 64, bytes - nv * 64);
+}
+
+__attribute__((target("avx512f,avx512vl,avx2"))) static void unpack_avx512(const AntsUnpackPlan *p, const uint8_t *packed, int64_t n_ants,
+                                                                        float *out) {
+    const int n = p->S2 * p->C, C = p->C, V = p->V;
+    constexpr int B = 8;
+    alignas(64) float buf[B * 228 * 8 + 16];
+    int off[228];
+    for (int v = 0; v < V; ++v) off[v] = p->vis[v] * C;
+    for (int b = 0; b < B; ++b) memcpy(buf + b * n, p->templ, (size_t)n * sizeof(float));
+    const __m256i perm = _mm256_loadu_si256((const __m256i *)p->perm);
+    const __m128i foodmask = _mm_set_epi32(0, 0xFFFF, 0, 0);
+    const __mmask8 lanes = (__mmask8)((1u << C) - 1u);
+    for (int64_t a0 = 0; a0 < n_ants; a0 += B) {
+        const int nb = (int)(n_ants - a0 < B ? n_ants - a0 : B);
+        for (int b = 0; b < nb; ++b) {
+            float *o = buf + b * n;
+            const uint8_t *rec = packed + (a0 + b) * V * 12;
+            for (int v = 0; v < V; ++v, rec += 12) {
+                const __m128i x = _mm_loadu_si128((const __m128i *)rec);
+                const __m128 foodf = _mm_cvtepi32_ps(_mm_and_si128(x, foodmask));
+                const __m128 vals = _mm_blend_ps(_mm_castsi128_ps(x), foodf, 12);
+                const __m256 spread = _mm256_permutevar8x32_ps(_mm256_castps128_ps256(vals), perm);
+                const __m256 lut = _mm256_loadu_ps(p->lut[rec[10]]);
+                _mm256_mask_storeu_ps(o + off[v], lanes, _mm256_or_ps(lut, spread));
+            }
+        }
+        stream_out512(out + a0 * n, buf, (size_t)nb * n * sizeof(float));
+    }
+    _mm_sfence();
+}
+#endif
+
 void ants_unpack_range(const AntsUnpackPlan *p, const uint8_t *packed, int64_t n_ants, float *out) {
 #if defined(__x86_64__)
+    if (p->simd == 2 && n_ants > 1) {
+        unpack_avx512(p, packed, n_ants - 1, out);
+        unpack_scalar(p, packed + (n_ants - 1) * (int64_t)p->V * 12, 1, out + (n_ants - 1) * (int64_t)p->S2 * p->C);
+        return;
+    }
     if (p->simd && n_ants > 1) {
         // (the vector path loads 16 bytes per 12-byte sample: the last ant goes through the scalar path so that nothing
         //  past the caller's buffer is read)

@@ -1224,13 +1224,14 @@ k_diffuse_tma(Params p, const __grid_constant__ CUtensorMap tmap, int src_z0, in
     }
 }
 // after an import: the sign bit of every plane value = the wall bit of its cell record
-__global__ void k_plane_walls(Params p) {
-    const int64_t n = (int64_t)p.E * p.W * p.H;
+__global__ void k_plane_walls(Params p, int env0, int n_env) {
+    const int64_t n = (int64_t)n_env * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
+        e += env0;
         const bool wall = ld_wall(p, rec_at(p, (int)e, cidx(p, x, y)));
         for (int k = 0; k < p.P; ++k) {
             double *pv = plane_at(p, (int)e, k, x, y);
@@ -1308,14 +1309,15 @@ __global__ void __launch_bounds__(256) k_absorb_sweep(Params p) {
 // ------------------------------------------------------------------------------------------------ import / export helpers
 // dense host-layout arrays <-> record fields.  `dense` is [E][planes_per_env][W][H]; field = plane `k` of them.
 __global__ void k_pack_f64(Params p, const double *__restrict__ dense, int planes_per_env, int k, int byte_off,
-                           int phero_k, uint32_t now, uint32_t now_abs) {
-    const int64_t n = (int64_t)p.E * p.W * p.H;
+                           int phero_k, uint32_t now, uint32_t now_abs, int env0, int n_env) {
+    const int64_t n = (int64_t)n_env * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
-        int64_t e = ex / p.W;
+        int64_t e = ex / p.W;                                                  // position in the imported window
         int x = (int)(ex - e * p.W);
         double v = dense[((e * planes_per_env + k) * p.W + x) * p.H + y];
+        e += env0;
         uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
         if (phero_k >= 0 && p.diffuse) {
             *plane_at(p, (int)e, phero_k, x, y) = v;                           // (k_plane_walls sets the sign afterwards)
@@ -1344,14 +1346,14 @@ __global__ void k_unpack_f64(Params p, double *__restrict__ dense, int planes_pe
     }
 }
 // what: 0 = walls (stored as 0/1), 1 = explored (meta low half: 0xFFFF = explored long ago; occupancy cleared)
-__global__ void k_pack_u8(Params p, const uint8_t *__restrict__ dense, int what) {
-    const int64_t n = (int64_t)p.E * p.W * p.H;
+__global__ void k_pack_u8(Params p, const uint8_t *__restrict__ dense, int what, int env0, int n_env) {
+    const int64_t n = (int64_t)n_env * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
-        uint8_t *r = rec_at(p, (int)e, cidx(p, x, y));
+        uint8_t *r = rec_at(p, env0 + (int)e, cidx(p, x, y));
         if (what == 0) st_wall(p, r, dense[j] != 0);
         else { st_explored(p, r, dense[j] ? p.explored_old : 0u); st_occ(p, r, 0u); }
     }
@@ -1368,13 +1370,14 @@ __global__ void k_unpack_u8(Params p, uint8_t *__restrict__ dense, int what, int
     }
 }
 // the anthill disc as a bit of every cell record (anthill.py:31-33), after the anthill was imported
-__global__ void k_hill_mark(Params p) {
-    const int64_t n = (int64_t)p.E * p.W * p.H;
+__global__ void k_hill_mark(Params p, int env0, int n_env) {
+    const int64_t n = (int64_t)n_env * p.W * p.H;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         int64_t ex = j / p.H;
         int y = (int)(j - ex * p.H);
         int64_t e = ex / p.W;
         int x = (int)(ex - e * p.W);
+        e += env0;
         st_hill(p, rec_at(p, (int)e, cidx(p, x, y)), in_hill(p.hill + 4 * e, x, y));
     }
 }
@@ -1436,8 +1439,8 @@ __global__ void k_lazy_fold(Params p, uint32_t now, uint32_t now_abs, int unbox)
         }
     }
 }
-__global__ void k_rock_grid_build(Params p) {          // one block per env (after import)
-    const int e = blockIdx.x;
+__global__ void k_rock_grid_build(Params p, int env0) {   // one block per imported env
+    const int e = env0 + blockIdx.x;
     const int gcells = p.grid_w * p.grid_h;
     unsigned long long *g = p.rock_grid + (int64_t)e * gcells;
     for (int k = threadIdx.x; k < gcells; k += blockDim.x) g[k] = 0ull;
@@ -1446,11 +1449,12 @@ __global__ void k_rock_grid_build(Params p) {          // one block per env (aft
         rock_grid_mark(p, e, r, p.rock_c[((int64_t)e * p.R + r) * 2], p.rock_c[((int64_t)e * p.R + r) * 2 + 1],
                        p.rock_rad[(int64_t)e * p.R + r]);
 }
-__global__ void k_tiles_from_phero(Params p) {
+__global__ void k_tiles_from_phero(Params p, int env0, int n_env) {
     // mark every tile that holds a non-zero pheromone cell (after import)
     const int64_t tiles_per_env = (int64_t)p.tiles_x * p.tiles_y;
-    const int64_t ntiles = (int64_t)p.E * tiles_per_env;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ntiles = (int64_t)n_env * tiles_per_env;
+    for (int64_t tw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tw < ntiles; tw += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = tw + (int64_t)env0 * tiles_per_env;
         int e = (int)(t / tiles_per_env);
         int tin = (int)(t - (int64_t)e * tiles_per_env);
         int tx = tin / p.tiles_y, ty = tin - tx * p.tiles_y;

@@ -43,6 +43,10 @@ struct RowPrep {                 // 72 bytes per ant, shared memory (phase A -> 
 __device__ __forceinline__ int wrap1(int v, int n) {
     return (int)min(min((unsigned)v, (unsigned)(v + n)), (unsigned)(v - n));
 }
+// np.round(v).astype(int) (half to even, RL_api.py:117) for |v| < 2^31 without the quarter-rate F2I.F64: adding
+// 1.5 * 2^52 leaves the rounded integer (two's complement) in the low word of the sum -- the add itself rounds to
+// nearest-even, exactly like rint()
+__device__ __forceinline__ int round_half_even(double v) { return __double2loint(v + 6755399441055744.0); }
 __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2 (2^-22 relative); arguments here are in [-15, 0]
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -185,7 +189,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     // ---- phase B: a lane processes one window row of one ant (its S columns); two ways of handing out the rows
     const int warp = tid >> 5, lane = tid & 31;
     const int W = p.W, H = p.H;
-    const int nby64 = p.nby << 6;
+    const int nby64m = (p.nby << 6) - 64;
     // ages that still show a value: the table's last entry is the 0 the reference's < 0.01 cut produced
     const uint32_t tab_len = p.tab_len > 0 ? (uint32_t)p.tab_len - 1u : 0u;
     const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
@@ -195,6 +199,9 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const bool any_plain = !eager && *p.plain_flag != 0u;           // lazy field: plain (non-boxed) values may exist
     // boxed deposit b = box | t: (box | now) - b = now - t = age; zero and plain values give an "age" >= 2^22
     const uint32_t nowb = REC16 ? box32(now_abs) : (REC8 ? now_abs : (now_abs & kBoxMask));
+    // 8-byte records: both 15-bit deposit steps of a cell are aged in one subtraction (bit 15 of each half set in the
+    // minuend: no borrow crosses the halves)
+    const uint32_t nowb2 = ((now_abs & kBox8Mask) | kBox8) * 0x00010001u;
     const uint32_t ogs = obs_gen << 8;
     float *wobs0 = s_obs + warp * kRowsTiles * TILE;
     constexpr bool kLateWait = (UNR >= S);
@@ -221,10 +228,10 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     const double X = p.off_c[j];
                     const double rx = ct * X - stY;
                     const double ry = st * X + ctY;
-                    int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
+                    int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
                     ix = wrap1(ix, W); iy = wrap1(iy, H);
-                    // cidx(): 8 x 8 blocks of 64 records
-                    cell[u] = (uint32_t)((ix >> 3) * nby64 + (ix & 7) * 8 + (iy >> 3) * 56 + iy);
+                    // cidx(): 8 x 8 blocks of 64 records; (x & 7) * 8 = 8 x - 64 (x >> 3), (y >> 3) * 64 + (y & 7) = y + 56 (y >> 3)
+                    cell[u] = (uint32_t)((ix >> 3) * nby64m + ix * 8 + (iy >> 3) * 56 + iy);
                     const uint8_t *rp = cells + ((size_t)cell[u] << SH);
                     if (REC8) {                    // the whole cell in one 64-bit load, four cells per sector
                         const uint2 v8 = *reinterpret_cast<const uint2 *>(rp);
@@ -246,7 +253,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     const double X = p.off_c[j];                           // the same arithmetic as above
                     const double rx = ct * X - stY;
                     const double ry = st * X + ctY;
-                    int ix = __double2int_rn(rx + xf), iy = __double2int_rn(ry + yf);
+                    int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
                     ix = wrap1(ix, W); iy = wrap1(iy, H);
                     // strict sqrt(d2) < r, decided on the squares unless d2 is within 1e-12 of r^2
                     const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
@@ -271,15 +278,16 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     float v5;                      // food as the f32 observation shows it
                     if (REC8) {
                         const uint32_t pk = lo[u].y >> 16;                 // [hill|occ][wall|explored]
-                        const uint32_t c0 = lo[u].x & 0xFFFFu, c1 = lo[u].x >> 16;
                         occupied = (pk & 0x7Fu) == occ_gen;
                         hill = (pk & 0x80u) != 0;
                         wl = (pk & 0x8000u) != 0;
                         fresh = (pk & 0x7F00u) == 0u;
                         seen_now = (pk & 0x7F00u) == ogs;
                         v5 = (float)(lo[u].y & 0xFFFFu);                   // (an escaped amount is patched in below)
-                        age0 = (c0 & kBox8) ? ((nowb - c0) & kBox8Mask) : 0xFFFFFFFFu;
-                        age1 = (c1 & kBox8) ? ((nowb - c1) & kBox8Mask) : 0xFFFFFFFFu;
+                        // per half: age = (now - step) mod 2^15 for a boxed deposit (bit 15 set), >= 2^15 (= expired) else
+                        const uint32_t d2 = nowb2 - (lo[u].x & 0x7FFF7FFFu);
+                        const uint32_t a2 = (d2 & 0x7FFF7FFFu) | (~lo[u].x & 0x80008000u);
+                        age0 = a2 & 0xFFFFu; age1 = a2 >> 16;
                         if (explore_on && fresh) rp[7] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
                     } else if (REC16) {
                         const uint32_t pk = lo[u].w;

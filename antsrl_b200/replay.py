@@ -1,12 +1,17 @@
 """Replay memory that stays in HBM.
 
-Mirror of the reference's `agents/replay_memory.py:6-114` (a ring buffer of float32 tensors: states, agent
-states, actions, rewards, new states, new agent states, dones; `extend` wraps around, `random_access` samples
-without replacement), fed with the DEVICE tensors the batched step loop returns instead of numpy arrays, so an
-on-device policy trains without the (E*N, 7, 7, C) observations ever crossing PCIe.  PyTorch is plumbing here:
-the ring-buffer writes are two slice copies per field on the current stream.
+Mirror of the reference's `agents/replay_memory.py:6-114` (a ring buffer of tensors with the reference's dtypes:
+float32 states / agent states / rewards, integer actions, bool dones; `extend` writes rolling, `random_access`
+samples without replacement), fed with the DEVICE tensors the batched step loop returns instead of numpy arrays, so
+an on-device policy trains without the (E*N, 7, 7, C) observations ever crossing PCIe.  PyTorch is plumbing here:
+the ring-buffer writes are two slice copies per field on the current stream, the sample indices are drawn on the
+device (no host round trip per minibatch).
+
+Pinned against the reference class with identical inputs by tests/test_replay_cpu.py.  One deliberate deviation:
+when a batch crosses the end of the buffer, the reference's recursive call passes the already stacked (n, 2)
+action array where `extend` expects the (rotation, pheromone) pair (replay_memory.py:99-114), so it stores two
+garbled entries and drops the rest of the batch; this class wraps around as the docstring of the reference intends.
 """
-import random
 
 
 class DeviceReplayMemory:
@@ -20,11 +25,11 @@ class DeviceReplayMemory:
         ag = tuple(agent_space)
         self.states = torch.zeros((self.max_len,) + obs, dtype=torch.float32, device=device)       # replay_memory.py:18-24
         self.agent_states = torch.zeros((self.max_len,) + ag, dtype=torch.float32, device=device)
-        self.actions = torch.zeros((self.max_len, int(action_space)), dtype=torch.float32, device=device)
+        self.actions = torch.zeros((self.max_len, int(action_space)), dtype=torch.int64, device=device)
         self.rewards = torch.zeros((self.max_len,), dtype=torch.float32, device=device)
         self.new_states = torch.zeros((self.max_len,) + obs, dtype=torch.float32, device=device)
         self.new_agent_states = torch.zeros((self.max_len,) + ag, dtype=torch.float32, device=device)
-        self.dones = torch.zeros((self.max_len,), dtype=torch.float32, device=device)
+        self.dones = torch.zeros((self.max_len,), dtype=torch.bool, device=device)
 
     def __len__(self):                                             # replay_memory.py:26-27
         return self.fill
@@ -34,7 +39,9 @@ class DeviceReplayMemory:
                 self.new_agent_states[idx], self.dones[idx])
 
     def random_access(self, n):                                    # replay_memory.py:49-58
-        idx = self._t.as_tensor(random.sample(range(len(self)), n), device=self.states.device)
+        if n > len(self):
+            raise ValueError("Sample larger than population")          # what random.sample raises in the reference
+        idx = self._t.randperm(len(self), device=self.states.device)[:n]   # without replacement, drawn on the device
         return self[idx]
 
     def extend(self, states, agent_states, actions, rewards, new_states, new_agent_states, done):
@@ -42,8 +49,8 @@ class DeviceReplayMemory:
         entries are overwritten; `actions` = (rotation, pheromone or None) like the reference."""
         t = self._t
         rot, ph = actions
-        rot = rot.reshape(-1).to(t.float32)
-        ph = t.ones_like(rot) if ph is None else ph.reshape(-1).to(t.float32)        # replay_memory.py:99-102
+        rot = rot.reshape(-1).to(t.int64)
+        ph = t.ones_like(rot) if ph is None else ph.reshape(-1).to(t.int64)          # replay_memory.py:99-102
         act = t.stack((rot, ph), dim=-1)
         n = act.shape[0]
         fields = ((self.states, states.reshape((n,) + self.states.shape[1:])),
@@ -56,7 +63,7 @@ class DeviceReplayMemory:
             add = min(self.max_len - self.head, n - pos)
             for dst, src in fields:
                 dst[self.head:self.head + add].copy_(src[pos:pos + add])
-            self.dones[self.head:self.head + add] = float(done)
+            self.dones[self.head:self.head + add] = bool(done)
             self.fill = max(self.fill, min(self.max_len, self.head + add))
             self.head = (self.head + add) % self.max_len
             pos += add

@@ -489,6 +489,74 @@ def run_reference(args):
     emit(line)
 
 
+# ----------------------------------------------------------------------------------------------- configs[0]: the drop-in
+DROPIN_LOOP = """
+import sys, types, json, time
+for name in ("noise", "matplotlib", "matplotlib.pyplot"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+ROOT, REF, USE_DROPIN, K, W = %(root)r, %(ref)r, %(dropin)r, %(k)d, %(w)d
+if USE_DROPIN:
+    sys.path.insert(0, ROOT)
+    import antsrl_b200
+    sys.path.insert(0, antsrl_b200.dropin_path())
+else:
+    sys.path.insert(0, REF)
+import numpy as np
+from environment.RL_api import RLApi
+from environment.rewards.reward_custom import All_Rewards
+from generator.environment_generator import EnvironmentGenerator
+from generator.map_generators import CirclesGenerator
+api = RLApi(All_Rewards(1, 2, 10, 1, 3), 1, 1, 40 / 180 * np.pi, 0.05, 0.5)               # main.py:42-50
+gen = EnvironmentGenerator(200, 200, 50, 2, 0, CirclesGenerator(20, 5, 10), CirclesGenerator(10, 5, 15), K + W + 1, seed=1000)
+env = gen.generate(api)                                                                  # main.py:79
+api.ants.activate_all_pheromones(np.ones((50, 2)) * 10)                                  # agent.initialize
+np.random.seed(777)
+act = np.random.RandomState(4242)
+obs, agent_state, state = api.observation()                                              # main.py:88
+t0 = None
+for s in range(W + K):
+    if s == W:
+        t0 = time.perf_counter()
+    rot = act.randint(0, 3, 50) - 1                                                      # the agents' exploration branch
+    ph = act.randint(0, 3, 50)
+    obs, agent_state, reward, done = api.step(rot, ph)                                   # main.py:98
+    env.update()                                                                         # main.py:131
+dt = time.perf_counter() - t0
+print(json.dumps({"ms_per_step": dt * 1000 / K, "reward_sum": float(np.sum(reward)), "obs_shape": list(obs.shape)}))
+"""
+
+
+def run_dropin(args):
+    """BASELINE.json configs[0]: the reference's default generated map (200x200, 50 ants) driven for K steps by random
+    actions through main.py's loop -- once over the drop-in packages (environment / generator of antsrl_b200.dropin: ONE
+    environment per handle, numpy in / numpy out, the reference's global-RNG collision noise) and once over the
+    unmodified reference on the host."""
+    from oracle import ref_harness
+    K, W_ = args.steps, max(args.warmup, 3)
+    out = {}
+    for name, use in (("dropin", True), ("reference", False)):
+        if not use and not ref_harness.reference_available():
+            continue
+        code = DROPIN_LOOP % dict(root=ROOT, ref=ref_harness.REFERENCE_ROOT, dropin=use, k=K, w=W_)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=3000)
+        if r.returncode != 0:
+            sys.stderr.write(r.stderr[-3000:])
+            raise SystemExit("bench.py: the %s loop failed" % name)
+        out[name] = json.loads(r.stdout.strip().splitlines()[-1])
+    d = out["dropin"]
+    line = {"metric": "ant-steps/sec (envs x ants x steps)", "value": 50 * 1000.0 / d["ms_per_step"], "unit": "ant-steps/s",
+            "n_gpus": 1, "steps": K, "warmup": W_, "ms_per_step": d["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg1: reference default generated map 200x200, 50 ants, ONE environment through the drop-in "
+                                   "RLApi / Environment classes (main.py's loop, random actions, reference's global-RNG noise)"},
+            "reference_ms_per_step": out.get("reference", {}).get("ms_per_step"),
+            "speedup_vs_reference": (out["reference"]["ms_per_step"] / d["ms_per_step"]) if "reference" in out else None,
+            "note": "one small environment per call is latency bound (launches + the host round trip of every call); the "
+                    "batched path (default workload) is the throughput configuration"}
+    emit(line)
+
+
 def torchrun_command(n_gpus, argv, port=None):
     """The contract's multi-GPU launch of this script: one process per GPU on one node, rendezvous on 127.0.0.1."""
     port = port or (29500 + os.getpid() % 2000)
@@ -520,7 +588,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS) + ["cfg1"],
+                    help="cfg1 = BASELINE configs[0]: ONE default environment through the drop-in classes")
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's)")
     ap.add_argument("--evap", default="lazy", choices=["lazy", "tiles", "dense"])
     ap.add_argument("--record", default="compact8", choices=["compact8", "compact", "f64"],
@@ -541,7 +610,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "ours" and args.gpus != world:
         sys.stderr.write("bench.py: --gpus %d but WORLD_SIZE=%d; running on %d rank(s)\n" % (args.gpus, world, world))
-    if args.impl == "reference":
+    if args.workload == "cfg1":
+        run_dropin(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

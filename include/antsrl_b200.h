@@ -125,6 +125,8 @@ typedef struct AntsStats {
     int64_t total_tiles;
     int64_t food_commits, absorb_events;      /* of the last step / update */
     int64_t device_bytes;                     /* HBM held by the handle */
+    int64_t e2e_dense_permille;               /* ants_step_host: share of the ants (in 1/1000) the DMA engine copies dense while
+                                                 the host threads expand the packed rest (follows the slower side) */
 } AntsStats;
 
 typedef struct AntsBatch AntsBatch;
@@ -147,6 +149,9 @@ int ants_export_state(AntsBatch *b, AntsHostState *s);
  * Environment.save_state() (environment.py:36-40: a visualize_copy of every object, pickled by main.py:139-147 for
  * the viewer) needs for ONE environment of a large batch without moving the other E - 1. */
 int ants_export_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, AntsHostState *s);
+/* ... and the import of such a window: a new map / new ants for the envs [env0, env0 + n_envs) only (main.py:66-79
+ * generates a new environment per episode), or a large batch uploaded in slices.  The scalars stay batch-wide. */
+int ants_import_env_state(AntsBatch *b, int32_t env0, int32_t n_envs, const AntsHostState *s);
 
 /* Ants.activate_all_pheromones, ants.py:86-87.  act: host [E][N][P] */
 int ants_activate_all_pheromones(AntsBatch *b, const double *act, int32_t is_bool);

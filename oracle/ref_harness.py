@@ -5,8 +5,8 @@ Imported by ``tests/`` (golden generation, live-reference checks), by ``bench.py
 modules and drives them through their public API.  Where the reference comes from, in this order:
   1. ``$ANTSRL_REFERENCE`` if set,
   2. the checkout ``/root/reference`` (build container),
-  3. ``oracle/_ref`` -- the same modules byte-compiled from that checkout by the committed recipe
-     ``oracle/build_ref.py`` (sourceless ``.pyc``, git-ignored, shipped to the GPU box with the snapshot).
+  3. ``oracle/_ref/reference.zip`` -- the same modules byte-compiled from that checkout by the committed recipe
+     ``oracle/build_ref.py`` (an archive of sourceless ``.pyc``, git-ignored, shipped to the GPU box with the snapshot).
 
 Shims applied from outside the reference tree:
   1. ``noise`` / ``matplotlib`` stubs (imported at ``utils.py:2-3``, ``anthill.py:2-3``, ``food.py:2-3``,
@@ -24,7 +24,7 @@ import types
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-COMPILED_ROOT = os.path.join(_HERE, "_ref")
+COMPILED_ROOT = os.path.join(_HERE, "_ref", "reference.zip")
 
 
 def _find_reference():
@@ -41,8 +41,14 @@ REFERENCE_ROOT = _find_reference()
 
 def reference_available():
     """True if the reference can be imported here (checkout or the byte-compiled oracle/_ref)."""
-    return (os.path.exists(os.path.join(REFERENCE_ROOT, "environment", "RL_api.py")) or
-            os.path.exists(os.path.join(REFERENCE_ROOT, "environment", "RL_api.pyc")))
+    if os.path.isfile(REFERENCE_ROOT):                  # the byte-compiled archive: usable by the interpreter that wrote it
+        try:
+            import importlib.util, json
+            with open(os.path.join(os.path.dirname(REFERENCE_ROOT), "MANIFEST.json")) as f:
+                return json.load(f).get("magic") == importlib.util.MAGIC_NUMBER.hex()
+        except Exception:
+            return False
+    return os.path.exists(os.path.join(REFERENCE_ROOT, "environment", "RL_api.py"))
 
 
 def reference_kind():

@@ -37,8 +37,9 @@ def test_abi_version_and_struct_sizes(lib):
     assert lib.ants_abi_version() == _cabi.ABI_VERSION
     # layout of the ctypes mirrors must match the C structs (computed by hand from the header)
     assert ctypes.sizeof(_cabi.AntsHostState) == 23 * 8 + 8 + 4 + 4
-    assert ctypes.sizeof(_cabi.AntsStats) == 9 * 8
+    assert ctypes.sizeof(_cabi.AntsStats) == 10 * 8
     assert ctypes.sizeof(_cabi.AntsConfig) % 8 == 0
+    assert ctypes.sizeof(_cabi.AntsPackedLayout) == 5 * 4 + 4 + 8 + 8 * 4 + 2 * 4 + 4 + 228
 
 
 def test_create_fails_loudly_without_gpu(lib):

@@ -508,7 +508,7 @@ def test_device_replay_memory_ring_buffer():
     # slots 0..29 hold entries 50..79 (steps 2 (second half) and 3), slots 30..49 hold entries 30..49 (step 1 tail, step 2 head)
     allobs = torch.cat([l[0] for l in log]); allrot = torch.cat([l[1] for l in log]); allrew = torch.cat([l[2] for l in log])
     assert torch.equal(mem.states[:30], allobs[50:80]) and torch.equal(mem.states[30:], allobs[30:50])
-    assert torch.equal(mem.actions[:30, 0], allrot[50:80].float())
+    assert torch.equal(mem.actions[:30, 0], allrot[50:80].to(torch.int64))
     assert torch.allclose(mem.rewards[30:], allrew[30:50].float())
     s = mem.random_access(16)
     assert s[0].shape == (16, 7, 7, 6) and s[2].shape == (16, 2) and s[0].is_cuda
@@ -645,4 +645,55 @@ def test_rollout_matches_oracle(record, n_rocks, n_ants, n_envs):
         refs.append(r)
     _cmp_outputs((obs, ast, rew), refs, "last step of the rollout")
     compare_state(b.export_state(), oracles, "after the rollout", cfg)
+    b.close()
+
+
+@pytest.mark.parametrize("record,n_rocks", [("compact8", 3), ("f64", 0)])
+def test_windowed_import_resets_some_environments(record, n_rocks):
+    """ants_import_env_state: a batch uploaded in two slices equals the batch uploaded at once, and a new episode for
+    ONE environment in the middle of the others' (main.py:66-79 generates a new map per episode) leaves its neighbours
+    untouched: everything is compared with the oracle after every step."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from parity_util import compare_state
+    from oracle.antsrl_oracle import OracleEnv
+    T = 24
+    scen = [make_scenario(seed=1400 + e, w=56, h=48, n_ants=40, n_rocks=n_rocks, steps=T, n_walls=5, n_food=8) for e in range(5)]
+    cfg = scen[0][0]
+    oracles = [OracleEnv(c, i) for c, i, _ in scen[:4]]
+    b = BatchedAnts(cfg, 4, evap_mode="lazy", record=record)
+    b.import_state(stack_init(cfg, [i for _, i, _ in scen[:3]]), envs=(0, 3))      # two slices
+    b.import_state(stack_init(cfg, [scen[3][1]]), envs=(3, 1))
+    b.observe()
+    for o in oracles:
+        o.observation()
+    src = [0, 1, 2, 3]                       # which scenario's tape drives env e
+    t_env = [0, 0, 0, 0]
+    for t in range(T):
+        if t == 9:
+            # env 2 starts a new episode on scenario 4's map; the timestep stays the batch's (lockstep)
+            fresh = OracleEnv(cfg, scen[4][1])
+            fresh.s["timestep"] = int(oracles[0].s["timestep"])
+            st = stack_init(cfg, [dict(fresh.s)])
+            st.pop("timestep", None); st.pop("rw_alias", None); st.pop("act_bool", None)
+            b.import_state(st, envs=(2, 1))
+            fresh.s["rw_alias"] = oracles[0].s["rw_alias"]       # batch-wide flag (the reward no longer aliases holding)
+            fresh.s["rw_holding_prev"] = fresh.s["holding"].copy()
+            oracles[2] = fresh
+            src[2], t_env[2] = 4, 0
+        rot = np.stack([scen[src[e]][2]["rot"][t_env[e]] for e in range(4)]).astype(np.int8)
+        ph = np.stack([scen[src[e]][2]["ph"][t_env[e]] for e in range(4)]).astype(np.int8)
+        refs = []
+        for e, o in enumerate(oracles):
+            p_, a_, r_, _ = o.step(rot[e].astype(np.int64), ph[e].astype(np.int64))
+            refs.append((p_, a_, r_.copy()))
+        obs, ast, rew, _ = b.step(torch.from_numpy(rot).cuda(), torch.from_numpy(ph).cuda())
+        _cmp_outputs((obs, ast, rew), refs, "step %d" % t)
+        noise = np.stack([scen[src[e]][2]["noise"][t_env[e]] for e in range(4)])
+        for e, o in enumerate(oracles):
+            o.update(noise[e])
+        b.update(torch.from_numpy(noise).cuda())
+        compare_state(b.export_state(), oracles, "after update %d" % t, cfg)
+        for e in range(4):
+            t_env[e] += 1
     b.close()
