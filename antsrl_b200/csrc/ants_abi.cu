@@ -811,6 +811,7 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
     p.nby = p.Hp / 8;
     p.EN = (int64_t)p.E * p.N;
     b->use_pdl = (p.EN >= 131072 || getenv("ANTS_FORCE_PDL")) ? 1 : 0;   // (ANTS_FORCE_PDL: the parity tests under PDL)
+    if (getenv("ANTS_NO_PDL")) b->use_pdl = 0;
     p.plane = (int64_t)p.Wp * p.Hp;
     p.radius = cfg->radius; p.S = 2 * cfg->radius + 1; p.S2 = p.S * p.S; p.C = cfg->n_channels;
     p.has_mask = cfg->has_mask;
@@ -880,6 +881,11 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
                     !getenv("ANTS_NO_FUSED")) ? 1 : 0;
         b->env_group = g;
         b->env_apt = cap / ants::kEnvThreads;
+        // The block-per-environment kernel is heavy (256 threads x 64 registers, 33 KB of shared memory): launched as a
+        // programmatic dependent it sits on the SMs waiting for the perception kernel and takes registers and shared
+        // memory from it (measured: rollouts 0.37-0.61 ms per step against 0.36 for separate launches), so the pair
+        // runs in plain stream order
+        if (b->fused && !getenv("ANTS_FORCE_PDL")) b->use_pdl = 0;
         b->env_smem = cap * 32 + g * p.R * 4;
     }
     int rc = ANTS_OK;

@@ -79,13 +79,25 @@ __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("pre
 // Heavy or rare pieces of the per-ant work are kept out of line: the kernel body is unrolled over the ants of a thread,
 // and inlining them four times made it 12 000 instructions (ncu: 2.5 stall cycles per instruction waiting for the
 // instruction cache).
-__device__ __noinline__ double env_wrap(double v, double n) { return pymod_near(v, n); }
-__device__ __noinline__ void env_sincos(double t, double *s, double *c) { sincos(t, s, c); }
+#ifndef ANTS_ENV_HOT_INLINE
+#define ANTS_ENV_HOT_INLINE 1      // the helpers every ant runs (wrap, sincos, food load, deposit): inline (1) or called (0)
+#endif
+#ifndef ANTS_ENV_SPECULATE
+#define ANTS_ENV_SPECULATE 0       // update+move: move before the mandible rule, again for the ants whose holding changes
+                                   // (measured slower: 0.111 against 0.098 ms on the cfg4 shard)
+#endif
+#if ANTS_ENV_HOT_INLINE
+#define ANTS_ENV_HOT __forceinline__
+#else
+#define ANTS_ENV_HOT __noinline__
+#endif
+__device__ ANTS_ENV_HOT double env_wrap(double v, double n) { return pymod_near(v, n); }
+__device__ ANTS_ENV_HOT void env_sincos(double t, double *s, double *c) { sincos(t, s, c); }
 __device__ __noinline__ double env_noise(const Params &p, int e, uint32_t step_id, int ant) {
     return philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)ant);
 }
 // the owner of a cell adds its activations and clamps (ants.py:98-100, pheromone.py:36-41)
-__device__ __noinline__ void env_deposit(const Params &p, uint8_t *rec, int64_t i, uint32_t now, uint32_t now_abs) {
+__device__ ANTS_ENV_HOT void env_deposit(const Params &p, uint8_t *rec, int64_t i, uint32_t now, uint32_t now_abs) {
     for (int q = 0; q < p.P; ++q) {
         const double av = p.act[(int64_t)q * p.EN + i];
         if (av == 0.0) continue;
@@ -99,7 +111,7 @@ __device__ __noinline__ double env_food_commit(const Params &p, uint8_t *fr, dou
     st_food(p, fr, v);
     return ld_food(p, fr);
 }
-__device__ __noinline__ double env_ld_food(const Params &p, const uint8_t *r) { return ld_food(p, r); }
+__device__ ANTS_ENV_HOT double env_ld_food(const Params &p, const uint8_t *r) { return ld_food(p, r); }
 
 // the rock-grid entries follow a rock that moved (clear the old box, set the new one); a whole warp calls this
 __device__ __noinline__ void env_move_rock_grid(const Params &p, int e, int r, double cx, double cy, double nx, double ny, double rad, int lane) {
@@ -149,8 +161,11 @@ __device__ __noinline__ void env_push_by_rocks(const Params &p, int e, unsigned 
     *y = env_wrap(*y + sy, (double)p.H);
 }
 
+#ifndef ANTS_ENV_MINBLOCKS
+#define ANTS_ENV_MINBLOCKS 4       // resident blocks per SM the register budget allows (4 x 256 threads x 64 registers)
+#endif
 template <bool UPDATE, bool MOVE, int APT>
-__global__ void __launch_bounds__(kEnvThreads, 4)
+__global__ void __launch_bounds__(kEnvThreads, ANTS_ENV_MINBLOCKS)
 k_env(const __grid_constant__ Params p, const EnvArgs a) {
     pdl_begin();
     constexpr int CAP = APT * kEnvThreads;
@@ -346,7 +361,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 prefetch_l2(rec_of(el[k], cell[k]));                   // consumed after the barrier
                 env_hash_max(hkeys, hvals, HMASK, (uint32_t)(el[k] * p.plane + cell[k]) + 1u, (uint32_t)ant + 1u);
             }
-            if (MOVE) {
+            if (MOVE && ANTS_ENV_SPECULATE) {
                 // The move of the coming step (ants.py:62-80), ahead of the mandible rule: heading and rotation do not
                 // depend on the food, the speed only through the holding of an ant that picks up or drops in this very
                 // step -- those few are moved again below.  This takes the record of the NEW cell (a second random
@@ -407,7 +422,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         for (int k = 0; k < APT; ++k) {
             const int64_t i = i0 + lac[k];
             hold[k] = p.holding[i]; mand[k] = p.mandibles[i];
-            rot[k] = (!UPDATE && a.rot != nullptr) ? a.rot[i] : (int8_t)0;
+            rot[k] = (!(UPDATE && ANTS_ENV_SPECULATE) && a.rot != nullptr) ? a.rot[i] : (int8_t)0;
         }
     }
     if (UPDATE && MOVE) {
@@ -440,11 +455,12 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             // (after an update the prev cell IS the current cell: its hill bit decides whether dropped food is queued)
             flags[k] = (own ? 1 : 0) | (delta != 0.0 ? 2 : 0) | ((UPDATE && hill) ? 4 : 0);
             fd[k] = fd[k] + delta;                                                      // what the owner will write (ants.py:116)
-            if (!UPDATE || h != hold[k]) {
+            constexpr bool kSpec = UPDATE && (ANTS_ENV_SPECULATE != 0);
+            if (!kSpec || h != hold[k]) {
                 // MOVE alone: the move itself.  After an update it already ran with the old holding (above): only an
                 // ant whose holding just changed moves again, with the speed that goes with it
-                double t = UPDATE ? p.theta[i] : th[k];
-                if (!UPDATE && a.rot != nullptr) t = env_wrap(t + (double)rot[k] * p.max_rot_speed, 6.283185307179586);   // ants.py:62-67
+                double t = kSpec ? p.theta[i] : th[k];
+                if (!kSpec && a.rot != nullptr) t = env_wrap(t + (double)rot[k] * p.max_rot_speed, 6.283185307179586);   // ants.py:62-67
                 double fwd = (1.0 * p.max_speed) * (1.0 - h * p.csr);                   // RL_api.py:194
                 if (fwd < 0.0) fwd *= p.bsr;                                            // RL_api.py:195
                 double sn, cs;

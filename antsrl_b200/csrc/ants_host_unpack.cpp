@@ -50,10 +50,46 @@ void ants_unpack_plan_finish(AntsUnpackPlan *p) {
             for (int j = 0; j < p->n_fix; ++j) seen |= p->fix[j] == k;
             if (!seen) p->fix[p->n_fix++] = k;
         }
+    // tables of the AVX-512 path
+    int vidx[228];
+    for (int k = 0; k < 228; ++k) vidx[k] = -1;
+    for (int v = 0; v < p->V; ++v) vidx[p->vis[v]] = v;
+    bool table_ok = n <= 116 * 16;
+    p->n_vec = (n + 15) / 16;
+    for (int j = 0; table_ok && j < p->n_vec; ++j) {
+        int vf = -1;
+        for (int l = 0; l < 16; ++l) {
+            const int f = 16 * j + l;
+            if (f < n && vidx[f / p->C] >= 0 && (vf < 0 || vidx[f / p->C] < vf)) vf = vidx[f / p->C];
+        }
+        p->vec_src[j] = vf < 0 ? -1 : 12 * vf;
+        p->vec_val[j] = p->vec_food[j] = p->vec_store[j] = 0;
+        for (int l = 0; l < 16; ++l) {
+            const int f = 16 * j + l;
+            p->vec_idx[j][l] = 0; p->vec_bit[j][l] = 0u; p->vec_base[j][l] = 0.f;
+            if (f >= n) continue;
+            p->vec_store[j] |= (uint16_t)(1u << l);
+            const int smp = f / p->C, c = f - smp * p->C, v = vidx[smp];
+            if (v < 0) { p->vec_base[j][l] = -1.f; continue; }
+            const int rel = 3 * (v - vf);
+            if (c == p->val_ch[0]) { p->vec_idx[j][l] = rel; p->vec_val[j] |= (uint16_t)(1u << l); }
+            else if (c == p->val_ch[1]) { p->vec_idx[j][l] = rel + 1; p->vec_val[j] |= (uint16_t)(1u << l); }
+            else if (c == p->food_ch) { p->vec_idx[j][l] = rel + 2; p->vec_food[j] |= (uint16_t)(1u << l); }
+            else {
+                p->vec_idx[j][l] = rel + 2;
+                for (int k = 0; k < 8; ++k)
+                    if (p->flag_ch[k] == c) p->vec_bit[j][l] = 1u << (16 + k);
+            }
+            if (p->vec_idx[j][l] > 15) table_ok = false;       // (fewer than 4 channels: more than 5 samples per vector)
+        }
+    }
     p->simd = 0;
 #if defined(__x86_64__)
     if (p->C <= 8 && __builtin_cpu_supports("avx2")) p->simd = 1;
-    if (p->simd && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && !getenv("ANTS_NO_AVX512")) p->simd = 2;
+    if (p->simd && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && !getenv("ANTS_NO_AVX512")) {
+        p->simd = 2;
+        if (table_ok && !getenv("ANTS_NO_AVX512_TABLE")) p->simd = 3;
+    }
 #endif
 }
 
@@ -169,14 +205,77 @@ __attribute__((target("avx512f,avx512vl,avx2"))) static void unpack_avx512(const
 }
 #endif
 
+#if defined(__x86_64__)
+// AVX-512, one output vector at a time: 16 consecutive floats of an ant's dense observation come from one 64-byte window
+// of its packed record through one permute; the u16 counts are converted and the flag bits tested on the same register
+__attribute__((target("avx512f,avx512vl,avx2"))) static void unpack_avx512_table(const AntsUnpackPlan *p, const uint8_t *packed,
+                                                                              int64_t n_ants, float *out) {
+    const int n = p->S2 * p->C, NV = p->n_vec;
+    const int64_t bpa = (int64_t)p->V * 12;
+    const __m512i lo16 = _mm512_set1_epi32(0xFFFF);
+    const __m512 one = _mm512_set1_ps(1.f);
+    // The ants' observations form one flat float stream at `out`.  They are assembled in a cache-resident staging buffer
+    // whose 64-byte phase equals the destination's, and every line of the stream leaves with a non-temporal store as soon
+    // as it is complete (ant by ant: the write-combining buffers drain while the next ant is assembled), so no line of
+    // the destination is read and only the first and last partial line of the range see ordinary stores.
+    constexpr int EPOCH = 8;                                   // ants per pass over the staging buffer
+    alignas(64) float buf[16 + EPOCH * 228 * 8 + 32];
+    const int64_t total = n_ants * n;
+    int64_t written = 0, streamed = 0;                         // flat floats assembled / delivered
+    int64_t epoch0 = 0;                                        // flat index held at stage[0]
+    float *stage = buf + (((uintptr_t)out & 63) >> 2);         // stage[k - epoch0] <-> out[k], same alignment
+    bool head_done = (((uintptr_t)out & 63) == 0);
+    for (int64_t a = 0; a < n_ants; ++a) {
+        if (a > 0 && a % EPOCH == 0) {                         // new pass: carry the incomplete line to the front
+            const int64_t left = written - streamed;           // < 16 floats, and out + streamed is line aligned
+            memmove(buf, stage + (streamed - epoch0), (size_t)left * sizeof(float));
+            stage = buf; epoch0 = streamed;
+        }
+        float *o = stage + (written - epoch0);
+        const uint8_t *rec = packed + a * bpa;
+        for (int j = 0; j < NV; ++j) {
+            __m512 r = _mm512_loadu_ps(p->vec_base[j]);
+            if (p->vec_src[j] >= 0) {
+                const __m512i win = _mm512_loadu_si512((const void *)(rec + p->vec_src[j]));
+                const __m512i g = _mm512_permutexvar_epi32(_mm512_loadu_si512((const void *)p->vec_idx[j]), win);
+                r = _mm512_mask_mov_ps(r, (__mmask16)p->vec_val[j], _mm512_castsi512_ps(g));
+                r = _mm512_mask_mov_ps(r, (__mmask16)p->vec_food[j], _mm512_cvtepi32_ps(_mm512_and_si512(g, lo16)));
+                r = _mm512_mask_mov_ps(r, _mm512_test_epi32_mask(g, _mm512_loadu_si512((const void *)p->vec_bit[j])), one);
+            }
+            _mm512_mask_storeu_ps(o + 16 * j, (__mmask16)p->vec_store[j], r);
+        }
+        written += n;
+        if (!head_done) {                                      // the first, partial line of the range
+            const int64_t head = 16 - (((uintptr_t)out & 63) >> 2);
+            if (written < head) continue;
+            memcpy(out, stage, (size_t)head * sizeof(float));
+            streamed = head; head_done = true;
+        }
+        for (; streamed + 16 <= written; streamed += 16)
+            _mm512_stream_si512((__m512i *)(out + streamed), _mm512_load_si512((const void *)(stage + (streamed - epoch0))));
+    }
+    if (!head_done) streamed = 0;                              // (a range shorter than its first partial line)
+    memcpy(out + streamed, stage + (streamed - epoch0), (size_t)(total - streamed) * sizeof(float));
+    _mm_sfence();
+}
+#endif
+
 void ants_unpack_range(const AntsUnpackPlan *p, const uint8_t *packed, int64_t n_ants, float *out) {
 #if defined(__x86_64__)
-    if (p->simd == 2 && n_ants > 1) {
+    if (p->simd == 3 && n_ants > 6) {
+        // (a window reads 64 bytes from some sample of the record: the last ants of the range go through the scalar path
+        //  so that nothing past the caller's buffer is read)
+        const int64_t tail = (64 + (int64_t)p->V * 12 - 1) / ((int64_t)p->V * 12) + 1;
+        unpack_avx512_table(p, packed, n_ants - tail, out);
+        unpack_scalar(p, packed + (n_ants - tail) * (int64_t)p->V * 12, tail, out + (n_ants - tail) * (int64_t)p->S2 * p->C);
+        return;
+    }
+    if (p->simd >= 2 && n_ants > 1) {
         unpack_avx512(p, packed, n_ants - 1, out);
         unpack_scalar(p, packed + (n_ants - 1) * (int64_t)p->V * 12, 1, out + (n_ants - 1) * (int64_t)p->S2 * p->C);
         return;
     }
-    if (p->simd && n_ants > 1) {
+    if (p->simd >= 1 && n_ants > 1) {
         // (the vector path loads 16 bytes per 12-byte sample: the last ant goes through the scalar path so that nothing
         //  past the caller's buffer is read)
         unpack_avx2(p, packed, n_ants - 1, out);

@@ -83,6 +83,9 @@ template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 
 #ifndef ANTS_ROWS_UNR
 #define ANTS_ROWS_UNR 7
 #endif
+#ifndef ANTS_ROWS_PREFETCH
+#define ANTS_ROWS_PREFETCH 4       // samples of the NEXT chunk's row whose records are prefetched into L2 (0 = off, S = all)
+#endif
 __global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
 k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
                 double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
@@ -207,7 +210,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     constexpr bool kLateWait = (UNR >= S);
     // one row: sample cells, record loads, decode, staging-tile stores; returns the row's count of unexplored samples
     auto row_body = [&](const RowPrep &q, const double offY, const uint32_t mrow, const uint32_t orow_s,
-                        const uint32_t amask) -> int {
+                        const uint32_t amask, const RowPrep *qn) -> int {
         const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
         const int e = q.e;
         const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
@@ -245,6 +248,24 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         lo[u] = ld_record16(rp);
                     }
                     if (REC == 0) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
+                }
+            }
+            if (ANTS_ROWS_PREFETCH > 0 && qn != nullptr && j0 == 0) {
+                // While this row's record loads are in flight: the same row of the ant this lane serves in the NEXT chunk.
+                // ncu (bench batch) showed 30 % of all warp stall samples on the first use of the loaded records; the
+                // address arithmetic of a few samples costs issue slots the kernel has to spare (46 % issue utilisation)
+                // and turns those DRAM misses into L2 hits.  Every other sample: neighbours share or adjoin a sector.
+                const double ct2 = qn->ct, st2 = qn->st, xf2 = qn->xf, yf2 = qn->yf;
+                const uint8_t *cells2 = p.cells + (((int64_t)qn->e * p.plane) << SH);
+                const double stY2 = st2 * offY, ctY2 = ct2 * offY;
+#pragma unroll
+                for (int k = 0; k < ANTS_ROWS_PREFETCH && k < S; ++k) {
+                    const int j = ANTS_ROWS_PREFETCH >= S ? k : (k * (S - 1)) / (ANTS_ROWS_PREFETCH > 1 ? ANTS_ROWS_PREFETCH - 1 : 1);
+                    const double X = p.off_c[j];
+                    int ix = round_half_even((ct2 * X - stY2) + xf2), iy = round_half_even((st2 * X + ctY2) + yf2);
+                    ix = wrap1(ix, W); iy = wrap1(iy, H);
+                    const uint32_t c2 = (uint32_t)((ix >> 3) * nby64m + ix * 8 + (iy >> 3) * 56 + iy);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(cells2 + ((size_t)c2 << SH)));
                 }
             }
             if (LAYOUT == 2 && flags) {            // a rock may reach this ant's window (few ants): RL_api.py:132-135
@@ -414,7 +435,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             const uint32_t amask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
             if (lane < nrows) {
                 const uint32_t orow_s = tiles_s + (uint32_t)((((la >> 2) & 1) * TILE + ((la & 3) * S2 + li * S) * C) * 4);
-                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask);
+                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask, nullptr);
                 s_rowcnt[(warp * 32 + la) * S + li] = (uint8_t)cnt;
             }
             const bool last = nrows <= 32;
@@ -457,7 +478,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 __syncwarp();
             }
             if (lane_on && la < n_in) {
-                const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask);
+                const RowPrep *qn = (g + G < 32 && i0 + G + la < p.EN) ? &prep[warp * 32 + g + G + la] : nullptr;
+                const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn);
                 s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
             }
             flush(wobs, i0, n_in);
