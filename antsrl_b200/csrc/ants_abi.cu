@@ -211,6 +211,14 @@ struct AntsBatch {
     // dense while the host threads expand the packed rest; the split follows whichever side finished later
     double dense_frac = 0.2;
     int dense_frac_fixed = 0;
+    // ants_rollout: the batch as groups of environments on streams of their own -- the perception kernel of one group
+    // (issue bound, all registers of an SM) overlaps the block-per-environment kernel of another (latency bound)
+    struct Group { cudaStream_t s = nullptr; cudaEvent_t done = nullptr; int env0 = 0, env1 = 0; };
+    std::vector<Group> groups;
+    cudaEvent_t ev_fork = nullptr;
+    int grouped = 0;                // inside a grouped rollout (whole-batch passes must join the groups first)
+    cudaStream_t cur_stream = nullptr;   // target of the step-kernel launches: nullptr = the handle's stream, whole batch
+    int cur_env0 = 0, cur_env1 = 0;
 };
 
 namespace {
@@ -304,7 +312,7 @@ void launch_step(AntsBatch *b, void (*kernel)(KArgs...), unsigned grid, unsigned
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
-    cfg.stream = b->stream;
+    cfg.stream = b->cur_stream ? b->cur_stream : b->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -319,12 +327,31 @@ int check_launch(const char *what) {
     return ANTS_OK;
 }
 
+// grouped rollout: the groups' streams branch off the handle's stream and join it again; a whole-batch pass in between
+// (generation fold, lazy-field fold) joins them first
+void fork_groups(AntsBatch *b) {
+    cudaEventRecord(b->ev_fork, b->stream);
+    for (auto &g : b->groups) cudaStreamWaitEvent(g.s, b->ev_fork, 0);
+}
+void join_groups(AntsBatch *b) {
+    for (auto &g : b->groups) {
+        cudaEventRecord(g.done, g.s);
+        cudaStreamWaitEvent(b->stream, g.done, 0);
+    }
+}
+struct WholeBatchPass {
+    AntsBatch *b;
+    explicit WholeBatchPass(AntsBatch *b_) : b(b_) { if (b->grouped) join_groups(b); }
+    ~WholeBatchPass() { if (b->grouped) fork_groups(b); }
+};
+
 // 16-bit (f64 records) or 7/8-bit (compact records) generation counters: before either wraps, ONE pass folds
 // every live exploration stamp into "explored long ago" and clears the occupancy stamps.  Called at the start of
 // observe / step, before any stamp of the new generation is written.
 void maybe_fold_generations(AntsBatch *b) {
     const uint32_t obs_lim = b->p.explored_old - 2u, occ_lim = (b->p.rec16 || b->p.rec8) ? 0x7Eu : 0xFFFEu;
     if (b->obs_gen + 1u >= obs_lim || b->occ_gen + 1u >= occ_lim) {
+        WholeBatchPass wb(b);
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 16, 256, 0, b->stream>>>(b->p, 1, 1);
         b->obs_gen = 0;
@@ -333,6 +360,7 @@ void maybe_fold_generations(AntsBatch *b) {
 }
 uint32_t next_obs_gen(AntsBatch *b) {
     if (b->obs_gen >= b->p.explored_old - 2u) {   // fold live stamps into "explored long ago" before the counter wraps
+        WholeBatchPass wb(b);
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 1, 0);
         b->obs_gen = 0;
@@ -341,6 +369,7 @@ uint32_t next_obs_gen(AntsBatch *b) {
 }
 uint32_t next_occ_gen(AntsBatch *b) {
     if (b->occ_gen >= ((b->p.rec16 || b->p.rec8) ? 0x7Eu : 0xFFFEu)) {
+        WholeBatchPass wb(b);
         LaunchScope ls(b, F_MISC);
         ants::k_meta_renormalize<<<148 * 8, 256, 0, b->stream>>>(b->p, 0, 1);
         b->occ_gen = 0;
@@ -355,9 +384,19 @@ uint32_t next_owner_phase(AntsBatch *b) {
     return ++b->owner_phase;
 }
 
+int launch_perceive_range(AntsBatch *b, uint32_t og, float *d_obs, float *d_as, float *d_state, double *d_reward, int is_step);
+
 int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward, int is_step) {
+    const uint32_t og = next_obs_gen(b);
+    TRY(launch_perceive_range(b, og, d_obs, d_as, d_state, d_reward, is_step));
+    b->rw_alias = 0;
+    return ANTS_OK;
+}
+
+// the perception kernel over the current launch target (whole batch, or one group of a grouped rollout)
+int launch_perceive_range(AntsBatch *b, uint32_t og, float *d_obs, float *d_as, float *d_state, double *d_reward, int is_step) {
     const Params &p = b->p;
-    uint32_t og = next_obs_gen(b);
+    const int64_t ant0 = b->cur_stream ? (int64_t)b->cur_env0 * p.N : 0, ant1 = b->cur_stream ? (int64_t)b->cur_env1 * p.N : p.EN;
     int blocks = 0;
     {
         LaunchScope ls(b, F_PERCEIVE);
@@ -368,11 +407,11 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
         const int threads = b->perceive_threads;
         blocks = (int)cdiv(p.EN, threads);
         if (b->perceive_rows) {
-            const int rblocks = (int)cdiv(p.EN, ants::kRowsThreads);
+            const int rblocks = (int)cdiv(ant1 - ant0, ants::kRowsThreads);
 #define ANTS_ROWS(L, R16, SS)                                                                               \
     launch_step(b, ants::k_perceive_rows<L, R16, SS>, (unsigned)rblocks, (unsigned)ants::kRowsThreads,      \
                 (size_t)b->rows_smem, p, d_obs, d_as, d_state, d_reward, og, b->occ_gen, is_step,          \
-                b->rw_alias, b->lazy_now, b->lazy_abs)
+                b->rw_alias, b->lazy_now, b->lazy_abs, ant0, ant1)
 #define ANTS_ROWS_S(SS)                                                                          \
     do {                                                                                         \
         if (p.rec8) { if (layout == 2) ANTS_ROWS(2, 2, SS); else ANTS_ROWS(1, 2, SS); }         \
@@ -400,16 +439,17 @@ int launch_perceive(AntsBatch *b, float *d_obs, float *d_as, float *d_state, dou
         }
 #undef ANTS_PERCEIVE
     }
-    b->rw_alias = 0;
     return check_launch("k_perceive");
 }
 
 
 // ------------------------------------------------------------------------------------------------ block-per-env path
 template <bool UPDATE, bool MOVE>
-void launch_env(AntsBatch *b, const ants::EnvArgs &a) {
+void launch_env(AntsBatch *b, ants::EnvArgs a) {
     const Params &p = b->p;
-    const unsigned grid = (unsigned)cdiv(p.E, b->env_group);
+    a.env_base = b->cur_stream ? b->cur_env0 : 0;
+    a.env_end = b->cur_stream ? b->cur_env1 : p.E;
+    const unsigned grid = (unsigned)cdiv(a.env_end - a.env_base, b->env_group);
     if (b->env_apt == 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
     else if (b->env_apt == 2) launch_step(b, ants::k_env<UPDATE, MOVE, 2>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
     else launch_step(b, ants::k_env<UPDATE, MOVE, 4>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
@@ -432,6 +472,7 @@ int env_args_update(AntsBatch *b, const double *d_noise, ants::EnvArgs *a) {
     if (p.P > 0 && p.lazy) {
         const bool unbox = p.rec8 ? ((b->lazy_abs & 0x3FFFu) == 0x3FFFu) : (b->lazy_abs >= ants::kBoxMask - 2u);
         if (b->lazy_now >= p.ts_mask - 1u || unbox) {
+            WholeBatchPass wb(b);
             LaunchScope ls(b, F_EVAP);
             ants::k_lazy_fold<<<148 * 16, 256, 0, b->stream>>>(p, b->lazy_now, b->lazy_abs, unbox ? 1 : 0);
             b->lazy_now = 0;
@@ -442,7 +483,7 @@ int env_args_update(AntsBatch *b, const double *d_noise, ants::EnvArgs *a) {
         b->lazy_abs += 1;
     }
     a->noise = d_noise;
-    a->use_flag = b->wall_flags_valid;
+    a->use_flag = 0;               // (the block-per-env kernels read the wall bit with the record they need anyway)
     a->now = b->lazy_now; a->now_abs = b->lazy_abs;
     a->group = b->env_group; a->cap = b->env_apt * ants::kEnvThreads;
     return ANTS_OK;
@@ -512,6 +553,87 @@ int do_update_move_fused(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph) 
     b->stats.updates++;
     b->move_done = 1;
     return ANTS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ grouped rollout
+int ensure_groups(AntsBatch *b, int want) {
+    if (!b->groups.empty()) return ANTS_OK;
+    const Params &p = b->p;
+    if (cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(ANTS_E_CUDA, "cudaEventCreate failed");
+    const int blocks = (int)cdiv(p.E, b->env_group);                 // block-per-env kernel: env_group envs per block
+    const int G = want < blocks ? want : blocks;
+    for (int g = 0; g < G; ++g) {
+        AntsBatch::Group gr;
+        gr.env0 = (int)((int64_t)blocks * g / G) * b->env_group;
+        gr.env1 = g + 1 == G ? p.E : (int)((int64_t)blocks * (g + 1) / G) * b->env_group;
+        if (cudaStreamCreateWithFlags(&gr.s, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&gr.done, cudaEventDisableTiming) != cudaSuccess)
+            return fail(ANTS_E_CUDA, "stream / event creation for the rollout groups failed");
+        b->groups.push_back(gr);
+    }
+    return ANTS_OK;
+}
+
+template <typename F>
+int for_each_group(AntsBatch *b, F launch) {
+    int rc = ANTS_OK;
+    for (auto &g : b->groups) {
+        b->cur_stream = g.s; b->cur_env0 = g.env0; b->cur_env1 = g.env1;
+        rc = launch();
+        if (rc != ANTS_OK) break;
+    }
+    b->cur_stream = nullptr;
+    return rc;
+}
+
+// T x [step; update] with every kernel launched once per group of environments on the group's stream.  Host bookkeeping
+// (generation counters, lazy-field counters, timestep) advances once per step for the whole batch; the rare whole-batch
+// passes join the groups (WholeBatchPass).  Same results as the plain loop: groups share no state.
+int rollout_grouped(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape, int32_t n_steps, float *d_obs,
+                    float *d_as, double *d_reward) {
+    const int64_t EN = b->p.EN;
+    if (d_ph_tape && b->p.P != 2) return fail(ANTS_E_ARG, "pheromone actions need exactly two pheromones (ants.py:92-96)");
+    b->grouped = 1;
+    fork_groups(b);
+    int rc = ANTS_OK;
+    for (int t = 0; t < n_steps && rc == ANTS_OK; ++t) {
+        const int8_t *r = d_rot_tape ? d_rot_tape + (int64_t)t * EN : nullptr;
+        const int8_t *h = d_ph_tape ? d_ph_tape + (int64_t)t * EN : nullptr;
+        if (!b->move_done) {                                   // (only the first step: later moves ride on the updates)
+            ants::EnvArgs a = {};
+            env_args_move(b, r, h, &a);
+            rc = for_each_group(b, [&] { launch_env<false, true>(b, a); return check_launch("k_env<move>"); });
+            if (rc != ANTS_OK) break;
+            b->stats.kernel_launches += (int64_t)b->groups.size();
+        }
+        b->move_done = 0;
+        b->prev_synced = 0;
+        const uint32_t og = next_obs_gen(b);
+        rc = for_each_group(b, [&] { return launch_perceive_range(b, og, d_obs, d_as, nullptr, d_reward, 1); });
+        if (rc != ANTS_OK) break;
+        b->rw_alias = 0;
+        b->stats.steps++;
+        ants::EnvArgs a = {};
+        rc = env_args_update(b, nullptr, &a);
+        if (rc != ANTS_OK) break;
+        if (t + 1 < n_steps) {
+            b->prev_synced = 1;
+            env_args_move(b, d_rot_tape ? r + EN : nullptr, d_ph_tape ? h + EN : nullptr, &a);
+            rc = for_each_group(b, [&] { launch_env<true, true>(b, a); return check_launch("k_env<update, move>"); });
+            b->move_done = 1;
+        } else {
+            rc = for_each_group(b, [&] { launch_env<true, false>(b, a); return check_launch("k_env<update>"); });
+            b->prev_synced = 1;
+        }
+        b->wall_flags_valid = 0;
+        b->stats.active_tiles = 0;
+        b->stats.updates++;
+        b->stats.kernel_launches += (int64_t)b->groups.size();     // (the perception launches count themselves)
+    }
+    join_groups(b);
+    b->grouped = 0;
+    b->cur_stream = nullptr;
+    return rc;
 }
 
 int do_observe(AntsBatch *b, float *d_obs, float *d_as, float *d_state, double *d_reward) {
@@ -1102,6 +1224,8 @@ int ants_destroy(AntsBatch *b) {
     for (auto e : b->event_pool) cudaEventDestroy(e);
     for (void *d : b->allocs) cudaFree(d);
     if (b->h_counts) cudaFreeHost(b->h_counts);
+    for (auto &g : b->groups) { if (g.s) { cudaStreamSynchronize(g.s); cudaStreamDestroy(g.s); } if (g.done) cudaEventDestroy(g.done); }
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
     if (b->h_packed) cudaFreeHost(b->h_packed);
     for (auto e : b->chunk_ev) cudaEventDestroy(e);
     delete b->unpack_plan;
@@ -1377,6 +1501,26 @@ int ants_rollout(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_tape
     if (!b) return fail(ANTS_E_ARG, "null handle");
     CK(cudaSetDevice(b->cfg.device));
     const int64_t EN = b->p.EN;
+    if (n_steps <= 0) return ANTS_OK;
+    if (!d_obs || !d_agent_state) return fail(ANTS_E_ARG, "ants_rollout: obs and agent_state buffers are required");
+    {   // groups of environments on their own streams: large batches on the block-per-env kernels (ANTS_ROLLOUT_GROUPS
+        // overrides: 1 = off)
+        int want = (b->fused && b->perceive_rows && EN >= 131072) ? 4 : 1;
+        if (const char *x = getenv("ANTS_ROLLOUT_GROUPS")) want = atoi(x);
+        if (want > 1 && b->fused && b->perceive_rows && !b->profiling) {
+            if (b->needs_sweep) {                              // first update after an import: the plain path sweeps the hill
+                const int8_t *r0 = d_rot_tape, *h0 = d_ph_tape;
+                TRY(do_step(b, r0, h0, d_obs, d_agent_state, d_reward, nullptr));
+                TRY(do_update(b, nullptr));
+                if (n_steps == 1) return ANTS_OK;
+                d_rot_tape = d_rot_tape ? d_rot_tape + EN : nullptr;
+                d_ph_tape = d_ph_tape ? d_ph_tape + EN : nullptr;
+                n_steps -= 1;
+            }
+            TRY(ensure_groups(b, want));
+            if (b->groups.size() > 1) return rollout_grouped(b, d_rot_tape, d_ph_tape, n_steps, d_obs, d_agent_state, d_reward);
+        }
+    }
     for (int t = 0; t < n_steps; ++t) {
         const int8_t *r = d_rot_tape ? d_rot_tape + (int64_t)t * EN : nullptr;
         const int8_t *h = d_ph_tape ? d_ph_tape + (int64_t)t * EN : nullptr;

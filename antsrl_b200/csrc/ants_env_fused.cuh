@@ -39,6 +39,7 @@ struct EnvArgs {
     double act_on;                           // MOVE: 256 (float activations) or 1 (bool dtype, ants.py:83)
     uint32_t now, now_abs;                   // UPDATE: lazy-field counters of this update (deposit timestamps)
     int32_t group, cap;                      // envs per block, ants per block
+    int32_t env_base, env_end;               // the envs [env_base, env_end) of the batch (ants_rollout: groups on own streams)
 };
 
 __device__ __forceinline__ uint32_t env_hash_slot(uint32_t key, uint32_t mask) { return (key * 2654435761u >> 11) & mask; }
@@ -178,8 +179,8 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     constexpr uint32_t HMASK = 2u * CAP - 1u;
 
     const int tid = threadIdx.x;
-    const int env0 = blockIdx.x * a.group;
-    const int n_env = min(a.group, p.E - env0);
+    const int env0 = a.env_base + blockIdx.x * a.group;
+    const int n_env = min(a.group, a.env_end - env0);
     const int n_loc = n_env * p.N;                                     // ants of this block
     const int64_t i0 = (int64_t)env0 * p.N;
     const int W = p.W, H = p.H;
@@ -204,7 +205,8 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     // together, with the index of an idle slot clamped to the block's last ant: the kernel lives on memory-level
     // parallelism (two random DRAM sectors per ant: the cell it deposits on and the cell it moves to).
     double th[APT];
-    int newcell[APT];              // MOVE: the cell the ant moves to
+    int newcell[APT];              // MOVE: the cell the ant moves to ...
+    int newxy[APT];                // ... and its coordinates (x << 16 | y)
     int cell[APT];                 // UPDATE: the cell the ant ends the update in; MOVE alone: its prev cell
     int el[APT];                   // environment within the block
     int lac[APT];                  // the ant's slot in the block (clamped)
@@ -215,7 +217,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         valid[k] = la < n_loc;
         lac[k] = valid[k] ? la : (n_loc - 1);
         el[k] = a.group == 1 ? 0 : lac[k] / p.N;
-        th[k] = 0.0; cell[k] = 0; newcell[k] = 0;
+        th[k] = 0.0; cell[k] = 0; newcell[k] = 0; newxy[k] = 0;
     }
     // record of cell c of the block's env g: (g * plane + c) fits 32 bits (the hash keys rely on the same bound)
     uint8_t *const cells0 = p.cells + (((int64_t)env0 * p.plane) << p.rec_shift);
@@ -255,14 +257,18 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         for (int k = 0; k < APT; ++k) {
             const int64_t i = i0 + lac[k];
             x[k] = p.x[i]; y[k] = p.y[i]; th[k] = p.theta[i];
-            in_wall[k] = a.use_flag ? p.wall_hit[i] != 0 : false;
-            if (p.P > 0) { prefetch_l2(p.act + i); if (p.P > 1) prefetch_l2(p.act + p.EN + i); }   // read by the depositing owners
+            // what the later phases read, requested now (no registers held): the activations of the depositing owners,
+            // the ant state of the move
+            if (p.P > 0) { prefetch_l2(p.act + i); if (p.P > 1) prefetch_l2(p.act + p.EN + i); }
+            prefetch_l2(p.reward_state + i);
+            if (MOVE) { prefetch_l2(p.holding + i); prefetch_l2(p.mandibles + i); if (a.rot != nullptr) prefetch_l2(a.rot + i); }
         }
-        if (!a.use_flag) {
+        // Walls.update (walls.py:24-25): the wall bit of the cell the ant stands on.  This is the ONE random DRAM sector of
+        // the ant per iteration: unless a wall or a rock moves it, it is also the cell it deposits on and the cell whose
+        // food the mandible rule reads (the move of the previous step only stored the occupancy stamp there).
 #pragma unroll
-            for (int k = 0; k < APT; ++k)
-                in_wall[k] = ld_wall(p, rec_of(el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));
-        }
+        for (int k = 0; k < APT; ++k)
+            in_wall[k] = ld_wall(p, rec_of(el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));
         unsigned long long rm[APT];
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
@@ -375,8 +381,8 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 const double x1 = env_wrap(x[k] + cs * fwd, Wd);                        // ants.py:69-80
                 const double y1 = env_wrap(y[k] + sn * fwd, Hd);
                 p.x[i] = x1; p.y[i] = y1; p.theta[i] = t;
-                newcell[k] = cidx(p, cell_of(x1, W), cell_of(y1, H));
-                prefetch_l2(rec_of(el[k], newcell[k]));
+                const int nx = cell_of(x1, W), ny = cell_of(y1, H);
+                newcell[k] = cidx(p, nx, ny); newxy[k] = (nx << 16) | ny;
             }
         }
         __syncthreads();
@@ -468,8 +474,8 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 const double x = env_wrap(x0 + cs * fwd, Wd);                           // ants.py:69-80
                 const double y = env_wrap(y0 + sn * fwd, Hd);
                 p.x[i] = x; p.y[i] = y; p.theta[i] = t;
-                newcell[k] = cidx(p, cell_of(x, W), cell_of(y, H));
-                prefetch_l2(rec_of(el[k], newcell[k]));
+                const int nx = cell_of(x, W), ny = cell_of(y, H);
+                newcell[k] = cidx(p, nx, ny); newxy[k] = (nx << 16) | ny;
             }
         }
     }
@@ -505,13 +511,19 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             p.act[p.EN + i] = (v != 0 && v != 1) ? a.act_on : 0.0;
         }
     }
-    // the new cell may be a cell whose food an owner just rewrote: stamps touch other bytes of the record
+    // Occupancy stamp of the new cell (RL_api.py:136-142), a store without a load: the byte it shares with the anthill bit
+    // of the compact records is rebuilt from the disc test on integers (the same test k_hill_mark wrote the bit with).
+    // Whether the new cell is a wall is read by the coming update, together with everything else it needs of that cell.
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         if (!valid[k]) continue;
         uint8_t *orec = rec_of(el[k], newcell[k]);
-        p.wall_hit[i0 + lac[k]] = ld_wall(p, orec) ? 1 : 0;            // for Walls.update of the coming update
-        st_occ(p, orec, a.occ_gen);
+        if (p.rec8 || p.rec16) {
+            const bool hill = in_hill(p.hill + 4 * (env0 + el[k]), newxy[k] >> 16, newxy[k] & 0xFFFF);
+            orec[p.rec8 ? 6 : 12] = (uint8_t)((hill ? 0x80u : 0u) | (a.occ_gen & 0x7Fu));
+        } else {
+            st_occ(p, orec, a.occ_gen);
+        }
     }
 }
 

@@ -84,12 +84,15 @@ template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 
 #define ANTS_ROWS_UNR 7
 #endif
 #ifndef ANTS_ROWS_PREFETCH
-#define ANTS_ROWS_PREFETCH 4       // samples of the NEXT chunk's row whose records are prefetched into L2 (0 = off, S = all)
+#define ANTS_ROWS_PREFETCH 0       // samples of the NEXT chunk's row whose records are prefetched into L2 (0 = off, S = all).
+                                   // Measured on the cfg4 shard: 0.240 ms without, 0.254 with 4, 0.269 with 7 -- the
+                                   // kernel has no issue slots to spare for the address arithmetic
 #endif
 __global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
 k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
                 double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
-                uint32_t now, uint32_t now_abs) {
+                uint32_t now, uint32_t now_abs, int64_t ant0, int64_t ant_end) {
+    // (ants [ant0, ant_end) of the batch: ants_rollout runs groups of environments on streams of their own)
     pdl_begin();
     static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
     constexpr bool REC16 = (REC == 1), REC8 = (REC == 2);
@@ -106,14 +109,14 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     uint8_t *s_rowcnt = reinterpret_cast<uint8_t *>(prep + kRowsThreads);   // [threads][S]
 
     const int tid = threadIdx.x;
-    const int64_t base = (int64_t)blockIdx.x * kRowsThreads;
+    const int64_t base = ant0 + (int64_t)blockIdx.x * kRowsThreads;
     const bool explore_on = p.explore_on != 0;
 
     // ---- phase A (thread per ant): frame, reward terms that do not need the exploration count, small outputs
     double r_other = 0.0, r_mult = 1.0;
     {
         const int64_t i = base + tid;
-        if (i < p.EN) {
+        if (i < ant_end) {
             const int e = (int)(i / p.N);
             const double x = p.x[i], y = p.y[i], th = p.theta[i], hold = p.holding[i];
             double s0, c0, st, ct;
@@ -251,10 +254,9 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 }
             }
             if (ANTS_ROWS_PREFETCH > 0 && qn != nullptr && j0 == 0) {
-                // While this row's record loads are in flight: the same row of the ant this lane serves in the NEXT chunk.
-                // ncu (bench batch) showed 30 % of all warp stall samples on the first use of the loaded records; the
-                // address arithmetic of a few samples costs issue slots the kernel has to spare (46 % issue utilisation)
-                // and turns those DRAM misses into L2 hits.  Every other sample: neighbours share or adjoin a sector.
+                // (experiment, off by default) while this row's record loads are in flight: prefetch the same row of the
+                // ant this lane serves in the NEXT chunk.  ncu (bench batch) showed 30 % of all warp stall samples on the
+                // first use of the loaded records, but the extra address arithmetic costs more than the L2 hits give back.
                 const double ct2 = qn->ct, st2 = qn->st, xf2 = qn->xf, yf2 = qn->yf;
                 const uint8_t *cells2 = p.cells + (((int64_t)qn->e * p.plane) << SH);
                 const double stY2 = st2 * offY, ctY2 = ct2 * offY;
@@ -409,7 +411,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         }
     };
     const int64_t wbase = base + warp * 32;
-    const int n_valid = (p.EN - wbase >= 32) ? 32 : (p.EN > wbase ? (int)(p.EN - wbase) : 0);   // ants of this warp
+    const int n_valid = (ant_end - wbase >= 32) ? 32 : (ant_end > wbase ? (int)(ant_end - wbase) : 0);   // ants of this warp
     if (FLAT) {
         // All 32 ants of the warp as 32 * S rows: iteration t hands rows 32t .. 32t+31 to the lanes (no idle lanes:
         // S iterations instead of 32 / 4 chunks of 4 * S <= 32 rows).  Ant a stages into slot (a / 4) & 1 of two
@@ -467,8 +469,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         }
         for (int g = 0; g < 32; g += G) {
             const int64_t i0 = wbase + g;
-            if (i0 >= p.EN) break;
-            const int n_in = (p.EN - i0 < G) ? (int)(p.EN - i0) : G;
+            if (i0 >= ant_end) break;
+            const int n_in = (ant_end - i0 < G) ? (int)(ant_end - i0) : G;
             const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
             float *wobs = wobs0 + tsel * TILE;
             const uint32_t orow_s = orow_s0 + (uint32_t)(tsel * TILE * 4);
@@ -478,7 +480,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 __syncwarp();
             }
             if (lane_on && la < n_in) {
-                const RowPrep *qn = (g + G < 32 && i0 + G + la < p.EN) ? &prep[warp * 32 + g + G + la] : nullptr;
+                const RowPrep *qn = (g + G < 32 && i0 + G + la < ant_end) ? &prep[warp * 32 + g + G + la] : nullptr;
                 const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn);
                 s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
             }
@@ -490,7 +492,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     // ---- phase C: reward epilogue, thread per ant (this warp's own ants)
     {
         const int64_t i = base + tid;
-        if (i < p.EN) {
+        if (i < ant_end) {
             int count = 0;
             if (explore_on) {
 #pragma unroll

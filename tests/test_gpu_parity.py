@@ -223,10 +223,13 @@ def test_lazy_timestamp_fold():
         np.testing.assert_allclose(outs[fmt]["phero"], outs["tiles"]["phero"], rtol=1e-5, atol=0)
 
 
+@pytest.mark.parametrize("groups", [1, 3], ids=["one_stream", "three_groups"])
 @pytest.mark.parametrize("record,n_rocks", [("compact8", 0), ("compact8", 4), ("compact", 0), ("f64", 4)])
-def test_rollout_equals_step_update_loop(record, n_rocks):
-    """ants_rollout (device-resident action tapes, C loop) == the same steps issued one by one."""
+def test_rollout_equals_step_update_loop(record, n_rocks, groups, monkeypatch):
+    """ants_rollout (device-resident action tapes, C loop; optionally the batch as groups of environments on streams of
+    their own) == the same steps issued one by one."""
     import torch
+    monkeypatch.setenv("ANTS_ROLLOUT_GROUPS", str(groups))
     from antsrl_b200 import BatchedAnts
     scen = [make_scenario(seed=800 + e, w=48, h=48, n_ants=40, n_rocks=n_rocks, steps=12, n_walls=6) for e in range(3)]
     cfg = scen[0][0]
@@ -613,9 +616,10 @@ def test_partial_import_keeps_scalars():
     b.close()
 
 
+@pytest.mark.parametrize("groups", [1, 4], ids=["one_stream", "four_groups"])
 @pytest.mark.parametrize("record,n_rocks,n_ants,n_envs", [("compact8", 6, 300, 3), ("compact8", 0, 50, 7), ("compact", 4, 520, 2),
                                                           ("f64", 3, 1024, 2), ("compact8", 2, 1100, 2)])
-def test_rollout_matches_oracle(record, n_rocks, n_ants, n_envs):
+def test_rollout_matches_oracle(record, n_rocks, n_ants, n_envs, groups, monkeypatch):
     """ants_rollout (update_k and the move of step_{k+1} in ONE launch of the block-per-environment kernel; 1, 2 or 4
     ants per thread, several envs per block for small N; 1100 ants per env falls back to the flat kernels) against the
     oracle: last observation / reward and the full final state after 30 steps, Philox noise, crowded hill (shared
@@ -624,6 +628,7 @@ def test_rollout_matches_oracle(record, n_rocks, n_ants, n_envs):
     from antsrl_b200 import BatchedAnts
     from oracle.antsrl_oracle import OracleEnv, philox_uniform
     from parity_util import compare_state
+    monkeypatch.setenv("ANTS_ROLLOUT_GROUPS", str(groups))
     T = 30
     scen = [make_scenario(seed=1200 + e, w=72, h=64, n_ants=n_ants, n_rocks=n_rocks, steps=T, n_walls=6, n_food=14)
             for e in range(n_envs)]
@@ -696,4 +701,37 @@ def test_windowed_import_resets_some_environments(record, n_rocks):
         compare_state(b.export_state(), oracles, "after update %d" % t, cfg)
         for e in range(4):
             t_env[e] += 1
+    b.close()
+
+
+def test_grouped_rollout_crosses_generation_folds(monkeypatch):
+    """150 steps of ants_rollout with the batch split into groups on their own streams: the 7-bit generation counters of
+    the compact records fold on the way (whole-batch passes that must join the groups first and fork them again)."""
+    import torch
+    from antsrl_b200 import BatchedAnts
+    from oracle.antsrl_oracle import OracleEnv, philox_uniform
+    from parity_util import compare_state
+    monkeypatch.setenv("ANTS_ROLLOUT_GROUPS", "2")
+    T, E, N = 150, 4, 48
+    scen = [make_scenario(seed=1700 + e, w=64, h=56, n_ants=N, n_rocks=3, steps=T, n_walls=5, n_food=8) for e in range(E)]
+    cfg = scen[0][0]
+    oracles = [OracleEnv(c, i) for c, i, _ in scen]
+    b = BatchedAnts(cfg, E, evap_mode="lazy", record="compact8", rng_seed=31)
+    b.import_state(stack_init(cfg, [i for _, i, _ in scen]))
+    b.observe()
+    for o in oracles:
+        o.observation()
+    rot = torch.from_numpy(np.stack([[s[2]["rot"][t] for s in scen] for t in range(T)])).cuda().contiguous()
+    ph = torch.from_numpy(np.stack([[s[2]["ph"][t] for s in scen] for t in range(T)])).cuda().contiguous()
+    obs, ast, rew = b.rollout(rot[:100], ph[:100])           # two calls: the second one starts with move_done cleared
+    obs, ast, rew = b.rollout(rot[100:], ph[100:])
+    refs = []
+    for e, o in enumerate(oracles):
+        for t in range(T):
+            r = o.step(scen[e][2]["rot"][t].astype(np.int64), scen[e][2]["ph"][t].astype(np.int64))
+            o.update(philox_uniform(31, e, int(o.s["timestep"]), N))
+        refs.append(r)
+    _cmp_outputs((obs, ast, rew), refs, "last step of the grouped rollout")
+    compare_state(b.export_state(), oracles, "after the grouped rollout", cfg)
+    assert b.stats()["kernel_launches"] > 2 * T
     b.close()
