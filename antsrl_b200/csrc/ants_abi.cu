@@ -483,7 +483,7 @@ int env_args_update(AntsBatch *b, const double *d_noise, ants::EnvArgs *a) {
         b->lazy_abs += 1;
     }
     a->noise = d_noise;
-    a->use_flag = 0;               // (the block-per-env kernels read the wall bit with the record they need anyway)
+    a->use_flag = b->wall_flags_valid;
     a->now = b->lazy_now; a->now_abs = b->lazy_abs;
     a->group = b->env_group; a->cap = b->env_apt * ants::kEnvThreads;
     return ANTS_OK;
@@ -608,6 +608,7 @@ int rollout_grouped(AntsBatch *b, const int8_t *d_rot_tape, const int8_t *d_ph_t
         }
         b->move_done = 0;
         b->prev_synced = 0;
+        b->wall_flags_valid = 1;
         const uint32_t og = next_obs_gen(b);
         rc = for_each_group(b, [&] { return launch_perceive_range(b, og, d_obs, d_as, nullptr, d_reward, 1); });
         if (rc != ANTS_OK) break;

@@ -162,6 +162,12 @@ __device__ __noinline__ void env_push_by_rocks(const Params &p, int e, unsigned 
     *y = env_wrap(*y + sy, (double)p.H);
 }
 
+#ifndef ANTS_ENV_WALLFLAG
+#define ANTS_ENV_WALLFLAG 1        // 1: the move reads the record of the new cell (prefetched) and leaves its wall bit in
+                                   //    wall_hit[] for the coming update; 0: the move only stores the occupancy stamp and the
+                                   //    update reads the wall bit with the record it needs anyway -- one random sector less
+                                   //    per ant, but a dependent DRAM load at the head of the kernel: 0.117 against 0.101 ms
+#endif
 #ifndef ANTS_ENV_MINBLOCKS
 #define ANTS_ENV_MINBLOCKS 4       // resident blocks per SM the register budget allows (4 x 256 threads x 64 registers)
 #endif
@@ -266,9 +272,14 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         // Walls.update (walls.py:24-25): the wall bit of the cell the ant stands on.  This is the ONE random DRAM sector of
         // the ant per iteration: unless a wall or a rock moves it, it is also the cell it deposits on and the cell whose
         // food the mandible rule reads (the move of the previous step only stored the occupancy stamp there).
+        if (ANTS_ENV_WALLFLAG && a.use_flag) {
 #pragma unroll
-        for (int k = 0; k < APT; ++k)
-            in_wall[k] = ld_wall(p, rec_of(el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));
+            for (int k = 0; k < APT; ++k) in_wall[k] = p.wall_hit[i0 + lac[k]] != 0;
+        } else {
+#pragma unroll
+            for (int k = 0; k < APT; ++k)
+                in_wall[k] = ld_wall(p, rec_of(el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));
+        }
         unsigned long long rm[APT];
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
@@ -383,6 +394,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 p.x[i] = x1; p.y[i] = y1; p.theta[i] = t;
                 const int nx = cell_of(x1, W), ny = cell_of(y1, H);
                 newcell[k] = cidx(p, nx, ny); newxy[k] = (nx << 16) | ny;
+                if (ANTS_ENV_WALLFLAG) prefetch_l2(rec_of(el[k], newcell[k]));
             }
         }
         __syncthreads();
@@ -476,6 +488,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 p.x[i] = x; p.y[i] = y; p.theta[i] = t;
                 const int nx = cell_of(x, W), ny = cell_of(y, H);
                 newcell[k] = cidx(p, nx, ny); newxy[k] = (nx << 16) | ny;
+                if (ANTS_ENV_WALLFLAG) prefetch_l2(rec_of(el[k], newcell[k]));
             }
         }
     }
@@ -511,14 +524,17 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             p.act[p.EN + i] = (v != 0 && v != 1) ? a.act_on : 0.0;
         }
     }
-    // Occupancy stamp of the new cell (RL_api.py:136-142), a store without a load: the byte it shares with the anthill bit
-    // of the compact records is rebuilt from the disc test on integers (the same test k_hill_mark wrote the bit with).
-    // Whether the new cell is a wall is read by the coming update, together with everything else it needs of that cell.
+    // Occupancy stamp of the new cell (RL_api.py:136-142) and its wall bit for the coming update.  (ANTS_ENV_WALLFLAG = 0:
+    // the stamp as a store without a load -- the byte it shares with the anthill bit of the compact records is rebuilt from
+    // the disc test on integers, the same test k_hill_mark wrote the bit with -- and the wall bit read by the update.)
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         if (!valid[k]) continue;
         uint8_t *orec = rec_of(el[k], newcell[k]);
-        if (p.rec8 || p.rec16) {
+        if (ANTS_ENV_WALLFLAG) {
+            p.wall_hit[i0 + lac[k]] = ld_wall(p, orec) ? 1 : 0;        // for Walls.update of the coming update
+            st_occ(p, orec, a.occ_gen);
+        } else if (p.rec8 || p.rec16) {
             const bool hill = in_hill(p.hill + 4 * (env0 + el[k]), newxy[k] >> 16, newxy[k] & 0xFFFF);
             orec[p.rec8 ? 6 : 12] = (uint8_t)((hill ? 0x80u : 0u) | (a.occ_gen & 0x7Fu));
         } else {

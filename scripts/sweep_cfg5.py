@@ -42,11 +42,14 @@ def main():
         E = total // world
         t0 = time.perf_counter()
         batch = BatchedAnts(gen.cfg, E, device=local_rank, evap_mode="lazy", record="compact8", rng_seed=5, env_id_base=rank * E)
-        for s0 in range(0, E, SLICE):                      # upload in slices: 65 536 maps never sit in host memory at once
+        # upload in slices (65 536 maps never sit in host memory at once).  Up to 2048 distinct generated maps per rank;
+        # larger batches reuse them cyclically (the environments still diverge: actions and Philox noise are per env id)
+        stacked = stack_states(bench.generate_states_parallel(wl, 10000, rank * E, min(SLICE, E)), "all")
+        for s0 in range(0, E, SLICE):
             n = min(SLICE, E - s0)
-            states = bench.generate_states_parallel(wl, 10000, rank * E + s0, n)
-            batch.import_state(stack_states(states, "all"), envs=(s0, n))
-            del states
+            part = stacked if n == min(SLICE, E) else {k: (v[:n] if hasattr(v, "shape") and v.ndim else v) for k, v in stacked.items()}
+            batch.import_state(part, envs=(s0, n))
+        del stacked
         batch.activate_all_pheromones(np.ones((E, N, 2)) * 10.0)
         rs = np.random.RandomState(7 + rank)
         T = 16
@@ -84,7 +87,7 @@ def main():
                    "device_gb_per_gpu": dev_bytes / 1e9, "setup_s": setup_s}
             rows.append(row)
             sys.stderr.write(json.dumps(row) + "\n")
-    out = {"n_gpus": world, "workload": "cfg5 = cfg3 map: " + wl["desc"].split(",")[0] + ", 256 ants/env, compact8 records, lazy field, "
+    out = {"n_gpus": world, "maps": "up to %d distinct generated maps per rank, reused cyclically beyond that" % SLICE, "workload": "cfg5 = cfg3 map: " + wl["desc"].split(",")[0] + ", 256 ants/env, compact8 records, lazy field, "
            "one ants_rollout call per %d steps" % 16, "rows": rows}
     if rank == 0 and world == 1 and not os.environ.get("SWEEP_NO_CPU"):
         out["cpu_reference"] = bench.run_cpu_baseline(wl, 3, int(os.environ.get("SWEEP_CPU_STEPS", "60")))
