@@ -196,7 +196,7 @@ struct AntsBatch {
     int perceive_smem = 0, perceive_layout = 0, perceive_group = 4, perceive_threads = 128, perceive_slow_wrap = 0;
     int perceive_rows = 0, rows_smem = 0;   // 1 = k_perceive_rows serves this configuration (default channel list, 7x7 window)
     // block-per-environment kernels (ants_env_fused.cuh): move / update / update+move in one launch each
-    int fused = 0, env_group = 1, env_apt = 4, env_smem = 0;
+    int fused = 0, env_group = 1, env_apt = 4, env_smem = 0, env_tpb = 256;
     int move_done = 0;              // ants_rollout: the move of the coming step already ran inside the last update launch
     // packed observation transport of the host-buffer path (ants_pack.cuh)
     AntsPackedLayout pack_layout;
@@ -450,7 +450,9 @@ void launch_env(AntsBatch *b, ants::EnvArgs a) {
     a.env_base = b->cur_stream ? b->cur_env0 : 0;
     a.env_end = b->cur_stream ? b->cur_env1 : p.E;
     const unsigned grid = (unsigned)cdiv(a.env_end - a.env_base, b->env_group);
-    if (b->env_apt == 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
+    if (b->env_tpb == 512) launch_step(b, ants::k_env<UPDATE, MOVE, 2, 512>, grid, 512u, (size_t)b->env_smem, p, a);
+    else if (b->env_tpb == 1024) launch_step(b, ants::k_env<UPDATE, MOVE, 1, 1024>, grid, 1024u, (size_t)b->env_smem, p, a);
+    else if (b->env_apt == 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
     else if (b->env_apt == 2) launch_step(b, ants::k_env<UPDATE, MOVE, 2>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
     else launch_step(b, ants::k_env<UPDATE, MOVE, 4>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
 }
@@ -1004,6 +1006,8 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
                     !getenv("ANTS_NO_FUSED")) ? 1 : 0;
         b->env_group = g;
         b->env_apt = cap / ants::kEnvThreads;
+        if (cap == 1024)               // experiment: the 1024-ant block as 512 threads x 2 ants or 1024 x 1
+            if (const char *x = getenv("ANTS_ENV_TPB")) { const int t = atoi(x); if (t == 512 || t == 1024) b->env_tpb = t; }
         // The block-per-environment kernel is heavy (256 threads x 64 registers, 33 KB of shared memory): launched as a
         // programmatic dependent it sits on the SMs waiting for the perception kernel and takes registers and shared
         // memory from it (measured: rollouts 0.37-0.61 ms per step against 0.36 for separate launches), so the pair

@@ -171,11 +171,11 @@ __device__ __noinline__ void env_push_by_rocks(const Params &p, int e, unsigned 
 #ifndef ANTS_ENV_MINBLOCKS
 #define ANTS_ENV_MINBLOCKS 4       // resident blocks per SM the register budget allows (4 x 256 threads x 64 registers)
 #endif
-template <bool UPDATE, bool MOVE, int APT>
-__global__ void __launch_bounds__(kEnvThreads, ANTS_ENV_MINBLOCKS)
+template <bool UPDATE, bool MOVE, int APT, int TPB = kEnvThreads>
+__global__ void __launch_bounds__(TPB, (ANTS_ENV_MINBLOCKS * kEnvThreads) / TPB)
 k_env(const __grid_constant__ Params p, const EnvArgs a) {
     pdl_begin();
-    constexpr int CAP = APT * kEnvThreads;
+    constexpr int CAP = APT * TPB;
     extern __shared__ __align__(16) unsigned char env_smem[];
     double *xs = reinterpret_cast<double *>(env_smem);                 // [CAP] positions between the phases
     double *ys = xs + CAP;
@@ -203,9 +203,9 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             else { seen_and = true; rule_mode = seen_or ? 3 : 2; }
         }
     }
-    for (int k = tid; k < 2 * CAP; k += kEnvThreads) { hkeys[k] = 0u; hvals[k] = 0u; }
+    for (int k = tid; k < 2 * CAP; k += TPB) { hkeys[k] = 0u; hvals[k] = 0u; }
     if (UPDATE && p.R > 0)
-        for (int k = tid; k < n_env * p.R; k += kEnvThreads) touch[k] = 0u;
+        for (int k = tid; k < n_env * p.R; k += TPB) touch[k] = 0u;
 
     // Per-ant values that live across the barriers (unrolled: registers).  Loads of the APT ants of a thread are issued
     // together, with the index of an idle slot clamped to the block's last ant: the kernel lives on memory-level
@@ -219,7 +219,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     bool valid[APT];
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
-        const int la = tid + k * kEnvThreads;
+        const int la = tid + k * TPB;
         valid[k] = la < n_loc;
         lac[k] = valid[k] ? la : (n_loc - 1);
         el[k] = a.group == 1 ? 0 : lac[k] / p.N;
@@ -239,7 +239,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             const uint32_t cnt = p.absorb_count[e];
             if (cnt == 0u) continue;
             if (cnt <= (uint32_t)p.N) {
-                for (uint32_t k = tid; k < cnt; k += kEnvThreads) env_absorb_cell(p, e, (int)p.absorb_list[(int64_t)e * p.N + k]);
+                for (uint32_t k = tid; k < cnt; k += TPB) env_absorb_cell(p, e, (int)p.absorb_list[(int64_t)e * p.N + k]);
             } else {
                 // more cells were queued than the env's segment holds (several steps without an update): sweep the disc
                 const int32_t *hl = p.hill + 4 * e;
@@ -247,7 +247,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
                 const int x0 = max(hl[0] - r, 0), x1 = min(hl[0] + r, W - 1), y0 = max(hl[1] - r, 0), y1 = min(hl[1] + r, H - 1);
                 const int bw = x1 - x0 + 1, bh = y1 - y0 + 1;
                 if (bw > 0 && bh > 0)
-                    for (int t = tid; t < bw * bh; t += kEnvThreads) {
+                    for (int t = tid; t < bw * bh; t += TPB) {
                         const int cx = x0 + t / bh, cy = y0 + t % bh;
                         if (in_hill(hl, cx, cy)) env_absorb_cell(p, e, cidx(p, cx, cy));
                     }
@@ -307,7 +307,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             //      touched ant-chunks in ant order (= np.sum(axis=0); untouched ants add exact 0), moves the rock and
             //      its rock-grid entries
             const int warp = tid >> 5, lane = tid & 31;
-            for (int pr = warp; pr < n_env * p.R; pr += kEnvThreads / 32) {
+            for (int pr = warp; pr < n_env * p.R; pr += TPB / 32) {
                 uint32_t tm = touch[pr];
                 if (tm == 0u) continue;
                 const int g = pr / p.R, r = pr - g * p.R, e = env0 + g;

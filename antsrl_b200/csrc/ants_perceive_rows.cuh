@@ -83,6 +83,10 @@ template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 
 #ifndef ANTS_ROWS_UNR
 #define ANTS_ROWS_UNR 7
 #endif
+#ifndef ANTS_ROWS_PIPE
+#define ANTS_ROWS_PIPE 0           // 1 = the record loads of the NEXT chunk are issued before the current chunk is decoded
+                                   // (double-buffered registers; compact records only)
+#endif
 #ifndef ANTS_ROWS_PREFETCH
 #define ANTS_ROWS_PREFETCH 0       // samples of the NEXT chunk's row whose records are prefetched into L2 (0 = off, S = all).
                                    // Measured on the cfg4 shard: 0.240 ms without, 0.254 with 4, 0.269 with 7 -- the
@@ -212,8 +216,10 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     float *wobs0 = s_obs + warp * kRowsTiles * TILE;
     constexpr bool kLateWait = (UNR >= S);
     // one row: sample cells, record loads, decode, staging-tile stores; returns the row's count of unexplored samples
+    // phase 2 = the whole row; phase 0 = only issue the record loads into (lo, hi, cell); phase 1 = only consume them
     auto row_body = [&](const RowPrep &q, const double offY, const uint32_t mrow, const uint32_t orow_s,
-                        const uint32_t amask, const RowPrep *qn) -> int {
+                        const uint32_t amask, const RowPrep *qn, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR],
+                        const int phase) -> int {
         const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
         const int e = q.e;
         const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
@@ -224,8 +230,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         int cnt = 0;
 #pragma unroll
         for (int j0 = 0; j0 < S; j0 += UNR) {
-            uint4 lo[UNR], hi[UNR];
-            uint32_t cell[UNR];
+            if (phase != 1) {
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
                 const int j = j0 + u;
@@ -253,6 +258,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     if (REC == 0) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
                 }
             }
+            }
+            if (phase == 0) return 0;
             if (ANTS_ROWS_PREFETCH > 0 && qn != nullptr && j0 == 0) {
                 // (experiment, off by default) while this row's record loads are in flight: prefetch the same row of the
                 // ant this lane serves in the NEXT chunk.  ncu (bench batch) showed 30 % of all warp stall samples on the
@@ -437,7 +444,9 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             const uint32_t amask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
             if (lane < nrows) {
                 const uint32_t orow_s = tiles_s + (uint32_t)((((la >> 2) & 1) * TILE + ((la & 3) * S2 + li * S) * C) * 4);
-                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask, nullptr);
+                uint4 lo[UNR], hi[UNR];
+                uint32_t cell[UNR];
+                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask, nullptr, lo, hi, cell, 2);
                 s_rowcnt[(warp * 32 + la) * S + li] = (uint8_t)cnt;
             }
             const bool last = nrows <= 32;
@@ -467,9 +476,12 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         for (int t = 0; t < kRowsTiles; ++t)
                             asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s0 + (uint32_t)((t * TILE + j * C + c) * 4)), "f"(-1.f) : "memory");
         }
-        for (int g = 0; g < 32; g += G) {
+        constexpr bool PIPE = (ANTS_ROWS_PIPE != 0) && REC != 0 && UNR >= S && kRowsTiles == 1;
+        uint4 loA[UNR], hiA[UNR], loB[UNR], hiB[UNR];
+        uint32_t cellA[UNR], cellB[UNR];
+        // one chunk of 4 ants: (issue +) decode + flush
+        auto chunk = [&](const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR], const int phase) {
             const int64_t i0 = wbase + g;
-            if (i0 >= ant_end) break;
             const int n_in = (ant_end - i0 < G) ? (int)(ant_end - i0) : G;
             const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
             float *wobs = wobs0 + tsel * TILE;
@@ -481,10 +493,34 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             }
             if (lane_on && la < n_in) {
                 const RowPrep *qn = (g + G < 32 && i0 + G + la < ant_end) ? &prep[warp * 32 + g + G + la] : nullptr;
-                const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn);
+                const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, phase);
                 s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
             }
             flush(wobs, i0, n_in);
+        };
+        // the record loads of a chunk alone
+        auto issue = [&](const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR]) {
+            const int64_t i0 = wbase + g;
+            if (g < 32 && i0 < ant_end && lane_on && i0 + la < ant_end)
+                row_body(prep[warp * 32 + g + la], offY, mrow, 0u, 0u, nullptr, lo, hi, cell, 0);
+        };
+        if (PIPE) {
+            // chunk g + 1 is on its way while chunk g is decoded: two register sets, the loop unrolled by two so that
+            // neither is indexed dynamically
+            issue(0, loA, hiA, cellA);
+            for (int g = 0; g < 32; g += 2 * G) {
+                if (wbase + g >= ant_end) break;
+                issue(g + G, loB, hiB, cellB);
+                chunk(g, loA, hiA, cellA, 1);
+                if (wbase + g + G >= ant_end) break;
+                issue(g + 2 * G, loA, hiA, cellA);
+                chunk(g + G, loB, hiB, cellB, 1);
+            }
+        } else {
+            for (int g = 0; g < 32; g += G) {
+                if (wbase + g >= ant_end) break;
+                chunk(g, loA, hiA, cellA, 2);
+            }
         }
     }
     __syncwarp();

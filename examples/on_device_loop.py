@@ -23,6 +23,7 @@ import bench         # noqa: E402
 from antsrl_b200 import BatchedAnts                      # noqa: E402
 from antsrl_b200.generator import stack_states           # noqa: E402
 from antsrl_b200.replay import DeviceReplayMemory        # noqa: E402
+from antsrl_b200.device_loop import DeviceActionSelector  # noqa: E402
 
 
 class TwoHeadPolicy(torch.nn.Module):                    # the shape of CollectModel (collect_agent.py:20-58)
@@ -57,6 +58,7 @@ def main():
     C = len(gen.cfg["channels"])
     policy = TwoHeadPolicy(49 * C, 2).cuda().half()
     mem = DeviceReplayMemory(a.replay, (7, 7, C), (2,), 2)
+    selector = DeviceActionSelector(env, a.epsilon, seed=1234)
     obs, ast, _, _ = env.observe()                                               # main.py:88
     obs, ast = obs.clone(), ast.clone()
     total_reward = torch.zeros((), dtype=torch.float64, device="cuda")
@@ -68,12 +70,7 @@ def main():
             total_reward.zero_()
         with torch.no_grad():                                                    # collect_agent.py:161-177
             q_rot, q_ph = policy(obs.reshape(E * N, -1).half(), ast.reshape(E * N, 2).half())
-            rot = (q_rot.argmax(1) - 1).to(torch.int8).reshape(E, N)
-            ph = q_ph.argmax(1).to(torch.int8).reshape(E, N)
-            r_rot, r_ph = env.sample_actions(seed=1234)
-            explore = torch.rand((E, 1), device="cuda") < a.epsilon               # per environment, like the reference
-            rot = torch.where(explore, r_rot, rot)
-            ph = torch.where(explore, r_ph, ph)
+            rot, ph, _ = selector.select(q_rot, q_ph)                            # argmax, or explore, per environment
         new_obs, new_ast, rew, done = env.step(rot, ph)                          # main.py:98
         mem.extend(obs, ast, (rot, ph), rew, new_obs, new_ast, done)             # main.py:102
         env.update(None)                                                         # main.py:131
