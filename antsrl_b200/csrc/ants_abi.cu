@@ -450,11 +450,12 @@ void launch_env(AntsBatch *b, ants::EnvArgs a) {
     a.env_base = b->cur_stream ? b->cur_env0 : 0;
     a.env_end = b->cur_stream ? b->cur_env1 : p.E;
     const unsigned grid = (unsigned)cdiv(a.env_end - a.env_base, b->env_group);
-    if (b->env_tpb == 512) launch_step(b, ants::k_env<UPDATE, MOVE, 2, 512>, grid, 512u, (size_t)b->env_smem, p, a);
-    else if (b->env_tpb == 1024) launch_step(b, ants::k_env<UPDATE, MOVE, 1, 1024>, grid, 1024u, (size_t)b->env_smem, p, a);
-    else if (b->env_apt == 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
-    else if (b->env_apt == 2) launch_step(b, ants::k_env<UPDATE, MOVE, 2>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
-    else launch_step(b, ants::k_env<UPDATE, MOVE, 4>, grid, (unsigned)ants::kEnvThreads, (size_t)b->env_smem, p, a);
+    const int shape = b->env_tpb * 8 + b->env_apt;                 // (threads per block, ants per thread)
+    if (shape == 512 * 8 + 2) launch_step(b, ants::k_env<UPDATE, MOVE, 2, 512>, grid, 512u, (size_t)b->env_smem, p, a);
+    else if (shape == 512 * 8 + 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1, 512>, grid, 512u, (size_t)b->env_smem, p, a);
+    else if (shape == 1024 * 8 + 1) launch_step(b, ants::k_env<UPDATE, MOVE, 1, 1024>, grid, 1024u, (size_t)b->env_smem, p, a);
+    else if (shape == 256 * 8 + 4) launch_step(b, ants::k_env<UPDATE, MOVE, 4, 256>, grid, 256u, (size_t)b->env_smem, p, a);
+    else launch_step(b, ants::k_env<UPDATE, MOVE, 1, 256>, grid, 256u, (size_t)b->env_smem, p, a);
 }
 
 // host bookkeeping at the start of a step: generation folds, the step's occupancy generation, the move's arguments
@@ -464,7 +465,7 @@ void env_args_move(AntsBatch *b, const int8_t *d_rot, const int8_t *d_ph, ants::
     a->occ_gen = next_occ_gen(b);
     a->all_stamp = b->prev_synced ? 0 : 1;
     a->act_on = b->act_bool ? 1.0 : 256.0;
-    a->group = b->env_group; a->cap = b->env_apt * ants::kEnvThreads;
+    a->group = b->env_group; a->cap = b->env_apt * b->env_tpb;
 }
 // ... of an update: timestep, the lazy field's counters (a fold of plain values / expired deposits before they wrap)
 int env_args_update(AntsBatch *b, const double *d_noise, ants::EnvArgs *a) {
@@ -487,7 +488,7 @@ int env_args_update(AntsBatch *b, const double *d_noise, ants::EnvArgs *a) {
     a->noise = d_noise;
     a->use_flag = b->wall_flags_valid;
     a->now = b->lazy_now; a->now_abs = b->lazy_abs;
-    a->group = b->env_group; a->cap = b->env_apt * ants::kEnvThreads;
+    a->group = b->env_group; a->cap = b->env_apt * b->env_tpb;
     return ANTS_OK;
 }
 
@@ -796,7 +797,9 @@ int ensure_packed(AntsBatch *b) {
     TRY(dev_alloc(b, &b->d_pack_fail, 1));
     if (cudaHostAlloc((void **)&b->h_packed, (size_t)bytes + 64, cudaHostAllocDefault) != cudaSuccess)
         return fail(ANTS_E_ALLOC, "cudaHostAlloc of %lld bytes (packed observation staging) failed", (long long)bytes);
-    b->chunk_ev.resize(16);
+    int max_chunks = 16;
+    if (const char *x = getenv("ANTS_E2E_CHUNKS")) max_chunks = atoi(x) < 1 ? 1 : (atoi(x) > 256 ? 256 : atoi(x));
+    b->chunk_ev.resize(max_chunks);
     for (auto &e : b->chunk_ev)
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess)
             return fail(ANTS_E_CUDA, "cudaEventCreate failed");
@@ -820,7 +823,7 @@ int packed_transfer(AntsBatch *b, uint8_t *h_dst, float *h_obs, float *h_agent_s
     }
     const int64_t n_packed = EN - n_dense;
     CK(cudaMemsetAsync(b->d_pack_fail, 0, sizeof(uint32_t), b->stream));
-    int n_chunks = (int)(n_packed / 16384);
+    int n_chunks = (int)(n_packed / (b->chunk_ev.size() > 16 ? 2048 : 16384));
     n_chunks = n_chunks < 1 ? 1 : (n_chunks > (int)b->chunk_ev.size() ? (int)b->chunk_ev.size() : n_chunks);
     const int64_t per = (cdiv(n_packed > 0 ? n_packed : 1, n_chunks) + 63) / 64 * 64;
     int used = 0;
@@ -1005,9 +1008,12 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         b->fused = ((p.lazy || p.P == 0) && cfg->diffuse_factor == 0.0 && p.N <= 1024 && p.plane < 0xFFFFFFF0ll &&
                     !getenv("ANTS_NO_FUSED")) ? 1 : 0;
         b->env_group = g;
-        b->env_apt = cap / ants::kEnvThreads;
-        if (cap == 1024)               // experiment: the 1024-ant block as 512 threads x 2 ants or 1024 x 1
-            if (const char *x = getenv("ANTS_ENV_TPB")) { const int t = atoi(x); if (t == 512 || t == 1024) b->env_tpb = t; }
+        // block shape: one ant per thread up to 512 ants per block; a 1024-ant block as 512 threads x 2 ants (measured
+        // on the cfg4 shard: 0.090 ms against 0.111 for 256 x 4 and 0.098 for 1024 x 1; ANTS_ENV_TPB selects those)
+        b->env_tpb = cap <= 256 ? 256 : 512;
+        if (cap == 1024)
+            if (const char *x = getenv("ANTS_ENV_TPB")) { const int t = atoi(x); if (t == 256 || t == 1024) b->env_tpb = t; }
+        b->env_apt = cap / b->env_tpb;
         // The block-per-environment kernel is heavy (256 threads x 64 registers, 33 KB of shared memory): launched as a
         // programmatic dependent it sits on the SMs waiting for the perception kernel and takes registers and shared
         // memory from it (measured: rollouts 0.37-0.61 ms per step against 0.36 for separate launches), so the pair

@@ -4,8 +4,9 @@
 // ants_kernels.cuh) split the iteration wherever "all ants of an environment have finished phase k" is needed -- the
 // last-writer scatters of the reference (quirk Q1: ants.py:116, pheromone.py:39), the ordered sum of the ants' pushes
 // on a rock (circle_obstacles.py:38-40) -- and resolve the scatters through a global `owner` array (atomicMax per ant,
-// re-read by a follow-up kernel: two random DRAM sectors per ant and scatter).  Here a block of 256 threads owns G
-// consecutive environments (G * N <= CAP ants, CAP in {256, 512, 1024}; a thread handles CAP / 256 ants), so those
+// re-read by a follow-up kernel: two random DRAM sectors per ant and scatter).  Here a block owns G consecutive
+// environments (G * N <= CAP ants, CAP in {256, 512, 1024}: 256 or 512 threads with one ant each, or 512 threads with two
+// for the 1024-ant block -- measured 0.090 ms on the cfg4 shard against 0.111 for 256 x 4 and 0.098 for 1024 x 1), so those
 // phase boundaries are block barriers, the owner of a cell is found in a shared-memory hash table
 // (cell -> highest ant index, atomicCAS / atomicMax on shared memory) and the rock pushes are summed from positions
 // staged in shared memory.  Per iteration of `update(); step()` the ants' state is read and written once, and the

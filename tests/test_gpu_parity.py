@@ -616,6 +616,17 @@ def test_partial_import_keeps_scalars():
     b.close()
 
 
+@pytest.mark.parametrize("tpb", [256, 1024])
+def test_block_shapes_of_the_env_kernel(tpb, monkeypatch):
+    """The 1024-ant block of k_env as 256 threads x 4 ants and as 1024 x 1 (ANTS_ENV_TPB; the default 512 x 2 runs in
+    every other 513..1024-ant test): a rollout and a step / update loop against the oracle."""
+    monkeypatch.setenv("ANTS_ENV_TPB", str(tpb))
+    test_rollout_matches_oracle("compact8", 5, 1000, 2, 1, monkeypatch)
+    kw = dict(seed=1800, w=72, h=64, n_ants=700, n_rocks=4, steps=12, n_walls=5, n_food=12)
+    rep = run_parity(_variants(kw, 2), evap_mode="lazy", record="compact8")
+    assert rep["state_checks"] == 12
+
+
 @pytest.mark.parametrize("groups", [1, 4], ids=["one_stream", "four_groups"])
 @pytest.mark.parametrize("record,n_rocks,n_ants,n_envs", [("compact8", 6, 300, 3), ("compact8", 0, 50, 7), ("compact", 4, 520, 2),
                                                           ("f64", 3, 1024, 2), ("compact8", 2, 1100, 2)])
