@@ -8,4 +8,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 WARM=300 python scripts/r2_prof.py > gpurun_out/${TAG}_plain2.log 2>&1 &&
 WARM=300 ncu --set full --clock-control none --import-source on -k regex:k_env -s 300 -c 1 -f -o gpurun_out/${TAG}_k_env python scripts/r2_prof.py > gpurun_out/${TAG}_ncu1.log 2>&1
 WARM=300 ncu --set full --clock-control none --import-source on -k regex:k_perceive_rows -s 300 -c 1 -f -o gpurun_out/${TAG}_k_perceive python scripts/r2_prof.py > gpurun_out/${TAG}_ncu2.log 2>&1
+ANTS_ROLLOUT_GROUPS=1 WARM=300 ncu --set full --clock-control none --import-source on -k regex:k_perceive_rows -s 300 -c 1 -f -o gpurun_out/${TAG}_k_perceive_whole python scripts/r2_prof.py > gpurun_out/${TAG}_ncu3.log 2>&1
 ls -la gpurun_out/${TAG}_*

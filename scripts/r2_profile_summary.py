@@ -4,7 +4,8 @@ captures of the two kernels of the step (k_perceive_rows, k_env) at the bench ba
 import csv, json, os, subprocess, sys
 from collections import defaultdict
 tag = sys.argv[1]
-ANTS = int(sys.argv[2]) if len(sys.argv) > 2 else 524288
+BATCH = int(sys.argv[2]) if len(sys.argv) > 2 else 524288
+GROUPS = int(sys.argv[3]) if len(sys.argv) > 3 else 4     # ants_rollout splits the batch into env groups: one launch = BATCH / GROUPS ants
 lines = ["# Round 2 - %s" % tag, "",
          "All under gpurun on one B200, `--clock-control none`, each command run plain (exit 0) right before its ncu run.", ""]
 lc = "gpurun_out/%s_launches.csv" % tag
@@ -34,15 +35,18 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__average_warp_latency_per_inst_issued.ratio",
         "smsp__thread_inst_executed_per_inst_executed.ratio"]
 scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}
-for kern in ("k_perceive", "k_env"):
+for kern in ("k_perceive", "k_env", "k_perceive_whole"):
     rep = "gpurun_out/%s_%s.ncu-rep" % (tag, kern)
     if not os.path.exists(rep):
         continue
+    ANTS = BATCH if kern.endswith("_whole") else BATCH // GROUPS
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, r = rows[0], rows[1], rows[2]
     g = lambda k: r[hdr.index(k)] if k in hdr else "n/a"
-    lines += ["## `%s` after 300 steps of the cfg4 shard (512 envs x 1024 ants; `ncu --set full --import-source on`)" % g("Kernel Name")[:60], "",
+    lines += ["## `%s` after 300 steps of the cfg4 shard (512 envs x 1024 ants; this launch: %d ants = %s; `ncu --set full --import-source on`)"
+              % (g("Kernel Name")[:60], ANTS, "the whole batch (ANTS_ROLLOUT_GROUPS=1, like bench.py's per-kernel pass)" if ANTS == BATCH
+                 else "one of %d env groups of ants_rollout" % GROUPS), "",
               "| metric | value |", "|---|---|"]
     for k in KEYS:
         if k in hdr:
@@ -56,8 +60,8 @@ for kern in ("k_perceive", "k_env"):
     wr = float(g("dram__bytes_write.sum")) * scale[units[hdr.index("dram__bytes_write.sum")]]
     lines += ["DRAM traffic of this launch: %.1f MB read + %.1f MB written = %.0f B per ant; %.0f warp-instructions per ant."
               % (rd / 1e6, wr / 1e6, (rd + wr) / ANTS, float(g("smsp__inst_executed.sum")) / ANTS), ""]
-    if kern == "k_perceive":
-        json.dump({"kernel": "k_perceive", "tag": "%s_k_perceive (%d ants per launch, after 300 steps)" % (tag, ANTS),
+    if kern == "k_perceive_whole":
+        json.dump({"kernel": "k_perceive", "tag": "%s_k_perceive_whole (%d ants per launch, after 300 steps)" % (tag, ANTS),
                    "dram_bytes_per_ant": (rd + wr) / ANTS, "ants": ANTS, "dram_bytes_read": rd, "dram_bytes_write": wr},
                   open("profiles/latest_traffic.json", "w"))
 open("profiles/%s.md" % tag, "w").write("\n".join(lines) + "\n")
