@@ -19,7 +19,10 @@
 
 namespace ants {
 
-constexpr int kRowsThreads = 128;
+#ifndef ANTS_ROWS_THREADS
+#define ANTS_ROWS_THREADS 128
+#endif
+constexpr int kRowsThreads = ANTS_ROWS_THREADS;
 constexpr int kRowsGroup = 4;
 #ifndef ANTS_ROWS_FLAT
 #define ANTS_ROWS_FLAT 0           // 1 = hand the 32 * S rows of a warp to the lanes without idle lanes (measured slower: 0.279 vs 0.241 ms)
@@ -78,10 +81,28 @@ __device__ __noinline__ float rock_channel(const Params &p, int e, unsigned long
 
 template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 16-byte, 2 = compact 8-byte
 #ifndef ANTS_ROWS_OCC
-#define ANTS_ROWS_OCC (ANTS_ROWS_FLAT ? 4 : 5)   // resident blocks per SM the register budget allows (shared memory: 4 / 5)
+#define ANTS_ROWS_OCC ((ANTS_ROWS_FLAT ? 4 : 5) * 128 / ANTS_ROWS_THREADS)   // resident blocks per SM the register budget allows (shared memory: 4 / 5 of 128 threads)
 #endif
 #ifndef ANTS_ROWS_UNR
 #define ANTS_ROWS_UNR 7
+#endif
+#ifndef ANTS_ROWS_ROCKS_WARP
+#define ANTS_ROWS_ROCKS_WARP 1     // 1 = the rock channel of an ant whose window a rock may reach is evaluated by the whole
+                                   // warp (its S*S samples over the lanes, ballots back to the row lanes) instead of by the
+                                   // ant's S row lanes while the other rows of the chunk idle
+#endif
+#ifndef ANTS_ROWS_MAGIC
+#define ANTS_ROWS_MAGIC 1          // 1 = 8-byte records: (float)age through the 2^23 exponent trick (PRMT + FFMA) instead of I2F + FMUL
+#endif
+#ifndef ANTS_ROWS_BASE64
+#define ANTS_ROWS_BASE64 1         // 1 = the environment's record base as one opaque 64-bit register (one IMAD.WIDE per sample address)
+#endif
+#ifndef ANTS_ROWS_FULLWARP
+#define ANTS_ROWS_FULLWARP 0       // 1 = a warp with all of its 32 ants runs a copy of the chunk loop without the ragged-end bookkeeping
+#endif
+#ifndef ANTS_ROWS_SYM
+#define ANTS_ROWS_SYM 1            // 1 = the window offsets are (j - radius) * DELTA (RL_api.py:92-93), so ct * X and st * X are
+                                   // computed for the positive columns only: a product's sign flips exactly with its factor's
 #endif
 #ifndef ANTS_ROWS_PIPE
 #define ANTS_ROWS_PIPE 0           // 1 = the record loads of the NEXT chunk are issued before the current chunk is decoded
@@ -116,85 +137,110 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const int64_t base = ant0 + (int64_t)blockIdx.x * kRowsThreads;
     const bool explore_on = p.explore_on != 0;
 
-    // ---- phase A (thread per ant): frame, reward terms that do not need the exploration count, small outputs
+    // ---- phase A (thread per ant): frame, reward terms that do not need the exploration count, small outputs.
+    // The kernel's pointers may alias as far as the compiler knows, so a load after a store waits for it: every load
+    // of the ant's state is issued first, the stores come last, and the dependent chain is state -> rock grid word ->
+    // rock discs (ncu, round 2: phase A / C were 12 % of the instructions and 29 % of the warps' stall samples).
     double r_other = 0.0, r_mult = 1.0;
+    int my_rock_flags = 0;
+    int rs_prev = 0;                                                           // reward_state, used by phase C
     {
         const int64_t i = base + tid;
         if (i < ant_end) {
             const int e = (int)(i / p.N);
             const double x = p.x[i], y = p.y[i], th = p.theta[i], hold = p.holding[i];
+            const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
+            const double pdist = (p.reward_kind == 0) ? p.rw_prev_dist[i] : 0.0;
+            const int32_t *hl = p.hill + 4 * e;
+            const int32_t hx = hl[0], hy = hl[1];
+            const float seed_f = (float)p.seed[i];
+            const uint8_t mand = p.mandibles[i];
+            const bool want_state = state_out != nullptr;
+            const double act0 = (want_state && p.P > 0) ? p.act[i] : 0.0;
+            const double act1 = (want_state && p.P > 1) ? p.act[(int64_t)p.EN + i] : 0.0;
+            if (is_step) rs_prev = p.reward_state[i];
             double s0, c0, st, ct;
             sincos(th, &s0, &c0);
-            sincos(th + 3.141592653589793 * 0.5, &st, &ct);                    // RL_api.py:101,107-108
             RowPrep q;
-            q.ct = ct; q.st = st;
             q.xf = x; q.yf = y;
-            if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // :103-104
+            if (p.fwd_delta != 0.0) { q.xf = x + c0 * p.fwd_delta; q.yf = y + s0 * p.fwd_delta; }   // RL_api.py:103-104
             q.e = e;
-            const int32_t *hl = p.hill + 4 * e;
-            const double hprev = rw_alias ? hold : p.rw_holding_prev[i];       // Q18
+            // grid candidates (the word is on its way while the frame and the reward terms are computed)
+            unsigned long long rm = (LAYOUT == 2) ? rock_candidates(p, e, q.xf, q.yf) : 0ull;
+            sincos(th + 3.141592653589793 * 0.5, &st, &ct);                    // RL_api.py:101,107-108
+            q.ct = ct; q.st = st;
             const double d = hold - hprev;
+            double nd = 0.0;
             if (p.reward_kind == 0) {                                          // All_Rewards, reward_custom.py:79-106
                 const double r_food = d < 0.0 ? 0.0 : d;
                 const double r_hill = d < 0.0 ? 1.0 : 0.0;
-                const double ddx = x - (double)hl[0], ddy = y - (double)hl[1];
-                const double nd = sqrt(ddx * ddx + ddy * ddy);
-                const double heading = (p.rw_prev_dist[i] > nd && hold > 0.0) ? 0.1 : 0.0;
-                p.rw_prev_dist[i] = nd;
+                const double ddx = x - (double)hx, ddy = y - (double)hy;
+                nd = sqrt(ddx * ddx + ddy * ddy);
+                const double heading = (pdist > nd && hold > 0.0) ? 0.1 : 0.0;
                 r_other = r_food * p.f_food + r_hill * p.f_anthill + heading * p.f_heading;
                 r_mult = (hold == 0.0) ? p.f_explore : p.f_explore_hold;
-                p.rw_holding_prev[i] = hold;
             } else if (p.reward_kind == 2) {                                   // Food_Reward, :37-40
                 r_other = d < 0.0 ? 10.0 : d;
-                p.rw_holding_prev[i] = hold;
             }
-            unsigned long long rm = 0ull;
-            if (LAYOUT == 2) {
-                // grid candidates, narrowed to the rocks whose disc can reach the window: a sample lies within
-                // radius*DELTA*sqrt(2) + 0.5 (rounding) of (xf, yf) on the torus
-                rm = rock_candidates(p, e, q.xf, q.yf);
-                if (rm) {
-                    const double *rc = p.rock_c + (int64_t)e * p.R * 2;
-                    const double *rr = p.rock_rad + (int64_t)e * p.R;
-                    const double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.0;
-                    unsigned long long keep = 0ull, it = rm;
-                    while (it) {
-                        const int r = __ffsll((long long)it) - 1;
-                        it &= it - 1;
-                        double dx = fabs(q.xf - rc[2 * r]), dy = fabs(q.yf - rc[2 * r + 1]);
-                        dx = fmin(dx, fabs((double)p.W - dx));
-                        dy = fmin(dy, fabs((double)p.H - dy));
-                        const double L = rr[r] + reach;
-                        if (dx < L && dy < L) keep |= 1ull << r;
-                    }
-                    rm = keep;
+            q.flags = 0;
+            q.rcx = q.rcy = 0.0; q.rrad = -1.0;
+            q.rocks = 0ull;
+            if (LAYOUT == 2 && rm) {
+                // narrowed to the rocks whose disc can reach the window: a sample lies within
+                // radius*DELTA*sqrt(2) + 0.5 (rounding) of (xf, yf) on the torus.  The discs of the first two
+                // candidates are loaded together (more than two are rare)
+                const double *rc = p.rock_c + (int64_t)e * p.R * 2;
+                const double *rr = p.rock_rad + (int64_t)e * p.R;
+                const double reach = (double)p.radius * p.delta * 1.4142135623730951 + 1.0;
+                auto near = [&](double cx, double cy, double rad) -> bool {
+                    double dx = fabs(q.xf - cx), dy = fabs(q.yf - cy);
+                    dx = fmin(dx, fabs((double)p.W - dx));
+                    dy = fmin(dy, fabs((double)p.H - dy));
+                    const double L = rad + reach;
+                    return dx < L && dy < L && dx * dx + dy * dy < L * L;
+                };
+                const int ra = __ffsll((long long)rm) - 1;
+                unsigned long long it = rm & (rm - 1);
+                const int rb = it ? __ffsll((long long)it) - 1 : ra;
+                it &= it - 1;
+                const double ax = rc[2 * ra], ay = rc[2 * ra + 1], arad = rr[ra];
+                const double bx = rc[2 * rb], by = rc[2 * rb + 1], brad = rr[rb];
+                const bool ka = near(ax, ay, arad), kb = (rb != ra) && near(bx, by, brad);
+                unsigned long long keep = (ka ? 1ull << ra : 0ull) | (kb ? 1ull << rb : 0ull);
+                while (it) {
+                    const int r = __ffsll((long long)it) - 1;
+                    it &= it - 1;
+                    if (near(rc[2 * r], rc[2 * r + 1], rr[r])) keep |= 1ull << r;
                 }
-            }
-            {
-                q.flags = 0;
-                q.rcx = q.rcy = 0.0; q.rrad = -1.0;
-                if (rm) {
-                    const int r = __ffsll((long long)rm) - 1;
-                    rm &= rm - 1;
-                    q.rcx = p.rock_c[((int64_t)e * p.R + r) * 2];
-                    q.rcy = p.rock_c[((int64_t)e * p.R + r) * 2 + 1];
-                    q.rrad = p.rock_rad[(int64_t)e * p.R + r];
-                    q.flags |= rm ? 6 : 2;
+                if (keep) {
+                    const int r = __ffsll((long long)keep) - 1;            // the first candidate rides in the prep record
+                    keep &= keep - 1;
+                    if (r == ra) { q.rcx = ax; q.rcy = ay; q.rrad = arad; }
+                    else if (r == rb) { q.rcx = bx; q.rcy = by; q.rrad = brad; }
+                    else { q.rcx = rc[2 * r]; q.rcy = rc[2 * r + 1]; q.rrad = rr[r]; }
+                    q.flags = keep ? 6 : 2;
+                    q.rocks = keep;
                 }
-                q.rocks = rm;
+                my_rock_flags = q.flags;
             }
             prep[tid] = q;
+            // the stores
+            if (p.reward_kind == 0) { p.rw_prev_dist[i] = nd; p.rw_holding_prev[i] = hold; }
+            else if (p.reward_kind == 2) p.rw_holding_prev[i] = hold;
             agent_state[2 * i] = (float)hold;                                  // RL_api.py:160-162
-            agent_state[2 * i + 1] = (float)p.seed[i];
-            if (state_out != nullptr) {                                        // RL_api.py:155-158
+            agent_state[2 * i + 1] = seed_f;
+            if (want_state) {                                                  // RL_api.py:155-158
                 float *so = state_out + i * (2 + p.P);
-                so[0] = (float)p.mandibles[i];
+                so[0] = (float)mand;
                 so[1] = (float)hold;
-                for (int k = 0; k < p.P; ++k) so[2 + k] = p.act[(int64_t)k * p.EN + i] > 0.0 ? 1.f : 0.f;
+                if (p.P > 0) so[2] = act0 > 0.0 ? 1.f : 0.f;
+                if (p.P > 1) so[3] = act1 > 0.0 ? 1.f : 0.f;
+                for (int k = 2; k < p.P; ++k) so[2 + k] = p.act[(int64_t)k * p.EN + i] > 0.0 ? 1.f : 0.f;
             }
         }
     }
     __syncwarp();        // a warp only reads the prep records of its own 32 ants
+    const uint32_t rock_ants = (LAYOUT == 2) ? __ballot_sync(0xffffffffu, my_rock_flags != 0) : 0u;   // bit a: ant a of the warp
 
     // ---- phase B: a lane processes one window row of one ant (its S columns); two ways of handing out the rows
     const int warp = tid >> 5, lane = tid & 31;
@@ -203,6 +249,9 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     // ages that still show a value: the table's last entry is the 0 the reference's < 0.01 cut produced
     const uint32_t tab_len = p.tab_len > 0 ? (uint32_t)p.tab_len - 1u : 0u;
     const float decay_c = (float)p.log2_keep;                       // obs = 2^(age * log2(keep)), see below
+    const float decay_c2 = -8388608.f * decay_c;
+    // 2^23 + table length as a float (8-byte records: live ages are < 2^15, everything else reads >= 2^15)
+    const float tab_len_f = __uint_as_float(0x4B000000u | (tab_len < 0x8000u ? tab_len : 0x8000u));
     const bool eager = (REC == 0) && !p.lazy;                       // f64 fields hold plain current values (no decay on read)
     const bool eager_planes = eager && p.diffuse != 0;              // ... in the diffusion planes (sign bit = wall)
     const double inv_max = 1.0 / p.phero_max_val;
@@ -215,19 +264,37 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const uint32_t ogs = obs_gen << 8;
     float *wobs0 = s_obs + warp * kRowsTiles * TILE;
     constexpr bool kLateWait = (UNR >= S);
+    constexpr bool ROCKS_WARP = (ANTS_ROWS_ROCKS_WARP != 0) && !FLAT && LAYOUT == 2;
     // one row: sample cells, record loads, decode, staging-tile stores; returns the row's count of unexplored samples
     // phase 2 = the whole row; phase 0 = only issue the record loads into (lo, hi, cell); phase 1 = only consume them
+    // exact rock test of one sample cell against the ant's candidate rocks (RL_api.py:132-135): strict sqrt(d2) < r,
+    // decided on the squares unless d2 is within 1e-12 of r^2
+    auto rock_hit = [&](const RowPrep &q, const int ix, const int iy) -> bool {
+        const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
+        const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
+        bool hit = d2 < r2 * 0.999999999999;
+        if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
+        if (!hit && (q.flags & 4)) hit = rock_channel(p, q.e, q.rocks, ix, iy) != 0.f;
+        return hit;
+    };
     auto row_body = [&](const RowPrep &q, const double offY, const uint32_t mrow, const uint32_t orow_s,
                         const uint32_t amask, const RowPrep *qn, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR],
-                        const int phase) -> int {
+                        const int phase, const uint32_t rbits_in) -> int {
         const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
         const int e = q.e;
         const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
+        if (ANTS_ROWS_BASE64) asm volatile("" : "+l"(cells));
         const double *plane0 = eager_planes ? p.phero_pl + (int64_t)e * 2 * p.plane : nullptr;   // [e][k = 0, 1]
         const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
         const int flags = q.flags;
-        uint32_t rbits = 0u;                                       // bit j: a rock covers the sample at column j
+        uint32_t rbits = rbits_in;                                 // bit j: a rock covers the sample at column j
         int cnt = 0;
+        constexpr int RH = S / 2;
+        double ctX[RH > 0 ? RH : 1], stX[RH > 0 ? RH : 1];         // ct * X, st * X of the columns right of the centre
+        if (ANTS_ROWS_SYM && phase != 1) {
+#pragma unroll
+            for (int k = 0; k < RH; ++k) { ctX[k] = ct * p.off_c[RH + 1 + k]; stX[k] = st * p.off_c[RH + 1 + k]; }
+        }
 #pragma unroll
         for (int j0 = 0; j0 < S; j0 += UNR) {
             if (phase != 1) {
@@ -236,9 +303,13 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 const int j = j0 + u;
                 if (j < S) {
                     // sample cell, RL_api.py:110-119: round_half_even(rot(theta + pi/2) * offset + xy_f) mod (W, H)
-                    const double X = p.off_c[j];
-                    const double rx = ct * X - stY;
-                    const double ry = st * X + ctY;
+                    double cX, sX;                         // ct * X, st * X with X = off_c[j] = -off_c[S - 1 - j]
+                    if (!ANTS_ROWS_SYM) { const double X = p.off_c[j]; cX = ct * X; sX = st * X; }
+                    else if (j == RH) { cX = 0.0; sX = 0.0; }      // (the sign of a zero is lost in the sums below)
+                    else if (j > RH) { cX = ctX[j - RH - 1]; sX = stX[j - RH - 1]; }
+                    else { cX = -ctX[RH - 1 - j]; sX = -stX[RH - 1 - j]; }
+                    const double rx = cX - stY;
+                    const double ry = sX + ctY;
                     int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
                     ix = wrap1(ix, W); iy = wrap1(iy, H);
                     // cidx(): 8 x 8 blocks of 64 records; (x & 7) * 8 = 8 x - 64 (x >> 3), (y >> 3) * 64 + (y & 7) = y + 56 (y >> 3)
@@ -277,7 +348,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(cells2 + ((size_t)c2 << SH)));
                 }
             }
-            if (LAYOUT == 2 && flags) {            // a rock may reach this ant's window (few ants): RL_api.py:132-135
+            if (LAYOUT == 2 && !ROCKS_WARP && flags) {   // a rock may reach this ant's window (few ants): RL_api.py:132-135
 #pragma unroll 1
                 for (int j = j0; j < S && j < j0 + UNR; ++j) {
                     const double X = p.off_c[j];                           // the same arithmetic as above
@@ -285,13 +356,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     const double ry = st * X + ctY;
                     int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
                     ix = wrap1(ix, W); iy = wrap1(iy, H);
-                    // strict sqrt(d2) < r, decided on the squares unless d2 is within 1e-12 of r^2
-                    const double ddx = (double)ix - q.rcx, ddy = (double)iy - q.rcy, rad = q.rrad;
-                    const double d2 = ddx * ddx + ddy * ddy, r2 = rad * rad;
-                    bool hit = d2 < r2 * 0.999999999999;
-                    if (!hit && d2 <= r2 * 1.000000000001) hit = sqrt(d2) < rad;
-                    if (!hit && (flags & 4)) hit = rock_channel(p, e, q.rocks, ix, iy) != 0.f;
-                    rbits |= (hit ? 1u : 0u) << j;
+                    rbits |= (rock_hit(q, ix, iy) ? 1u : 0u) << j;
                 }
             }
             if (kLateWait) {
@@ -305,6 +370,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << SH);
                     bool wl, occupied, fresh, seen_now, hill;
                     uint32_t age0, age1;
+                    float m0 = 0.f, m1 = 0.f;      // 2^23 + age as floats (8-byte records, ANTS_ROWS_MAGIC)
                     float v5;                      // food as the f32 observation shows it
                     if (REC8) {
                         const uint32_t pk = lo[u].y >> 16;                 // [hill|occ][wall|explored]
@@ -318,6 +384,10 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         const uint32_t d2 = nowb2 - (lo[u].x & 0x7FFF7FFFu);
                         const uint32_t a2 = (d2 & 0x7FFF7FFFu) | (~lo[u].x & 0x80008000u);
                         age0 = a2 & 0xFFFFu; age1 = a2 >> 16;
+                        if (ANTS_ROWS_MAGIC) {     // bytes [age lo, age hi, 00, 4B] = the float 2^23 + age
+                            m0 = __uint_as_float(__byte_perm(a2, 0x4B000000u, 0x7610u));
+                            m1 = __uint_as_float(__byte_perm(a2, 0x4B000000u, 0x7632u));
+                        }
                         if (explore_on && fresh) rp[7] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
                     } else if (REC16) {
                         const uint32_t pk = lo[u].w;
@@ -348,9 +418,18 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     // (float)(max_val * keep^k / max_val) = keep^k (the reference's per-step rounding moves it by
                     // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
                     // cut is the exact table length; inside a wall only a deposit of this very update shows.
-                    const uint32_t lim = wl ? 1u : tab_len;
-                    float v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
-                    float v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                    float v1, v2;
+                    if (REC8 && ANTS_ROWS_MAGIC) {
+                        // (2^23 + age) c - 2^23 c in one fused rounding = the rounded product age * c (2^23 c is exact);
+                        // the floats 2^23 + n order like the integers n
+                        const float limf = wl ? 8388609.f : tab_len_f;
+                        v1 = m0 < limf ? ex2_approx(__fmaf_rn(m0, decay_c, decay_c2)) : 0.f;
+                        v2 = m1 < limf ? ex2_approx(__fmaf_rn(m1, decay_c, decay_c2)) : 0.f;
+                    } else {
+                        const uint32_t lim = wl ? 1u : tab_len;
+                        v1 = age0 < lim ? ex2_approx((float)age0 * decay_c) : 0.f;
+                        v2 = age1 < lim ? ex2_approx((float)age1 * decay_c) : 0.f;
+                    }
                     if (REC == 0 && eager) {       // eager f64 fields (dense / tiles / diffusion): phero / max_val
                         v1 = (float)(__hiloint2double((int)lo[u].y, (int)lo[u].x) * inv_max);
                         v2 = (float)(__hiloint2double((int)lo[u].w, (int)lo[u].z) * inv_max);
@@ -446,7 +525,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 const uint32_t orow_s = tiles_s + (uint32_t)((((la >> 2) & 1) * TILE + ((la & 3) * S2 + li * S) * C) * 4);
                 uint4 lo[UNR], hi[UNR];
                 uint32_t cell[UNR];
-                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask, nullptr, lo, hi, cell, 2);
+                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask, nullptr, lo, hi, cell, 2, 0u);
                 s_rowcnt[(warp * 32 + la) * S + li] = (uint8_t)cnt;
             }
             const bool last = nrows <= 32;
@@ -479,10 +558,43 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         constexpr bool PIPE = (ANTS_ROWS_PIPE != 0) && REC != 0 && UNR >= S && kRowsTiles == 1;
         uint4 loA[UNR], hiA[UNR], loB[UNR], hiB[UNR];
         uint32_t cellA[UNR], cellB[UNR];
+        // the rock channel of the chunk's ants a rock may reach (bits of fa), by the whole warp: the S*S samples of
+        // such an ant go over the lanes (the same arithmetic as in row_body, so the same cells), the hits come back
+        // to the ant's row lanes as ballots.  Returns this lane's row bits.  (Warp-converged call.)
+        auto rock_rows = [&](const int g, uint32_t fa) -> uint32_t {
+            uint32_t rb = 0u;
+            while (fa) {
+                const int a = __ffs((int)fa) - 1;
+                fa &= fa - 1u;
+                const RowPrep &q = prep[warp * 32 + g + a];
+                const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
+#pragma unroll 1
+                for (int s0 = 0; s0 < S2; s0 += 32) {
+                    const int s = s0 + lane;
+                    bool hit = false;
+                    if (s < S2) {
+                        const int i = s / S, j = s - i * S;
+                        const double X = p.off_c[j], Y = p.off_c[i];
+                        const double stY = st * Y, ctY = ct * Y;
+                        const double rx = ct * X - stY;
+                        const double ry = st * X + ctY;
+                        int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
+                        ix = wrap1(ix, W); iy = wrap1(iy, H);
+                        hit = rock_hit(q, ix, iy);
+                    }
+                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                    const int sh = li * S - s0;                    // this lane's row starts at sample li * S of the window
+                    if (lane_on && la == a && sh > -S && sh < 32)
+                        rb |= (sh >= 0 ? (b >> sh) : (b << -sh)) & ((1u << S) - 1u);
+                }
+            }
+            return rb;
+        };
         // one chunk of 4 ants: (issue +) decode + flush
-        auto chunk = [&](const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR], const int phase) {
+        // (FULLW: all 32 ants of the warp exist, G ants in every chunk; a constant at each inlined call site)
+        auto chunk = [&](const bool FULLW, const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR], const int phase) {
             const int64_t i0 = wbase + g;
-            const int n_in = (ant_end - i0 < G) ? (int)(ant_end - i0) : G;
+            const int n_in = FULLW ? G : ((ant_end - i0 < G) ? (int)(ant_end - i0) : G);
             const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
             float *wobs = wobs0 + tsel * TILE;
             const uint32_t orow_s = orow_s0 + (uint32_t)(tsel * TILE * 4);
@@ -491,10 +603,20 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
                 __syncwarp();
             }
-            if (lane_on && la < n_in) {
-                const RowPrep *qn = (g + G < 32 && i0 + G + la < ant_end) ? &prep[warp * 32 + g + G + la] : nullptr;
-                const int cnt = row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, phase);
-                s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
+            const bool row_on = lane_on && (FULLW || la < n_in);
+            const RowPrep *qn = (ANTS_ROWS_PREFETCH > 0 && g + G < 32 && i0 + G + la < ant_end) ? &prep[warp * 32 + g + G + la] : nullptr;
+            const uint32_t fa = ROCKS_WARP ? ((rock_ants >> g) & ((1u << G) - 1u)) : 0u;     // warp-uniform
+            uint32_t rb = 0u;
+            if (ROCKS_WARP && phase == 2 && UNR >= S) {
+                // record loads first, the (rare) rock evaluation while they are in flight, then the decode
+                if (row_on) row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, 0, 0u);
+                if (fa) rb = rock_rows(g, fa);
+                if (row_on) s_rowcnt[(warp * 32 + g + la) * S + li] =
+                    (uint8_t)row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, 1, rb);
+            } else {
+                if (ROCKS_WARP && fa && phase != 0) rb = rock_rows(g, fa);
+                if (row_on) s_rowcnt[(warp * 32 + g + la) * S + li] =
+                    (uint8_t)row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, phase, rb);
             }
             flush(wobs, i0, n_in);
         };
@@ -502,7 +624,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         auto issue = [&](const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR]) {
             const int64_t i0 = wbase + g;
             if (g < 32 && i0 < ant_end && lane_on && i0 + la < ant_end)
-                row_body(prep[warp * 32 + g + la], offY, mrow, 0u, 0u, nullptr, lo, hi, cell, 0);
+                row_body(prep[warp * 32 + g + la], offY, mrow, 0u, 0u, nullptr, lo, hi, cell, 0, 0u);
         };
         if (PIPE) {
             // chunk g + 1 is on its way while chunk g is decoded: two register sets, the loop unrolled by two so that
@@ -511,15 +633,19 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             for (int g = 0; g < 32; g += 2 * G) {
                 if (wbase + g >= ant_end) break;
                 issue(g + G, loB, hiB, cellB);
-                chunk(g, loA, hiA, cellA, 1);
+                chunk(false, g, loA, hiA, cellA, 1);
                 if (wbase + g + G >= ant_end) break;
                 issue(g + 2 * G, loA, hiA, cellA);
-                chunk(g + G, loB, hiB, cellB, 1);
+                chunk(false, g + G, loB, hiB, cellB, 1);
             }
+        } else if (ANTS_ROWS_FULLWARP && n_valid == 32) {
+#pragma unroll 1
+            for (int g = 0; g < 32; g += G) chunk(true, g, loA, hiA, cellA, 2);
         } else {
+#pragma unroll 1
             for (int g = 0; g < 32; g += G) {
                 if (wbase + g >= ant_end) break;
-                chunk(g, loA, hiA, cellA, 2);
+                chunk(false, g, loA, hiA, cellA, 2);
             }
         }
     }
@@ -547,7 +673,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
             p.rewards[i] = reward;
             if (reward_out != nullptr) reward_out[i] = reward;
             if (is_step) {                                                     // ants.py:119-121 (Q16)
-                int rs = p.reward_state[i];
+                int rs = rs_prev;                                              // (loaded in phase A)
                 rs += ((reward - p.reward_threshold) > 0.0) ? 255 : 0;
                 p.reward_state[i] = (uint8_t)(rs > 255 ? 255 : rs);
             }
