@@ -99,9 +99,9 @@ __device__ __noinline__ double env_noise(const Params &p, int e, uint32_t step_i
     return philox_uniform(p.rng_seed, (uint32_t)(p.env_id_base + e), step_id, (uint32_t)ant);
 }
 // the owner of a cell adds its activations and clamps (ants.py:98-100, pheromone.py:36-41)
-__device__ ANTS_ENV_HOT void env_deposit(const Params &p, uint8_t *rec, int64_t i, uint32_t now, uint32_t now_abs) {
+__device__ ANTS_ENV_HOT void env_deposit(const Params &p, uint8_t *rec, int64_t i, uint32_t now, uint32_t now_abs, double av0, double av1) {
     for (int q = 0; q < p.P; ++q) {
-        const double av = p.act[(int64_t)q * p.EN + i];
+        const double av = q == 0 ? av0 : (q == 1 ? av1 : p.act[(int64_t)q * p.EN + i]);   // (the first two were loaded with the ant state)
         if (av == 0.0) continue;
         double v = phero_value(p, rec, q, now, now_abs) + av;                           // (evaporated up to this update)
         if (p.has_max_val) v = fmin(v, p.phero_max_val);
@@ -435,14 +435,22 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     //      itself and the stamps of the new cell are written after the next barrier
     double hold[APT];
     uint8_t mand[APT];
-    int8_t rot[APT];
+    int8_t rot[APT], phv[APT];     // (every load of the tapes here: past the first store of the loop below a load waits its turn)
     if (MOVE) {
 #pragma unroll
         for (int k = 0; k < APT; ++k) {
             const int64_t i = i0 + lac[k];
             hold[k] = p.holding[i]; mand[k] = p.mandibles[i];
             rot[k] = (!(UPDATE && ANTS_ENV_SPECULATE) && a.rot != nullptr) ? a.rot[i] : (int8_t)0;
+            phv[k] = a.ph != nullptr ? a.ph[i] : (int8_t)0;
         }
+    }
+    double av0[APT], av1[APT];     // the activations an owner deposits (ants.py:98-100)
+#pragma unroll
+    for (int k = 0; k < APT; ++k) {
+        const int64_t i = i0 + lac[k];
+        av0[k] = (UPDATE && p.P > 0) ? p.act[i] : 0.0;
+        av1[k] = (UPDATE && p.P > 1) ? p.act[p.EN + i] : 0.0;
     }
     if (UPDATE && MOVE) {
 #pragma unroll
@@ -455,7 +463,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         const int e = env0 + el[k], ant = lac[k] - el[k] * p.N;
         uint8_t *rec = rec_of(el[k], cell[k]);
         const bool own = env_hash_get(hkeys, hvals, HMASK, (uint32_t)(el[k] * p.plane + cell[k]) + 1u) == (uint32_t)ant + 1u;
-        if (UPDATE && own && p.P > 0) env_deposit(p, rec, i, a.now, a.now_abs);
+        if (UPDATE && own && p.P > 0) env_deposit(p, rec, i, a.now, a.now_abs, av0[k], av1[k]);
         if (MOVE) {
             const double x0 = xs[lac[k]], y0 = ys[lac[k]];
             const bool hill = in_hill(p.hill + 4 * e, cell_of(x0, W), cell_of(y0, H));  // RL_api.py:184
@@ -520,7 +528,7 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
             }
         }
         if (a.ph != nullptr) {                                                          // ants.py:89-96
-            const int v = a.ph[i];
+            const int v = phv[k];
             p.act[i] = (v == 1) ? a.act_on : 0.0;
             p.act[p.EN + i] = (v != 0 && v != 1) ? a.act_on : 0.0;
         }
@@ -528,13 +536,24 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     // Occupancy stamp of the new cell (RL_api.py:136-142) and its wall bit for the coming update.  (ANTS_ENV_WALLFLAG = 0:
     // the stamp as a store without a load -- the byte it shares with the anthill bit of the compact records is rebuilt from
     // the disc test on integers, the same test k_hill_mark wrote the bit with -- and the wall bit read by the update.)
+    // (the loads of all the thread's ants first, then the stores: a load behind a store is not moved up by the compiler)
+    uint32_t meta[APT];            // compact records: the 16 bits [hill | occ stamp][wall | explored stamp]; else the wall bit
+    if (ANTS_ENV_WALLFLAG) {
+#pragma unroll
+        for (int k = 0; k < APT; ++k) {
+            const uint8_t *orec = rec_of(el[k], newcell[k]);
+            meta[k] = (p.rec8 || p.rec16) ? (uint32_t)*reinterpret_cast<const uint16_t *>(orec + (p.rec8 ? 6 : 12))
+                                          : (ld_wall(p, orec) ? 0x8000u : 0u);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < APT; ++k) {
         if (!valid[k]) continue;
         uint8_t *orec = rec_of(el[k], newcell[k]);
         if (ANTS_ENV_WALLFLAG) {
-            p.wall_hit[i0 + lac[k]] = ld_wall(p, orec) ? 1 : 0;        // for Walls.update of the coming update
-            st_occ(p, orec, a.occ_gen);
+            p.wall_hit[i0 + lac[k]] = (uint8_t)(meta[k] >> 15);        // for Walls.update of the coming update
+            if (p.rec8 || p.rec16) orec[p.rec8 ? 6 : 12] = (uint8_t)((meta[k] & 0x80u) | (a.occ_gen & 0x7Fu));
+            else st_occ(p, orec, a.occ_gen);
         } else if (p.rec8 || p.rec16) {
             const bool hill = in_hill(p.hill + 4 * (env0 + el[k]), newxy[k] >> 16, newxy[k] & 0xFFFF);
             orec[p.rec8 ? 6 : 12] = (uint8_t)((hill ? 0x80u : 0u) | (a.occ_gen & 0x7Fu));

@@ -20,7 +20,7 @@
 namespace ants {
 
 #ifndef ANTS_ROWS_THREADS
-#define ANTS_ROWS_THREADS 128
+#define ANTS_ROWS_THREADS 32
 #endif
 constexpr int kRowsThreads = ANTS_ROWS_THREADS;
 constexpr int kRowsGroup = 4;
