@@ -15,6 +15,14 @@
 // records; two for f64 records), a branch-free decode and C shared-memory stores.  All record loads of a row are in
 // flight before the first is decoded.  Exploration counts are per-lane adds, summed over the S rows in the epilogue.
 // The staged (4 x S*S x C) f32 tile leaves with one TMA bulk store, as before.
+//
+// Round 2 (0.240 -> 0.177 ms on the cfg4 shard, 224 -> 195 warp instructions per ant): the kernel's pointers may alias
+// as far as the compiler knows, so in phase A (thread per ant) every load that followed a store waited for the
+// previous round trip -- all loads of the ant's state are now issued before the first store (-18 %); the rock channel
+// of the few ants a rock can reach is evaluated by the whole warp instead of the ant's S row lanes (-6 %); blocks of
+// one warp (the block index is warp-uniform to the compiler); the reward terms of phase C wait in shared memory, not in
+// registers of the chunk loop; ages go to float through the 2^23 exponent trick; half of the column products follow
+// from the symmetry of the window offsets.
 #pragma once
 
 namespace ants {
@@ -24,20 +32,16 @@ namespace ants {
 #endif
 constexpr int kRowsThreads = ANTS_ROWS_THREADS;
 constexpr int kRowsGroup = 4;
-#ifndef ANTS_ROWS_FLAT
-#define ANTS_ROWS_FLAT 0           // 1 = hand the 32 * S rows of a warp to the lanes without idle lanes (measured slower: 0.279 vs 0.241 ms)
-#endif
-#ifndef ANTS_ROWS_TILES
-#define ANTS_ROWS_TILES (ANTS_ROWS_FLAT ? 2 : 1)
-#endif
-constexpr int kRowsTiles = ANTS_ROWS_TILES;   // staging tiles per warp (2 = the bulk store of chunk g drains while g + 1 is staged)
+constexpr int kRowsTiles = 1;        // staging tiles per warp
 
-struct RowPrep {                 // 72 bytes per ant, shared memory (phase A -> phase B)
+struct RowPrep {                 // 96 bytes per ant, shared memory (phase A -> phase B, C)
     double ct, st;               // cos / sin(theta + pi/2)
     double xf, yf;               // position shifted forward by perception_fwd_delta
     unsigned long long rocks;    // further candidate rocks (beyond the first) whose disc can reach the window
     int e, flags;                // environment; 2 = a rock may reach the window, 4 = more than one
     double rcx, rcy, rrad;       // the first candidate rock
+    double r_other, r_mult;      // phase A -> phase C: the reward terms that do not need the exploration count ...
+    int rs_prev, pad;            // ... and the ant's reward_state (kept out of the registers of the chunk loop)
 };
 
 // one conditional add or subtract wraps a sample coordinate onto the torus (np.mod on ints, RL_api.py:118-119) when
@@ -81,38 +85,14 @@ __device__ __noinline__ float rock_channel(const Params &p, int e, unsigned long
 
 template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 16-byte, 2 = compact 8-byte
 #ifndef ANTS_ROWS_OCC
-#define ANTS_ROWS_OCC ((ANTS_ROWS_FLAT ? 4 : 5) * 128 / ANTS_ROWS_THREADS)   // resident blocks per SM the register budget allows (shared memory: 4 / 5 of 128 threads)
+#define ANTS_ROWS_OCC (5 * 128 / ANTS_ROWS_THREADS)   // resident warps per SM / warps per block: 20 warps at 96 registers
 #endif
-#ifndef ANTS_ROWS_UNR
-#define ANTS_ROWS_UNR 7
-#endif
-#ifndef ANTS_ROWS_ROCKS_WARP
-#define ANTS_ROWS_ROCKS_WARP 1     // 1 = the rock channel of an ant whose window a rock may reach is evaluated by the whole
-                                   // warp (its S*S samples over the lanes, ballots back to the row lanes) instead of by the
-                                   // ant's S row lanes while the other rows of the chunk idle
-#endif
-#ifndef ANTS_ROWS_MAGIC
-#define ANTS_ROWS_MAGIC 1          // 1 = 8-byte records: (float)age through the 2^23 exponent trick (PRMT + FFMA) instead of I2F + FMUL
-#endif
-#ifndef ANTS_ROWS_BASE64
-#define ANTS_ROWS_BASE64 1         // 1 = the environment's record base as one opaque 64-bit register (one IMAD.WIDE per sample address)
-#endif
-#ifndef ANTS_ROWS_FULLWARP
-#define ANTS_ROWS_FULLWARP 0       // 1 = a warp with all of its 32 ants runs a copy of the chunk loop without the ragged-end bookkeeping
-#endif
-#ifndef ANTS_ROWS_SYM
-#define ANTS_ROWS_SYM 1            // 1 = the window offsets are (j - radius) * DELTA (RL_api.py:92-93), so ct * X and st * X are
-                                   // computed for the positive columns only: a product's sign flips exactly with its factor's
-#endif
-#ifndef ANTS_ROWS_PIPE
-#define ANTS_ROWS_PIPE 0           // 1 = the record loads of the NEXT chunk are issued before the current chunk is decoded
-                                   // (double-buffered registers; compact records only)
-#endif
-#ifndef ANTS_ROWS_PREFETCH
-#define ANTS_ROWS_PREFETCH 0       // samples of the NEXT chunk's row whose records are prefetched into L2 (0 = off, S = all).
-                                   // Measured on the cfg4 shard: 0.240 ms without, 0.254 with 4, 0.269 with 7 -- the
-                                   // kernel has no issue slots to spare for the address arithmetic
-#endif
+// Measured on the cfg4 shard (512 envs x 1024 ants, 8-byte records, one B200) and left out of the code again:
+//   * all 32 * S rows of a warp handed to the lanes without idle lanes (two staging tiles): 0.279 ms against 0.241;
+//   * the record loads of chunk g + 1 issued before chunk g is decoded (two register sets): 0.278 - 0.338 ms;
+//   * L2 prefetch of the next chunk's records: 0.254 (4 samples per row) and 0.269 ms (all 7) against 0.240;
+//   * a second copy of the chunk loop for warps with all 32 ants (no ragged-end bookkeeping): 0.2248 against 0.2223;
+//   * 80 registers for 24 warps per SM (8 bytes of spills): 0.226 ms against 0.177.
 __global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
 k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
                 double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
@@ -121,13 +101,12 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     pdl_begin();
     static_assert(LAYOUT == 1 || LAYOUT == 2, "default channel lists only");
     constexpr bool REC16 = (REC == 1), REC8 = (REC == 2);
-    constexpr bool FLAT = (ANTS_ROWS_FLAT != 0) && S == 7 && REC != 0;
     constexpr int SH = REC8 ? 3 : (REC16 ? 4 : 5);                    // log2(record bytes)
     static_assert(kRowsGroup * S <= 32, "a chunk's rows must fit one warp");
     constexpr int S2 = S * S, C = (LAYOUT == 2) ? 7 : 6, SC = S2 * C;
     constexpr int G = kRowsGroup, ROWS = G * S, TILE = G * SC;       // TILE * 4 bytes is a multiple of 16
     constexpr int NW = kRowsThreads / 32;
-    constexpr int UNR = (REC != 0) ? (S < ANTS_ROWS_UNR ? S : ANTS_ROWS_UNR) : (S + 1) / 2;                      // record loads in flight per lane
+    constexpr int UNR = (REC != 0) ? S : (S + 1) / 2;                 // record loads in flight per lane
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_obs = reinterpret_cast<float *>(smem_raw);               // [NW][TILE]
     RowPrep *prep = reinterpret_cast<RowPrep *>(s_obs + NW * kRowsTiles * TILE);   // [threads]
@@ -141,10 +120,10 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     // The kernel's pointers may alias as far as the compiler knows, so a load after a store waits for it: every load
     // of the ant's state is issued first, the stores come last, and the dependent chain is state -> rock grid word ->
     // rock discs (ncu, round 2: phase A / C were 12 % of the instructions and 29 % of the warps' stall samples).
-    double r_other = 0.0, r_mult = 1.0;
     int my_rock_flags = 0;
-    int rs_prev = 0;                                                           // reward_state, used by phase C
     {
+        double r_other = 0.0, r_mult = 1.0;
+        int rs_prev = 0;                                                       // reward_state, used by phase C
         const int64_t i = base + tid;
         if (i < ant_end) {
             const int e = (int)(i / p.N);
@@ -223,6 +202,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 }
                 my_rock_flags = q.flags;
             }
+            q.r_other = r_other; q.r_mult = r_mult; q.rs_prev = rs_prev; q.pad = 0;
             prep[tid] = q;
             // the stores
             if (p.reward_kind == 0) { p.rw_prev_dist[i] = nd; p.rw_holding_prev[i] = hold; }
@@ -264,7 +244,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
     const uint32_t ogs = obs_gen << 8;
     float *wobs0 = s_obs + warp * kRowsTiles * TILE;
     constexpr bool kLateWait = (UNR >= S);
-    constexpr bool ROCKS_WARP = (ANTS_ROWS_ROCKS_WARP != 0) && !FLAT && LAYOUT == 2;
+    constexpr bool ROCKS = LAYOUT == 2;
     // one row: sample cells, record loads, decode, staging-tile stores; returns the row's count of unexplored samples
     // phase 2 = the whole row; phase 0 = only issue the record loads into (lo, hi, cell); phase 1 = only consume them
     // exact rock test of one sample cell against the ant's candidate rocks (RL_api.py:132-135): strict sqrt(d2) < r,
@@ -278,20 +258,20 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         return hit;
     };
     auto row_body = [&](const RowPrep &q, const double offY, const uint32_t mrow, const uint32_t orow_s,
-                        const uint32_t amask, const RowPrep *qn, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR],
-                        const int phase, const uint32_t rbits_in) -> int {
+                        const uint32_t amask, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR],
+                        const int phase, const uint32_t rbits) -> int {
         const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
         const int e = q.e;
         const uint8_t *cells = p.cells + (((int64_t)e * p.plane) << SH);
-        if (ANTS_ROWS_BASE64) asm volatile("" : "+l"(cells));
+        asm volatile("" : "+l"(cells));                            // one opaque 64-bit base: one IMAD.WIDE per sample address
         const double *plane0 = eager_planes ? p.phero_pl + (int64_t)e * 2 * p.plane : nullptr;   // [e][k = 0, 1]
         const double stY = st * offY, ctY = ct * offY;             // RL_api.py:110-111
-        const int flags = q.flags;
-        uint32_t rbits = rbits_in;                                 // bit j: a rock covers the sample at column j
-        int cnt = 0;
+        int cnt = 0;                                               // (rbits, bit j: a rock covers the sample at column j)
         constexpr int RH = S / 2;
-        double ctX[RH > 0 ? RH : 1], stX[RH > 0 ? RH : 1];         // ct * X, st * X of the columns right of the centre
-        if (ANTS_ROWS_SYM && phase != 1) {
+        // The window offsets are (j - radius) * DELTA (RL_api.py:92-93): ct * X and st * X are computed for the columns
+        // right of the centre only -- a product's sign flips exactly with its factor's
+        double ctX[RH > 0 ? RH : 1], stX[RH > 0 ? RH : 1];
+        if (phase != 1) {
 #pragma unroll
             for (int k = 0; k < RH; ++k) { ctX[k] = ct * p.off_c[RH + 1 + k]; stX[k] = st * p.off_c[RH + 1 + k]; }
         }
@@ -304,8 +284,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                 if (j < S) {
                     // sample cell, RL_api.py:110-119: round_half_even(rot(theta + pi/2) * offset + xy_f) mod (W, H)
                     double cX, sX;                         // ct * X, st * X with X = off_c[j] = -off_c[S - 1 - j]
-                    if (!ANTS_ROWS_SYM) { const double X = p.off_c[j]; cX = ct * X; sX = st * X; }
-                    else if (j == RH) { cX = 0.0; sX = 0.0; }      // (the sign of a zero is lost in the sums below)
+                    if (j == RH) { cX = 0.0; sX = 0.0; }           // (the sign of a zero is lost in the sums below)
                     else if (j > RH) { cX = ctX[j - RH - 1]; sX = stX[j - RH - 1]; }
                     else { cX = -ctX[RH - 1 - j]; sX = -stX[RH - 1 - j]; }
                     const double rx = cX - stY;
@@ -327,40 +306,13 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         lo[u] = ld_record16(rp);
                     }
                     if (REC == 0) hi[u] = *reinterpret_cast<const uint4 *>(rp + 16);
+                    asm volatile("" : "+r"(cell[u]));      // the decode keeps the 32-bit cell index, not the 64-bit address
                 }
             }
             }
             if (phase == 0) return 0;
-            if (ANTS_ROWS_PREFETCH > 0 && qn != nullptr && j0 == 0) {
-                // (experiment, off by default) while this row's record loads are in flight: prefetch the same row of the
-                // ant this lane serves in the NEXT chunk.  ncu (bench batch) showed 30 % of all warp stall samples on the
-                // first use of the loaded records, but the extra address arithmetic costs more than the L2 hits give back.
-                const double ct2 = qn->ct, st2 = qn->st, xf2 = qn->xf, yf2 = qn->yf;
-                const uint8_t *cells2 = p.cells + (((int64_t)qn->e * p.plane) << SH);
-                const double stY2 = st2 * offY, ctY2 = ct2 * offY;
-#pragma unroll
-                for (int k = 0; k < ANTS_ROWS_PREFETCH && k < S; ++k) {
-                    const int j = ANTS_ROWS_PREFETCH >= S ? k : (k * (S - 1)) / (ANTS_ROWS_PREFETCH > 1 ? ANTS_ROWS_PREFETCH - 1 : 1);
-                    const double X = p.off_c[j];
-                    int ix = round_half_even((ct2 * X - stY2) + xf2), iy = round_half_even((st2 * X + ctY2) + yf2);
-                    ix = wrap1(ix, W); iy = wrap1(iy, H);
-                    const uint32_t c2 = (uint32_t)((ix >> 3) * nby64m + ix * 8 + (iy >> 3) * 56 + iy);
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(cells2 + ((size_t)c2 << SH)));
-                }
-            }
-            if (LAYOUT == 2 && !ROCKS_WARP && flags) {   // a rock may reach this ant's window (few ants): RL_api.py:132-135
-#pragma unroll 1
-                for (int j = j0; j < S && j < j0 + UNR; ++j) {
-                    const double X = p.off_c[j];                           // the same arithmetic as above
-                    const double rx = ct * X - stY;
-                    const double ry = st * X + ctY;
-                    int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
-                    ix = wrap1(ix, W); iy = wrap1(iy, H);
-                    rbits |= (rock_hit(q, ix, iy) ? 1u : 0u) << j;
-                }
-            }
             if (kLateWait) {
-                if (lane == 0) bulk_store_wait_read<FLAT ? 0 : kRowsTiles - 1>();
+                if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
                 __syncwarp(amask);
             }
 #pragma unroll
@@ -370,7 +322,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     uint8_t *rp = const_cast<uint8_t *>(cells) + ((size_t)cell[u] << SH);
                     bool wl, occupied, fresh, seen_now, hill;
                     uint32_t age0, age1;
-                    float m0 = 0.f, m1 = 0.f;      // 2^23 + age as floats (8-byte records, ANTS_ROWS_MAGIC)
+                    float m0 = 0.f, m1 = 0.f;      // 2^23 + age as floats (8-byte records)
                     float v5;                      // food as the f32 observation shows it
                     if (REC8) {
                         const uint32_t pk = lo[u].y >> 16;                 // [hill|occ][wall|explored]
@@ -384,10 +336,9 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                         const uint32_t d2 = nowb2 - (lo[u].x & 0x7FFF7FFFu);
                         const uint32_t a2 = (d2 & 0x7FFF7FFFu) | (~lo[u].x & 0x80008000u);
                         age0 = a2 & 0xFFFFu; age1 = a2 >> 16;
-                        if (ANTS_ROWS_MAGIC) {     // bytes [age lo, age hi, 00, 4B] = the float 2^23 + age
-                            m0 = __uint_as_float(__byte_perm(a2, 0x4B000000u, 0x7610u));
-                            m1 = __uint_as_float(__byte_perm(a2, 0x4B000000u, 0x7632u));
-                        }
+                        // bytes [age lo, age hi, 00, 4B] = the float 2^23 + age: one PRMT instead of mask + I2F
+                        m0 = __uint_as_float(__byte_perm(a2, 0x4B000000u, 0x7610u));
+                        m1 = __uint_as_float(__byte_perm(a2, 0x4B000000u, 0x7632u));
                         if (explore_on && fresh) rp[7] = (uint8_t)(((pk >> 8) & 0x80u) | obs_gen);
                     } else if (REC16) {
                         const uint32_t pk = lo[u].w;
@@ -419,7 +370,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     // ~1e-16 k): evaluated as 2^(k log2 keep) in f32, < 1.2e-6 relative (bar 1e-5); the < 0.01
                     // cut is the exact table length; inside a wall only a deposit of this very update shows.
                     float v1, v2;
-                    if (REC8 && ANTS_ROWS_MAGIC) {
+                    if (REC8) {
                         // (2^23 + age) c - 2^23 c in one fused rounding = the rounded product age * c (2^23 c is exact);
                         // the floats 2^23 + n order like the integers n
                         const float limf = wl ? 8388609.f : tab_len_f;
@@ -497,157 +448,83 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
         }
     };
     const int64_t wbase = base + warp * 32;
-    const int n_valid = (ant_end - wbase >= 32) ? 32 : (ant_end > wbase ? (int)(ant_end - wbase) : 0);   // ants of this warp
-    if (FLAT) {
-        // All 32 ants of the warp as 32 * S rows: iteration t hands rows 32t .. 32t+31 to the lanes (no idle lanes:
-        // S iterations instead of 32 / 4 chunks of 4 * S <= 32 rows).  Ant a stages into slot (a / 4) & 1 of two
-        // 4-ant tiles; with S = 7 an iteration touches chunks t and t + 1 only, and chunk t is complete after it.
-        const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(wobs0);
-        for (int rr = lane; rr < 2 * ROWS; rr += 32) {             // masked samples read -1 (RL_api.py:147-148): written once
-            const int slot = rr / ROWS, rem = rr - slot * ROWS, a4 = rem / S, li = rem - a4 * S;
-            const uint32_t m = p.mask_rows[li];
-            const uint32_t o = tiles_s + (uint32_t)((slot * TILE + (a4 * S2 + li * S) * C) * 4);
-            for (int j = 0; j < S; ++j)
-                if (!((m >> j) & 1u))
-                    for (int c = 0; c < C; ++c)
-                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(o + (uint32_t)((j * C + c) * 4)), "f"(-1.f) : "memory");
-        }
-        __syncwarp();
-        const int chunks_total = (n_valid + G - 1) / G;
-        int flushed = 0;
-        for (int t = 0; t < S; ++t) {
-            const int nrows = n_valid * S - 32 * t;                // rows left for this iteration
-            if (nrows <= 0) break;
-            const int r = 32 * t + lane;
-            const int la = r / S, li = r - la * S;                 // ant of the warp, window row
-            const uint32_t amask = nrows >= 32 ? 0xffffffffu : ((1u << nrows) - 1u);
-            if (lane < nrows) {
-                const uint32_t orow_s = tiles_s + (uint32_t)((((la >> 2) & 1) * TILE + ((la & 3) * S2 + li * S) * C) * 4);
-                uint4 lo[UNR], hi[UNR];
-                uint32_t cell[UNR];
-                const int cnt = row_body(prep[warp * 32 + la], p.off_c[li], p.mask_rows[li], orow_s, amask, nullptr, lo, hi, cell, 2, 0u);
-                s_rowcnt[(warp * 32 + la) * S + li] = (uint8_t)cnt;
-            }
-            const bool last = nrows <= 32;
-            int c_hi = last ? chunks_total : (32 * (t + 1)) / ROWS;
-            if (c_hi > chunks_total) c_hi = chunks_total;
-            for (; flushed < c_hi; ++flushed) {
-                const int left = n_valid - G * flushed;
-                flush(wobs0 + (flushed & 1) * TILE, wbase + G * flushed, left < G ? left : G);
-            }
-        }
-    } else {
-        const int la = lane / S, li = lane - la * S;
-        const bool lane_on = lane < ROWS;
-        const double offY = p.off_c[lane_on ? li : 0];
-        uint32_t mrow = p.mask_rows[lane_on ? li : 0];
-        // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
-        uint32_t orow_s0 = (uint32_t)__cvta_generic_to_shared(wobs0 + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
-        asm volatile("" : "+r"(orow_s0), "+r"(mrow));                // keep them in registers (no rematerialisation)
-        // masked samples read -1 in every channel (RL_api.py:147-148) and their tile slots are never written again
-        if (lane_on) {
+    const int la = lane / S, li = lane - la * S;
+    const bool lane_on = lane < ROWS;
+    const double offY = p.off_c[lane_on ? li : 0];
+    uint32_t mrow = p.mask_rows[lane_on ? li : 0];
+    // this lane's row of the staging tile (fixed for the whole kernel), as a shared-space address
+    uint32_t orow_s = (uint32_t)__cvta_generic_to_shared(wobs0 + ((lane_on ? la : 0) * S2 + (lane_on ? li : 0) * S) * C);
+    asm volatile("" : "+r"(orow_s), "+r"(mrow));                   // keep them in registers (no rematerialisation)
+    // masked samples read -1 in every channel (RL_api.py:147-148) and their tile slots are never written again
+    if (lane_on) {
 #pragma unroll
-            for (int j = 0; j < S; ++j)
-                if (!((mrow >> j) & 1u))
+        for (int j = 0; j < S; ++j)
+            if (!((mrow >> j) & 1u))
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
-#pragma unroll
-                        for (int t = 0; t < kRowsTiles; ++t)
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s0 + (uint32_t)((t * TILE + j * C + c) * 4)), "f"(-1.f) : "memory");
-        }
-        constexpr bool PIPE = (ANTS_ROWS_PIPE != 0) && REC != 0 && UNR >= S && kRowsTiles == 1;
-        uint4 loA[UNR], hiA[UNR], loB[UNR], hiB[UNR];
-        uint32_t cellA[UNR], cellB[UNR];
-        // the rock channel of the chunk's ants a rock may reach (bits of fa), by the whole warp: the S*S samples of
-        // such an ant go over the lanes (the same arithmetic as in row_body, so the same cells), the hits come back
-        // to the ant's row lanes as ballots.  Returns this lane's row bits.  (Warp-converged call.)
-        auto rock_rows = [&](const int g, uint32_t fa) -> uint32_t {
-            uint32_t rb = 0u;
-            while (fa) {
-                const int a = __ffs((int)fa) - 1;
-                fa &= fa - 1u;
-                const RowPrep &q = prep[warp * 32 + g + a];
-                const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
+                for (int c = 0; c < C; ++c)
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(orow_s + (uint32_t)((j * C + c) * 4)), "f"(-1.f) : "memory");
+    }
+    // The rock channel of the chunk's ants a rock may reach (bits of fa), by the whole warp: the S*S samples of such an
+    // ant go over the lanes (the same arithmetic as in row_body, so the same cells), the hits come back to the ant's
+    // row lanes as ballots.  Returns this lane's row bits.  (Warp-converged call; the ant's S row lanes alone would
+    // leave the other rows of the chunk idle for S iterations: ncu showed 15 % of the kernel's instructions there.)
+    auto rock_rows = [&](const int g, uint32_t fa) -> uint32_t {
+        uint32_t rb = 0u;
+        while (fa) {
+            const int a = __ffs((int)fa) - 1;
+            fa &= fa - 1u;
+            const RowPrep &q = prep[warp * 32 + g + a];
+            const double ct = q.ct, st = q.st, xf = q.xf, yf = q.yf;
 #pragma unroll 1
-                for (int s0 = 0; s0 < S2; s0 += 32) {
-                    const int s = s0 + lane;
-                    bool hit = false;
-                    if (s < S2) {
-                        const int i = s / S, j = s - i * S;
-                        const double X = p.off_c[j], Y = p.off_c[i];
-                        const double stY = st * Y, ctY = ct * Y;
-                        const double rx = ct * X - stY;
-                        const double ry = st * X + ctY;
-                        int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
-                        ix = wrap1(ix, W); iy = wrap1(iy, H);
-                        hit = rock_hit(q, ix, iy);
-                    }
-                    const uint32_t b = __ballot_sync(0xffffffffu, hit);
-                    const int sh = li * S - s0;                    // this lane's row starts at sample li * S of the window
-                    if (lane_on && la == a && sh > -S && sh < 32)
-                        rb |= (sh >= 0 ? (b >> sh) : (b << -sh)) & ((1u << S) - 1u);
+            for (int s0 = 0; s0 < S2; s0 += 32) {
+                const int s = s0 + lane;
+                bool hit = false;
+                if (s < S2) {
+                    const int i = s / S, j = s - i * S;
+                    const double X = p.off_c[j], Y = p.off_c[i];
+                    const double stY = st * Y, ctY = ct * Y;
+                    const double rx = ct * X - stY;
+                    const double ry = st * X + ctY;
+                    int ix = round_half_even(rx + xf), iy = round_half_even(ry + yf);
+                    ix = wrap1(ix, W); iy = wrap1(iy, H);
+                    hit = rock_hit(q, ix, iy);
                 }
-            }
-            return rb;
-        };
-        // one chunk of 4 ants: (issue +) decode + flush
-        // (FULLW: all 32 ants of the warp exist, G ants in every chunk; a constant at each inlined call site)
-        auto chunk = [&](const bool FULLW, const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR], const int phase) {
-            const int64_t i0 = wbase + g;
-            const int n_in = FULLW ? G : ((ant_end - i0 < G) ? (int)(ant_end - i0) : G);
-            const int tsel = (kRowsTiles > 1) ? ((g / G) & 1) : 0;
-            float *wobs = wobs0 + tsel * TILE;
-            const uint32_t orow_s = orow_s0 + (uint32_t)(tsel * TILE * 4);
-            const uint32_t amask = (n_in * S >= 32) ? 0xffffffffu : ((1u << (n_in * S)) - 1u);   // the lanes with a row
-            if (!kLateWait) {
-                if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
-                __syncwarp();
-            }
-            const bool row_on = lane_on && (FULLW || la < n_in);
-            const RowPrep *qn = (ANTS_ROWS_PREFETCH > 0 && g + G < 32 && i0 + G + la < ant_end) ? &prep[warp * 32 + g + G + la] : nullptr;
-            const uint32_t fa = ROCKS_WARP ? ((rock_ants >> g) & ((1u << G) - 1u)) : 0u;     // warp-uniform
-            uint32_t rb = 0u;
-            if (ROCKS_WARP && phase == 2 && UNR >= S) {
-                // record loads first, the (rare) rock evaluation while they are in flight, then the decode
-                if (row_on) row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, 0, 0u);
-                if (fa) rb = rock_rows(g, fa);
-                if (row_on) s_rowcnt[(warp * 32 + g + la) * S + li] =
-                    (uint8_t)row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, 1, rb);
-            } else {
-                if (ROCKS_WARP && fa && phase != 0) rb = rock_rows(g, fa);
-                if (row_on) s_rowcnt[(warp * 32 + g + la) * S + li] =
-                    (uint8_t)row_body(prep[warp * 32 + g + la], offY, mrow, orow_s, amask, qn, lo, hi, cell, phase, rb);
-            }
-            flush(wobs, i0, n_in);
-        };
-        // the record loads of a chunk alone
-        auto issue = [&](const int g, uint4 (&lo)[UNR], uint4 (&hi)[UNR], uint32_t (&cell)[UNR]) {
-            const int64_t i0 = wbase + g;
-            if (g < 32 && i0 < ant_end && lane_on && i0 + la < ant_end)
-                row_body(prep[warp * 32 + g + la], offY, mrow, 0u, 0u, nullptr, lo, hi, cell, 0, 0u);
-        };
-        if (PIPE) {
-            // chunk g + 1 is on its way while chunk g is decoded: two register sets, the loop unrolled by two so that
-            // neither is indexed dynamically
-            issue(0, loA, hiA, cellA);
-            for (int g = 0; g < 32; g += 2 * G) {
-                if (wbase + g >= ant_end) break;
-                issue(g + G, loB, hiB, cellB);
-                chunk(false, g, loA, hiA, cellA, 1);
-                if (wbase + g + G >= ant_end) break;
-                issue(g + 2 * G, loA, hiA, cellA);
-                chunk(false, g + G, loB, hiB, cellB, 1);
-            }
-        } else if (ANTS_ROWS_FULLWARP && n_valid == 32) {
-#pragma unroll 1
-            for (int g = 0; g < 32; g += G) chunk(true, g, loA, hiA, cellA, 2);
-        } else {
-#pragma unroll 1
-            for (int g = 0; g < 32; g += G) {
-                if (wbase + g >= ant_end) break;
-                chunk(false, g, loA, hiA, cellA, 2);
+                const uint32_t b = __ballot_sync(0xffffffffu, hit);
+                const int sh = li * S - s0;                        // this lane's row starts at sample li * S of the window
+                if (lane_on && la == a && sh > -S && sh < 32)
+                    rb |= (sh >= 0 ? (b >> sh) : (b << -sh)) & ((1u << S) - 1u);
             }
         }
+        return rb;
+    };
+    uint4 lo[UNR], hi[UNR];
+    uint32_t cell[UNR];
+#pragma unroll 1
+    for (int g = 0; g < 32; g += G) {                              // one chunk of G ants: loads, decode, flush
+        const int64_t i0 = wbase + g;
+        if (i0 >= ant_end) break;
+        const int n_in = (ant_end - i0 < G) ? (int)(ant_end - i0) : G;
+        const uint32_t amask = (n_in * S >= 32) ? 0xffffffffu : ((1u << (n_in * S)) - 1u);   // the lanes with a row
+        if (!kLateWait) {
+            if (lane == 0) bulk_store_wait_read<kRowsTiles - 1>();
+            __syncwarp();
+        }
+        const bool row_on = lane_on && la < n_in;
+        const RowPrep &q = prep[warp * 32 + g + (row_on ? la : 0)];
+        const uint32_t fa = ROCKS ? ((rock_ants >> g) & ((1u << G) - 1u)) : 0u;             // warp-uniform
+        uint32_t rb = 0u;
+        int cnt;
+        if (UNR >= S) {
+            // the record loads first, the (rare) rock evaluation while they are in flight, then the decode
+            if (row_on) row_body(q, offY, mrow, orow_s, amask, lo, hi, cell, 0, 0u);
+            if (fa) rb = rock_rows(g, fa);
+            cnt = row_on ? row_body(q, offY, mrow, orow_s, amask, lo, hi, cell, 1, rb) : 0;
+        } else {
+            if (fa) rb = rock_rows(g, fa);
+            cnt = row_on ? row_body(q, offY, mrow, orow_s, amask, lo, hi, cell, 2, rb) : 0;
+        }
+        if (row_on) s_rowcnt[(warp * 32 + g + la) * S + li] = (uint8_t)cnt;
+        flush(wobs0, i0, n_in);
     }
     __syncwarp();
 
@@ -660,6 +537,8 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
 #pragma unroll
                 for (int k = 0; k < S; ++k) count += s_rowcnt[tid * S + k];
             }
+            const double r_other = prep[tid].r_other, r_mult = prep[tid].r_mult;
+            const int rs_prev = prep[tid].rs_prev;
             double reward;
             if (p.reward_kind == 1) {
                 reward = (double)count / 10.0;                                 // reward_custom.py:19
