@@ -92,7 +92,10 @@ template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 
 //   * the record loads of chunk g + 1 issued before chunk g is decoded (two register sets): 0.278 - 0.338 ms;
 //   * L2 prefetch of the next chunk's records: 0.254 (4 samples per row) and 0.269 ms (all 7) against 0.240;
 //   * a second copy of the chunk loop for warps with all 32 ants (no ragged-end bookkeeping): 0.2248 against 0.2223;
-//   * 80 registers for 24 warps per SM (8 bytes of spills): 0.226 ms against 0.177.
+//   * 80 registers for 24 warps per SM (8 bytes of spills): 0.226 ms against 0.177;
+//   * 2 or 3 ants per thread in phases A / C (a warp serving 64 or 96 ants, the round trips of phase A paid once for all
+//     of them; prep record cut to 64 bytes with the first rock's disc re-read from global memory): 0.247 and 0.282 ms
+//     against 0.189 for the same code with one ant per thread (profiles/r2_bench/perceive_variants_apt.txt).
 __global__ void __launch_bounds__(kRowsThreads, ANTS_ROWS_OCC)
 k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float *__restrict__ agent_state, float *__restrict__ state_out,
                 double *__restrict__ reward_out, uint32_t obs_gen, uint32_t occ_gen, int is_step, int rw_alias,
