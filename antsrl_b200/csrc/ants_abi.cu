@@ -1174,18 +1174,21 @@ int ants_create(const AntsConfig *cfg, AntsBatch **out) {
         b->rows_smem = (ants::kRowsThreads / 32) * ants::kRowsTiles * ants::kRowsGroup * p.S2 * C * 4 +
                        ants::kRowsThreads * (int)sizeof(ants::RowPrep) + ants::kRowsThreads * p.S;
     }
-    if (b->perceive_rows && b->rows_smem > 48 * 1024) {
+    if (b->perceive_rows) {
         const void *fns[12] = {(const void *)ants::k_perceive_rows<1, 0, 7>, (const void *)ants::k_perceive_rows<2, 0, 7>,
                                (const void *)ants::k_perceive_rows<1, 1, 7>, (const void *)ants::k_perceive_rows<2, 1, 7>,
                                (const void *)ants::k_perceive_rows<1, 2, 7>, (const void *)ants::k_perceive_rows<2, 2, 7>,
                                (const void *)ants::k_perceive_rows<1, 0, 5>, (const void *)ants::k_perceive_rows<2, 0, 5>,
                                (const void *)ants::k_perceive_rows<1, 1, 5>, (const void *)ants::k_perceive_rows<2, 1, 5>,
                                (const void *)ants::k_perceive_rows<1, 2, 5>, (const void *)ants::k_perceive_rows<2, 2, 5>};
-        for (int k = 0; k < 12; ++k)
+        for (int k = 0; k < 12 && b->rows_smem > 48 * 1024; ++k)
             if (cudaFuncSetAttribute(fns[k], cudaFuncAttributeMaxDynamicSharedMemorySize, b->rows_smem) != cudaSuccess) {
                 ants_destroy(b);
                 return fail(ANTS_E_CUDA, "k_perceive_rows needs %d B of shared memory", b->rows_smem);
             }
+        // shared memory / L1 split of the SM for the row kernel, in percent of shared memory (experiments; default: the driver's)
+        if (const char *cv = getenv("ANTS_ROWS_CARVEOUT"))
+            for (int k = 0; k < 12; ++k) cudaFuncSetAttribute(fns[k], cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
     }
     if (b->perceive_smem > 48 * 1024) {
         cudaError_t e = cudaSuccess;

@@ -93,6 +93,12 @@ template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 
 //   * L2 prefetch of the next chunk's records: 0.254 (4 samples per row) and 0.269 ms (all 7) against 0.240;
 //   * a second copy of the chunk loop for warps with all 32 ants (no ragged-end bookkeeping): 0.2248 against 0.2223;
 //   * 80 registers for 24 warps per SM (8 bytes of spills): 0.226 ms against 0.177;
+//   * shared memory / L1 split (ANTS_ROWS_CARVEOUT, profiles/r2_bench/perceive_carveout.txt): the driver's default puts
+//     the SM at 164 KB shared + 92 KB L1 with 16 resident warps, 0.177 ms; 196 / 228 KB shared (20 warps, <= 60 KB L1)
+//     0.221 ms; 132 KB (13 warps, 124 KB L1) 0.1815; 100 KB (10 warps) 0.204 -- the gathers need ~90 KB of L1, more
+//     warps than 16 do not pay for taking it away;
+//   * prep record cut to 64 bytes (the first rock's disc re-read from global memory in the rock path): 0.186 against
+//     0.177 at every split (perceive_carveout_prep64.txt);
 //   * 2 or 3 ants per thread in phases A / C (a warp serving 64 or 96 ants, the round trips of phase A paid once for all
 //     of them; prep record cut to 64 bytes with the first rock's disc re-read from global memory): 0.247 and 0.282 ms
 //     against 0.189 for the same code with one ant per thread (profiles/r2_bench/perceive_variants_apt.txt).
