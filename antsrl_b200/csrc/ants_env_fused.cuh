@@ -233,6 +233,21 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
     auto rec_of = [&](int g, int c) -> uint8_t * { return cells0 + ((size_t)((uint32_t)g * plane32 + (uint32_t)c) << rshift); };
 
     if (UPDATE) {
+        // the ants' positions and wall flags are requested before the absorb pass (which does not touch them): its queue
+        // counter is a round trip of its own, and nothing behind its barrier and stores would be moved up by the compiler
+        double x[APT], y[APT];
+        bool in_wall[APT];
+#pragma unroll
+        for (int k = 0; k < APT; ++k) {
+            const int64_t i = i0 + lac[k];
+            x[k] = p.x[i]; y[k] = p.y[i]; th[k] = p.theta[i];
+            in_wall[k] = (ANTS_ENV_WALLFLAG && a.use_flag) ? p.wall_hit[i] != 0 : false;
+            // what the later phases read, requested now (no registers held): the activations of the depositing owners,
+            // the ant state of the move
+            if (p.P > 0) { prefetch_l2(p.act + i); if (p.P > 1) prefetch_l2(p.act + p.EN + i); }
+            prefetch_l2(p.reward_state + i);
+            if (MOVE) { prefetch_l2(p.holding + i); prefetch_l2(p.mandibles + i); if (a.rot != nullptr) prefetch_l2(a.rot + i); }
+        }
         // ---- Anthill.update (anthill.py:41-46) for the cells queued by the previous move: nothing else in the update
         //      reads the food field
         for (int g = 0; g < n_env; ++g) {
@@ -258,25 +273,10 @@ k_env(const __grid_constant__ Params p, const EnvArgs a) {
         if (tid < n_env) p.absorb_count[env0 + tid] = 0u;
         // ---- Walls.update on ants (walls.py:24-28) + which rocks does an ant push (circle_obstacles.py:35-37)
         const int Gc = ((p.N + 31) / 32 + 31) / 32 * 32;               // ants per touch chunk (<= 32 chunks)
-        double x[APT], y[APT];
-        bool in_wall[APT];
-#pragma unroll
-        for (int k = 0; k < APT; ++k) {
-            const int64_t i = i0 + lac[k];
-            x[k] = p.x[i]; y[k] = p.y[i]; th[k] = p.theta[i];
-            // what the later phases read, requested now (no registers held): the activations of the depositing owners,
-            // the ant state of the move
-            if (p.P > 0) { prefetch_l2(p.act + i); if (p.P > 1) prefetch_l2(p.act + p.EN + i); }
-            prefetch_l2(p.reward_state + i);
-            if (MOVE) { prefetch_l2(p.holding + i); prefetch_l2(p.mandibles + i); if (a.rot != nullptr) prefetch_l2(a.rot + i); }
-        }
         // Walls.update (walls.py:24-25): the wall bit of the cell the ant stands on.  This is the ONE random DRAM sector of
         // the ant per iteration: unless a wall or a rock moves it, it is also the cell it deposits on and the cell whose
         // food the mandible rule reads (the move of the previous step only stored the occupancy stamp there).
-        if (ANTS_ENV_WALLFLAG && a.use_flag) {
-#pragma unroll
-            for (int k = 0; k < APT; ++k) in_wall[k] = p.wall_hit[i0 + lac[k]] != 0;
-        } else {
+        if (!(ANTS_ENV_WALLFLAG && a.use_flag)) {
 #pragma unroll
             for (int k = 0; k < APT; ++k)
                 in_wall[k] = ld_wall(p, rec_of(el[k], cidx(p, cell_of(x[k], W), cell_of(y[k], H))));

@@ -63,6 +63,9 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2 (2^-22 rela
 // 16-byte record load.  (Measured alternatives, all slower on the cfg4 shard: ld.global.L2::128B / L2::64B prefetch
 // sizes and the non-coherent path, 0.35 ms against 0.29 ms.)
 __device__ __forceinline__ uint4 ld_record16(const uint8_t *rp) { return *reinterpret_cast<const uint4 *>(rp); }
+// 8-byte record load.  (Cache policies measured on the cfg4 shard, 0.177 ms with the default: .cg (L2 only) 0.232,
+// L1::no_allocate 0.270, L1::evict_first 0.204, L1::evict_last 0.177 -- half of the gathers hit in L1.)
+__device__ __forceinline__ uint2 ld_record8(const uint8_t *rp) { return *reinterpret_cast<const uint2 *>(rp); }
 
 // value of a pheromone field that is neither zero nor a live boxed deposit outside walls (rare): kept out of line
 __device__ __noinline__ float phero_obs_slow(const Params &p, const uint8_t *rp, int k, uint32_t now, uint32_t now_abs) {
@@ -93,10 +96,11 @@ template <int LAYOUT, int REC, int S>      // REC: 0 = f64 records, 1 = compact 
 //   * L2 prefetch of the next chunk's records: 0.254 (4 samples per row) and 0.269 ms (all 7) against 0.240;
 //   * a second copy of the chunk loop for warps with all 32 ants (no ragged-end bookkeeping): 0.2248 against 0.2223;
 //   * 80 registers for 24 warps per SM (8 bytes of spills): 0.226 ms against 0.177;
-//   * shared memory / L1 split (ANTS_ROWS_CARVEOUT, profiles/r2_bench/perceive_carveout.txt): the driver's default puts
-//     the SM at 164 KB shared + 92 KB L1 with 16 resident warps, 0.177 ms; 196 / 228 KB shared (20 warps, <= 60 KB L1)
-//     0.221 ms; 132 KB (13 warps, 124 KB L1) 0.1815; 100 KB (10 warps) 0.204 -- the gathers need ~90 KB of L1, more
-//     warps than 16 do not pay for taking it away;
+//   * shared memory / L1 split (ANTS_ROWS_CARVEOUT, profiles/r2_bench/perceive_carveout.txt): 164 KB shared + 92 KB L1
+//     with 16 resident warps 0.177 ms; 196 / 228 KB shared (20 warps, <= 60 KB L1) 0.221 ms; 132 KB (13 warps, 124 KB
+//     L1) 0.1815; 100 KB (10 warps) 0.204 -- the gathers need ~90 KB of L1, more warps than 16 do not pay for taking it
+//     away.  ants_create asks for the 164 KB split (the driver's own choice follows the register count: it gave the
+//     80-register C = 6 kernel of cfg3 the 228 KB split, 0.205 ms against 0.154);
 //   * prep record cut to 64 bytes (the first rock's disc re-read from global memory in the rock path): 0.186 against
 //     0.177 at every split (perceive_carveout_prep64.txt);
 //   * 2 or 3 ants per thread in phases A / C (a warp serving 64 or 96 ants, the round trips of phase A paid once for all
@@ -304,7 +308,7 @@ k_perceive_rows(const __grid_constant__ Params p, float *__restrict__ obs, float
                     cell[u] = (uint32_t)((ix >> 3) * nby64m + ix * 8 + (iy >> 3) * 56 + iy);
                     const uint8_t *rp = cells + ((size_t)cell[u] << SH);
                     if (REC8) {                    // the whole cell in one 64-bit load, four cells per sector
-                        const uint2 v8 = *reinterpret_cast<const uint2 *>(rp);
+                        const uint2 v8 = ld_record8(rp);
                         lo[u] = make_uint4(v8.x, v8.y, 0u, 0u);
                     } else if (REC == 0 && eager_planes) {  // diffusion: the two pheromone values come from the row-major planes
                         const double *pv = plane0 + (int64_t)ix * p.Hp + iy;
