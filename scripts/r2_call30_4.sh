@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r2c30_bench4.json 2> gpurun_out/r2c30_bench4.err
+tail -1 gpurun_out/r2c30_bench4.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('4 GPUs', '%.4e'%d['value'], '%.4f'%d['ms_per_step'], 'late', d.get('late',{}).get('ms_per_step'), 'e2e %.3e'%d['e2e']['value'])"
