@@ -363,7 +363,7 @@ def run_ours(args):
                 "dram_frac": (traffic / (dom_ms_per_launch / 1000.0) / 1e9 / peak) if traffic else None,
                 "algorithmic_bytes_per_launch": abytes, "ms_per_launch": dom_ms_per_launch,
                 "note": "frac: algorithmic bytes = SURVEY.md 8-d (the reference's f64 fields at element granularity, f32 obs) "
-                        "/ event time / peak, i.e. how fast the reference's bytes are served; dram_frac: the DRAM bytes ncu "
+                        "/ event time / peak, i.e. how fast the reference's bytes are served (above 1 when the compact cell records carry them in fewer bytes than the survey counts); dram_frac: the DRAM bytes ncu "
                         "measured for this launch / event time / peak, i.e. how busy the HBM is (the 8-byte cell records "
                         "move far fewer bytes than the f64 planes)"}
     step_bytes = sum(algorithmic_bytes(f, wl, E, C, st) for f in kernels)
