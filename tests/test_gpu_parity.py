@@ -746,3 +746,15 @@ def test_grouped_rollout_crosses_generation_folds(monkeypatch):
     compare_state(b.export_state(), oracles, "after the grouped rollout", cfg)
     assert b.stats()["kernel_launches"] > 2 * T
     b.close()
+
+
+@pytest.mark.parametrize("record", ["compact8", "compact", "f64"])
+def test_row_kernel_5x5_window_with_rocks(record):
+    """The 5x5 window of the row-per-lane kernel (radius 2, S = 5) with rocks and the default channel list: the rock
+    channel of an ant a rock can reach is evaluated by the whole warp, 25 samples in one pass, and handed back to the
+    ant's five row lanes (ants_perceive_rows.cuh, rock_rows); RL_api.py:132-135."""
+    for seed in (501, 502):
+        scen = [make_scenario(seed=seed + 10 * e, w=48, h=40, n_ants=70, n_rocks=5, steps=14, radius=2, mask=None, fwd_delta=2)
+                for e in range(3)]
+        report = run_parity(scen, evap_mode="lazy", record=record)
+        assert report["state_checks"] == 14
